@@ -1,0 +1,149 @@
+/* ngan_b200 -- C ABI of the B200-native (sm_100a) kernels behind neuron-gan's progressive-growing WGAN-GP
+ * training step.  The shared library is libngan_b200.so (built in-tree by __graft_entry__.build()).
+ *
+ * The reference (oliviertrottier/neuron-gan) has no FFI / operator interface: its hot path is Python calling
+ * ATen operators.  Each entry point below therefore names the reference Python call
+ * site(s) (file:line in the reference tree) whose arithmetic it replaces.  The Python mirror of the reference
+ * interface (neuron_gan_b200/models.py, loss_functions.py, utils.py) calls these through ctypes; the same
+ * symbols can be bound from any language.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative NGAN_ERR_* code otherwise; ngan_last_error() returns a
+ *    thread-local message.  Nothing is allocated or freed on behalf of the caller, there are no hidden
+ *    synchronisations, every launch goes to the cudaStream_t passed as `stream` (void*).
+ *  - "c8" tensors are bf16 feature maps in C8-planar layout [B][C/8][H][W][8] (16-byte granules of 8 consecutive
+ *    channels); C must be a multiple of 16 for the conv kernels.  Images, scores, PixelNorm scales `r`
+ *    ([B][H][W]) and all parameters / gradients are fp32 in the reference's (torch) layouts.
+ *  - parameter-gradient outputs (gw, gb, dw, what) ACCUMULATE (+=); the caller zeroes them once per step.
+ *  - LeakyReLU + PixelNorm always come as a pair after a conv (models.py:261-268); "pn_bwd" below means
+ *    ga = mask(y) * r * (g - y * mean_c(g*y)), the gradient wrt the conv's pre-activation, computed from the
+ *    saved PixelNorm output y and scale r = (mean_c(h^2) + 1e-8)^-1/2 (models.py:118, 126).
+ */
+#ifndef NGAN_B200_H
+#define NGAN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGAN_OK 0
+#define NGAN_ERR_INVALID -1
+#define NGAN_ERR_CUDA -2
+#define NGAN_ERR_UNSUPPORTED -3
+
+int ngan_version(void);
+const char* ngan_last_error(void);
+
+/* ---- layout conversion at the boundary (torch NCHW fp32 <-> c8 bf16) ---- */
+int ngan_nchw_to_c8(const float* src, void* dst_c8, int B, int C, int H, int W, void* stream);
+int ngan_c8_to_nchw(const void* src_c8, float* dst, int B, int C, int H, int W, void* stream);
+
+/* ---- equalised-LR 3x3 convolution: Conv2d_normalized.forward, models.py:172-204 ---- */
+/* fp32 weight [cout][cin][3][3] -> bf16 UMMA operand images for the forward conv and for the data-gradient conv */
+int ngan_prep_conv_weight(const float* w, void* w_fwd, void* w_dgrad, int cin, int cout, void* stream);
+/* y = PixelNorm(LeakyReLU(scale*conv(x,W) + bias)), r = PixelNorm scale.  models.py:203-204 + 263-268 (+110-126) */
+int ngan_conv3x3_fwd(const void* x_c8, const void* w_fwd, const float* bias, float scale, float leak, void* y_c8,
+                     float* r, int B, int cin, int cout, int H, int W, void* stream);
+/* gx = scale * convT(ga, W): autograd's convolution_backward (input gradient) of models.py:204.  cin/cout are the
+ * LAYER's channel counts: ga has cout channels, gx has cin. */
+int ngan_conv3x3_dgrad(const void* ga_c8, const void* w_dgrad, float scale, void* gx_c8, int B, int cin, int cout,
+                       int H, int W, void* stream);
+/* same, with the pn_bwd of the producing layer fused: ga_prev = pn_bwd(gx; y_prev, r_prev) (+ addin).  gy_out
+ * (optional) receives gx itself, which the gradient-penalty double backward needs later. */
+int ngan_conv3x3_dgrad_pn(const void* ga_c8, const void* w_dgrad, float scale, float leak, const void* y_prev_c8,
+                          const float* r_prev, const void* addin_c8, void* ga_prev_c8, void* gy_out_c8, int B,
+                          int cin, int cout, int H, int W, void* stream);
+/* Double backward through conv + LeakyReLU + PixelNorm (the create_graph=True path of loss_functions.py:175):
+ * ghat_x is the cotangent on the layer's first-order input gradient; emits ghat_y (cotangent on the first-order
+ * gradient wrt this layer's output, i.e. the next layer's ghat_x) and ahat (cotangent injected at this layer's
+ * pre-activation for the second sweep).  y, r, gy are this layer's saved forward output / scale / first-order
+ * output gradient.  Formulas: SURVEY.md section 8a row 3. */
+int ngan_conv3x3_dbl(const void* ghat_x_c8, const void* w_fwd, float scale, float leak, const void* y_c8,
+                     const float* r, const void* gy_c8, void* ghat_y_c8, void* ahat_c8, int B, int cin, int cout,
+                     int H, int W, void* stream);
+/* dw[cout][cin][3][3] += scale * corr(x, ga): convolution_backward (weight gradient) of models.py:204 */
+int ngan_conv3x3_wgrad(const void* x_c8, const void* ga_c8, float scale, float* dw, int B, int cin, int cout, int H,
+                       int W, void* stream);
+/* gb[c] += sum_{b,y,x} ga: bias gradient of the biased 128->128 conv, models.py:469-471 */
+int ngan_bias_grad(const void* ga_c8, float* gb, int B, int C, int H, int W, void* stream);
+
+/* ---- resampling: Interpolate(x2, bilinear) models.py:78-89, 257; AvgPool2d(2) models.py:254 ---- */
+int ngan_upsample2x(const void* x_c8, void* out_c8, int B, int C, int H, int W, void* stream);
+int ngan_avgpool2(const void* x_c8, void* out_c8, int B, int C, int H, int W, void* stream);
+/* ga = pn_bwd(gscale * g) (+ addin); unpool != 0 reads g at (H/2, W/2) (adjoint of AvgPool2d(2); fold the 1/4
+ * into gscale).  gy_out (optional) receives gscale*g at full resolution. */
+int ngan_pn_bwd(const void* g_c8, int unpool, float gscale, const void* y_c8, const float* r, const void* addin_c8,
+                void* ga_c8, void* gy_out_c8, float leak, int B, int C, int H, int W, void* stream);
+/* adjoint of the bilinear x2 upsample fused with pn_bwd of the layer below it; extra_pre/extra_w add the
+ * faded-out ToImage branch's contribution extra_w[c]*extra_pre[b,y,x] (models.py:348).  H, W: low resolution. */
+int ngan_up2_bwd_pn_bwd(const void* g_up_c8, const void* y_c8, const float* r, const float* extra_pre,
+                        const float* extra_w, void* ga_c8, float leak, int B, int C, int H, int W, void* stream);
+
+/* ---- 1-channel fp32 image helpers (fade-in paths, models.py:335, 348, 507, 519; loss_functions.py:171) ---- */
+int ngan_pool_image(const float* x, float* out, int B, int H, int W, void* stream);
+int ngan_unpool_image(const float* g, float* out, float scale, int B, int H, int W, void* stream);
+int ngan_up2_image(const float* x, float* out, int B, int H, int W, void* stream);
+int ngan_up2_image_bwd(const float* g, float* out, float scale, int B, int H, int W, void* stream);
+int ngan_lerp(const float* a, const float* b, float alpha, float* out, long long n, void* stream);
+int ngan_axpby(const float* a, float ca, const float* b, float cb, float* out, long long n, void* stream);
+int ngan_interp_images(const float* real, const float* fake, const float* eps, float* out, int B,
+                       long long per_sample, void* stream);
+int ngan_scale_rows(const float* x, const float* coeff, float scale, float* out, int B, long long per_sample,
+                    void* stream);
+
+/* ---- FromImage / ToImage 1x1 convolutions, models.py:133-165 ---- */
+int ngan_fromim_fwd(const float* xp, const float* w, const float* b, void* out_c8, int B, int C, int H, int W,
+                    void* stream);
+/* discriminator fade-in, models.py:519-521: out = y_start + alpha*(y_end - y_start), y_start = FromIm_old(xp) */
+int ngan_d_fade_fwd(const void* y_end_c8, const float* xp, const float* w_old, const float* b_old, float alpha,
+                    void* out_c8, int B, int C, int H, int W, void* stream);
+int ngan_fromim_bwd(const void* g_c8, int unpool, float gscale, const float* xp, const float* w, float* gw, float* gb,
+                    float* g_img, int g_img_accumulate, int B, int C, int H, int W, void* stream);
+int ngan_fromim_dbl(const float* ghat_xp, float in_scale, const void* g_c8, int unpool, float gscale, const float* w,
+                    void* ghat_out_c8, float* what, int B, int C, int H, int W, void* stream);
+int ngan_toim_fwd(const void* y_c8, const float* w, float* img, int B, int C, int H, int W, void* stream);
+int ngan_toim_bwd(const float* g_img, float gscale, const float* img, const void* y_c8, const float* r,
+                  const float* w, void* ga_c8, float* gpre, float* gw, float leak, int B, int C, int H, int W,
+                  void* stream);
+
+/* ---- critic head: Conv2d_normalized(F -> 1, kernel S x S, pad 0) + Flatten, models.py:485-490 ---- */
+int ngan_head_fwd(const void* y_c8, const float* w, const float* bias, float scale, float* score, int B, int C,
+                  int S, void* stream);
+int ngan_head_bwd_pn(const float* gout, const float* w, float scale, const void* y_c8, const float* r, void* ga_c8,
+                     void* gy_out_c8, float leak, int B, int C, int S, void* stream);
+int ngan_head_wgrad(const void* t_c8, const float* coeff, float scale, float* gw, int B, int C, int S, void* stream);
+
+/* ---- generator stem: Linear_normalized + Unflatten + LeakyReLU + PixelNorm, models.py:299-311 ---- */
+int ngan_prep_linear_weight(const float* w, void* w_bf16, long long n, void* stream);
+int ngan_linear_fwd(const float* z, const void* w_bf16, float scale, float leak, void* y_c8, float* r, int B, int K,
+                    int C, int S, void* stream);
+int ngan_linear_wgrad(const void* ga_c8, const float* z, float scale, float* dw, int B, int K, int C, int S,
+                      void* stream);
+
+/* ---- WGAN-GP loss reductions, loss_functions.py:14-47, 59-74, 157-180 ---- */
+/* out3 = {D_loss, score_real, score_fake}; g_real/g_fake = d(gscale*D_loss)/d(score) per sample */
+int ngan_wloss(const float* s_real, const float* s_fake, float drift, float* out3, float* g_real, float* g_fake,
+               float gscale, int B, void* stream);
+int ngan_gloss(const float* s_fake, float* out1, float* g_fake, float gscale, int B, void* stream);
+/* pen = lambda*mean_b((norm_scale*||g_b|| - 1)^2); coeff_b = gscale * dpen/dnorm_b / norm_b */
+int ngan_gp_loss(const float* g, float norm_scale, float lambda, float* pen, float* coeff, float gscale, int B,
+                 long long per_sample, void* stream);
+
+/* ---- multi-tensor Adam, train.py:220-225 (torch.optim.Adam semantics, one step count per parameter) ---- */
+typedef struct {
+    float* p;            /* parameter, fp32, 16-byte aligned */
+    const float* g;      /* gradient */
+    float* m;            /* exp_avg */
+    float* v;            /* exp_avg_sq */
+    void* shadow_bf16;   /* optional bf16 copy of p refreshed in the same pass, or NULL */
+    long long n;
+    float step_size;     /* lr / (1 - beta1^t), t = this parameter's step count after the update */
+    float inv_bc2_sqrt;  /* 1 / sqrt(1 - beta2^t) */
+} ngan_adam_tensor;
+int ngan_adam_multi(const ngan_adam_tensor* tensors, int n_tensors, float beta1, float beta2, float eps,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGAN_B200_H */

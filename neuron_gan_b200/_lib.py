@@ -1,0 +1,70 @@
+"""ctypes binding of libngan_b200.so.  The prototypes are parsed from include/ngan_b200.h so the binding can
+never drift from the declared C ABI.  Loading fails loudly when the library has not been built."""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libngan_b200.so')
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'ngan_b200.h')
+
+_CTYPES = {'int': ctypes.c_int, 'float': ctypes.c_float, 'long long': ctypes.c_longlong}
+
+
+class AdamTensor(ctypes.Structure):
+    """Mirror of ngan_adam_tensor."""
+    _fields_ = [('p', ctypes.c_void_p), ('g', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p),
+                ('shadow_bf16', ctypes.c_void_p), ('n', ctypes.c_longlong), ('step_size', ctypes.c_float),
+                ('inv_bc2_sqrt', ctypes.c_float)]
+
+
+def parse_header(path=HEADER_PATH):
+    """Returns {name: (restype, [(ctype, argname), ...])} for every function declared in the header."""
+    src = open(path).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r'\b(int|const char\*)\s+(ngan_\w+)\s*\(([^)]*)\)\s*;', src):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        parsed = []
+        if args and args != 'void':
+            for a in args.split(','):
+                a = ' '.join(a.split())
+                if '*' in a:
+                    parsed.append((ctypes.c_void_p, a.split('*')[-1].strip()))
+                else:
+                    ty, nm = a.rsplit(' ', 1)
+                    parsed.append((_CTYPES[ty], nm))
+        protos[name] = (ctypes.c_char_p if ret != 'int' else ctypes.c_int, parsed)
+    return protos
+
+
+class NganError(RuntimeError):
+    pass
+
+
+_lib = None
+_protos = None
+
+
+def load():
+    global _lib, _protos
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                          '(neuron_gan_b200 has no CPU or PyTorch fallback)')
+    lib = ctypes.CDLL(LIB_PATH)
+    _protos = parse_header()
+    for name, (restype, args) in _protos.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
+        fn.restype = restype
+        fn.argtypes = [t for t, _ in args]
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise NganError(f'{name} failed ({rc}): {lib.ngan_last_error().decode()}')

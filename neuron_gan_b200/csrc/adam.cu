@@ -1,0 +1,96 @@
+// Multi-tensor Adam: one launch updates every active parameter of a network (reference train.py:220-225,
+// torch.optim.Adam(lr, betas=(beta1, 0.999)), eps 1e-8, no weight decay, no amsgrad):
+//   m = m + (1-b1)(g - m);  v = b2 v + (1-b2) g^2;  p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// Each parameter keeps its own step count t (torch skips parameters whose grad is None, so counts differ
+// between blocks that became active at different resolution phases); the two bias-correction scalars are
+// computed on the host in double precision, like torch does, and travel in the descriptor table, which is
+// passed by value in kernel-parameter space (no device-side table to maintain).
+// Optionally refreshes a bf16 shadow copy of the parameter in the same pass (the generator's linear weight).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ngan {
+
+constexpr int kAdamMaxTensors = 64;
+struct AdamEntry {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    __nv_bfloat16* shadow;
+    long long n;
+    float step_size;      // lr / (1 - beta1^t)
+    float inv_bc2_sqrt;   // 1 / sqrt(1 - beta2^t)
+};
+struct AdamTable {
+    AdamEntry e[kAdamMaxTensors];
+};
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ AdamTable tab, float beta1,
+                                                         float beta2, float eps) {
+    const AdamEntry& t = tab.e[blockIdx.y];
+    const long long n4 = t.n >> 2;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 p = reinterpret_cast<float4*>(t.p)[i];
+        const float4 g = __ldg(reinterpret_cast<const float4*>(t.g) + i);
+        float4 m = reinterpret_cast<float4*>(t.m)[i];
+        float4 v = reinterpret_cast<float4*>(t.v)[i];
+#define NGAN_ADAM1(c)                                                      \
+    m.c = m.c + (1.f - beta1) * (g.c - m.c);                               \
+    v.c = beta2 * v.c + (1.f - beta2) * g.c * g.c;                         \
+    p.c = p.c - t.step_size * (m.c / (sqrtf(v.c) * t.inv_bc2_sqrt + eps));
+        NGAN_ADAM1(x) NGAN_ADAM1(y) NGAN_ADAM1(z) NGAN_ADAM1(w)
+        reinterpret_cast<float4*>(t.p)[i] = p;
+        reinterpret_cast<float4*>(t.m)[i] = m;
+        reinterpret_cast<float4*>(t.v)[i] = v;
+        if (t.shadow) {
+            uint2 o;
+            o.x = pack_bf16(p.x, p.y);
+            o.y = pack_bf16(p.z, p.w);
+            reinterpret_cast<uint2*>(t.shadow)[i] = o;
+        }
+    }
+    // tail (n % 4 elements), handled by the first threads of block 0
+    if (blockIdx.x == 0) {
+        const long long i = (n4 << 2) + threadIdx.x;
+        if (i < t.n) {
+            const float g = t.g[i];
+            float m = t.m[i], v = t.v[i], p = t.p[i];
+            m = m + (1.f - beta1) * (g - m);
+            v = beta2 * v + (1.f - beta2) * g * g;
+            p = p - t.step_size * (m / (sqrtf(v) * t.inv_bc2_sqrt + eps));
+            t.p[i] = p; t.m[i] = m; t.v[i] = v;
+            if (t.shadow) t.shadow[i] = __float2bfloat16(p);
+        }
+    }
+#undef NGAN_ADAM1
+}
+
+int adam_multi_launch(const AdamEntry* entries, int n_tensors, float beta1, float beta2, float eps,
+                      cudaStream_t st) {
+    if (n_tensors <= 0) return NGAN_OK;
+    if (n_tensors > kAdamMaxTensors) {
+        set_error("adam_multi: %d tensors exceed the table size %d", n_tensors, kAdamMaxTensors);
+        return NGAN_ERR_INVALID;
+    }
+    AdamTable tab;
+    long long max_n = 0;
+    for (int i = 0; i < n_tensors; ++i) {
+        tab.e[i] = entries[i];
+        if (entries[i].n > max_n) max_n = entries[i].n;
+        if ((reinterpret_cast<uintptr_t>(entries[i].p) | reinterpret_cast<uintptr_t>(entries[i].g) |
+             reinterpret_cast<uintptr_t>(entries[i].m) | reinterpret_cast<uintptr_t>(entries[i].v)) & 15) {
+            set_error("adam_multi: tensor %d is not 16-byte aligned", i);
+            return NGAN_ERR_INVALID;
+        }
+    }
+    for (int i = n_tensors; i < kAdamMaxTensors; ++i) tab.e[i] = AdamEntry{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0.f};
+    long long bx = (max_n / 4 + 255) / 256;
+    if (bx > 148 * 8) bx = 148 * 8;
+    if (bx < 1) bx = 1;
+    adam_multi_kernel<<<dim3(static_cast<unsigned>(bx), n_tensors), 256, 0, st>>>(tab, beta1, beta2, eps);
+    return check_launch("adam_multi");
+}
+
+}  // namespace ngan

@@ -1,0 +1,834 @@
+// HBM-bound pointwise / per-pixel channel-reduction kernels of the PGGAN step (everything that is not a
+// 3x3 convolution): layout conversion, bilinear x2 / 2x2-mean resampling and their adjoints, PixelNorm +
+// LeakyReLU backward, FromImage / ToImage (1x1 convs, reference models.py:133-165) forward / backward /
+// double backward, fade-in blends (models.py:348-350, 519-521), the 16x16 critic head (models.py:485-490),
+// and the WGAN-GP loss reductions (loss_functions.py:14-47, 59-74, 157-180).
+//
+// All feature maps are C8-planar bf16 (common.cuh); one thread owns one pixel and walks the channel groups,
+// so a warp reads/writes 32 consecutive 16-byte granules (512 B, fully coalesced) per channel group and the
+// per-pixel channel reductions (PixelNorm statistics, 1x1 convs) are thread-local.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ngan {
+
+static inline int nblocks(size_t n, int threads) { return static_cast<int>((n + threads - 1) / threads); }
+
+// torch upsample_bilinear2d, scale 2, align_corners=False: source index / weight of output o (models.py:78-89)
+__device__ __forceinline__ void up2_src(int o, int n_in, int& i0, int& i1, float& l1) {
+    float s = (o + 0.5f) * 0.5f - 0.5f;
+    s = s < 0.f ? 0.f : s;
+    i0 = static_cast<int>(s);
+    l1 = s - i0;
+    i1 = i0 + 1 < n_in ? i0 + 1 : n_in - 1;
+}
+// weight with which input i contributes to output o (adjoint of the above)
+__device__ __forceinline__ float up2_adj_w(int o, int i, int n_in) {
+    if (o < 0 || o >= 2 * n_in) return 0.f;
+    int i0, i1;
+    float l1;
+    up2_src(o, n_in, i0, i1, l1);
+    return (i0 == i ? 1.f - l1 : 0.f) + (i1 == i ? l1 : 0.f);
+}
+
+// Sum 8 per-thread values over the warp and add them to smem[0..8) (one shared atomic per value per warp).
+__device__ __forceinline__ void warp_accum8(const float* v, float* smem8, int lane) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        float s = warp_sum(v[e]);
+        if (lane == 0) atomicAdd(smem8 + e, s);
+    }
+}
+
+// ------------------------------------------------------------------------------- layout conversion
+__global__ void nchw_to_c8_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int C, size_t HW,
+                                  size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t pix = i % HW;
+    const size_t bj = i / HW;  // b*(C/8) + j
+    const int nch = C / 8;
+    const size_t b = bj / nch, j = bj % nch;
+    const float* s = src + (b * C + j * 8) * HW + pix;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = s[e * HW];
+    dst[i] = pack8(f);
+}
+__global__ void c8_to_nchw_kernel(const uint4* __restrict__ src, float* __restrict__ dst, int C, size_t HW,
+                                  size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t pix = i % HW;
+    const size_t bj = i / HW;
+    const int nch = C / 8;
+    const size_t b = bj / nch, j = bj % nch;
+    float f[8];
+    unpack8(src[i], f);
+    float* d = dst + (b * C + j * 8) * HW + pix;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e * HW] = f[e];
+}
+int nchw_to_c8(const float* src, void* dst, int B, int C, int H, int W, cudaStream_t st) {
+    const size_t HW = static_cast<size_t>(H) * W, total = static_cast<size_t>(B) * (C / 8) * HW;
+    nchw_to_c8_kernel<<<nblocks(total, 256), 256, 0, st>>>(src, static_cast<uint4*>(dst), C, HW, total);
+    return check_launch("nchw_to_c8");
+}
+int c8_to_nchw(const void* src, float* dst, int B, int C, int H, int W, cudaStream_t st) {
+    const size_t HW = static_cast<size_t>(H) * W, total = static_cast<size_t>(B) * (C / 8) * HW;
+    c8_to_nchw_kernel<<<nblocks(total, 256), 256, 0, st>>>(static_cast<const uint4*>(src), dst, C, HW, total);
+    return check_launch("c8_to_nchw");
+}
+
+// ------------------------------------------------------------------------------- resampling (forward)
+__global__ void upsample2x_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int H, int W,
+                                     size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int OW = 2 * W, OH = 2 * H;
+    const int ox = static_cast<int>(i % OW);
+    const int oy = static_cast<int>((i / OW) % OH);
+    const size_t plane = i / (static_cast<size_t>(OW) * OH);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    up2_src(oy, H, y0, y1, ly);
+    up2_src(ox, W, x0, x1, lx);
+    const uint4* p = x + plane * H * W;
+    float a[8], b[8], c[8], d[8], o[8];
+    unpack8(__ldg(p + static_cast<size_t>(y0) * W + x0), a);
+    unpack8(__ldg(p + static_cast<size_t>(y0) * W + x1), b);
+    unpack8(__ldg(p + static_cast<size_t>(y1) * W + x0), c);
+    unpack8(__ldg(p + static_cast<size_t>(y1) * W + x1), d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        o[e] = (1.f - ly) * ((1.f - lx) * a[e] + lx * b[e]) + ly * ((1.f - lx) * c[e] + lx * d[e]);
+    out[i] = pack8(o);
+}
+int upsample2x_c8(const void* x, void* out, int B, int C, int H, int W, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * (C / 8) * H * W * 4;
+    upsample2x_c8_kernel<<<nblocks(total, 256), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out),
+                                                               H, W, total);
+    return check_launch("upsample2x_c8");
+}
+
+__global__ void avgpool2_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int H, int W, size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int OW = W / 2, OH = H / 2;
+    const int ox = static_cast<int>(i % OW);
+    const int oy = static_cast<int>((i / OW) % OH);
+    const size_t plane = i / (static_cast<size_t>(OW) * OH);
+    const uint4* p = x + plane * H * W + static_cast<size_t>(2 * oy) * W + 2 * ox;
+    float a[8], b[8], c[8], d[8], o[8];
+    unpack8(__ldg(p), a);
+    unpack8(__ldg(p + 1), b);
+    unpack8(__ldg(p + W), c);
+    unpack8(__ldg(p + W + 1), d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.25f * (a[e] + b[e] + c[e] + d[e]);
+    out[i] = pack8(o);
+}
+int avgpool2_c8(const void* x, void* out, int B, int C, int H, int W, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * (C / 8) * (H / 2) * (W / 2);
+    avgpool2_c8_kernel<<<nblocks(total, 256), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), H,
+                                                             W, total);
+    return check_launch("avgpool2_c8");
+}
+
+// ------------------------------------------------------------------------------- PixelNorm + LeakyReLU backward
+// ga = mask(y) * r * (g - y * mean_c(g*y)) + addin, g = gscale * G[(y,x) or (y/2,x/2)]   (SURVEY.md 8a row 3).
+// `unpool` reads G at half resolution: the adjoint of AvgPool2d(2) with the 1/4 folded into gscale by the caller.
+__global__ void pn_bwd_c8_kernel(const uint4* __restrict__ g, int unpool, float gscale, const uint4* __restrict__ y,
+                                 const float* __restrict__ r, const uint4* __restrict__ addin, uint4* __restrict__ ga,
+                                 uint4* __restrict__ gy_out, float leak, int C, int H, int W, size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t HW = static_cast<size_t>(H) * W;
+    const int px = static_cast<int>(i % W), py = static_cast<int>((i / W) % H);
+    const size_t b = i / HW;
+    const int nch = C / 8;
+    const size_t q0 = b * nch * HW + static_cast<size_t>(py) * W + px;
+    const size_t gHW = unpool ? HW / 4 : HW;
+    const size_t g0 = unpool ? b * nch * gHW + static_cast<size_t>(py >> 1) * (W >> 1) + (px >> 1) : q0;
+    float t = 0.f, gv[8], yv[8];
+    for (int j = 0; j < nch; ++j) {
+        unpack8(__ldg(g + g0 + j * gHW), gv);
+        unpack8(__ldg(y + q0 + j * HW), yv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t += gv[e] * yv[e];
+    }
+    t *= gscale / C;
+    const float rinv = r[i];
+    for (int j = 0; j < nch; ++j) {
+        unpack8(__ldg(g + g0 + j * gHW), gv);
+        unpack8(__ldg(y + q0 + j * HW), yv);
+        float o[8], ad[8];
+        if (addin) unpack8(__ldg(addin + q0 + j * HW), ad);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            gv[e] *= gscale;
+            o[e] = lrelu_mask(yv[e], leak) * rinv * (gv[e] - yv[e] * t) + (addin ? ad[e] : 0.f);
+        }
+        ga[q0 + j * HW] = pack8(o);
+        if (gy_out) gy_out[q0 + j * HW] = pack8(gv);
+    }
+}
+int pn_bwd_c8(const void* g, int unpool, float gscale, const void* y, const float* r, const void* addin, void* ga,
+              void* gy_out, float leak, int B, int C, int H, int W, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * H * W;
+    pn_bwd_c8_kernel<<<nblocks(total, 128), 128, 0, st>>>(
+        static_cast<const uint4*>(g), unpool, gscale, static_cast<const uint4*>(y), r,
+        static_cast<const uint4*>(addin), static_cast<uint4*>(ga), static_cast<uint4*>(gy_out), leak, C, H, W, total);
+    return check_launch("pn_bwd_c8");
+}
+
+// Adjoint of the bilinear x2 upsample fused with the PixelNorm/LeakyReLU backward of the layer that fed it.
+// g_up: [B][C/8][2H][2W][8]; y, r, ga at H x W.  extra_pre/extra_w: the faded-out ToImage branch adds
+// extra_w[c] * extra_pre[pixel] to the gradient wrt y (generator transition, models.py:348).
+template <int C>
+__global__ void up2_bwd_pn_bwd_kernel(const uint4* __restrict__ g_up, const uint4* __restrict__ y,
+                                      const float* __restrict__ r, const float* __restrict__ extra_pre,
+                                      const float* __restrict__ extra_w, uint4* __restrict__ ga, float leak, int H,
+                                      int W, size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    constexpr int NCH = C / 8;
+    const size_t HW = static_cast<size_t>(H) * W;
+    const int px = static_cast<int>(i % W), py = static_cast<int>((i / W) % H);
+    const size_t b = i / HW;
+    float wy[4], wx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        wy[k] = up2_adj_w(2 * py - 1 + k, py, H);
+        wx[k] = up2_adj_w(2 * px - 1 + k, px, W);
+    }
+    float g[C];
+    const size_t UW = 2 * static_cast<size_t>(W), UHW = 4 * HW;
+    const float ep = extra_pre ? extra_pre[i] : 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const uint4* p = g_up + (b * NCH + j) * UHW;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            if (wy[a] == 0.f) continue;
+            const size_t row = static_cast<size_t>(2 * py - 1 + a) * UW;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (wx[c] == 0.f) continue;
+                float v[8];
+                unpack8(__ldg(p + row + (2 * px - 1 + c)), v);
+                const float w = wy[a] * wx[c];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] += w * v[e];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[j * 8 + e] = acc[e] + (extra_pre ? extra_w[j * 8 + e] * ep : 0.f);
+    }
+    const size_t q0 = b * NCH * HW + static_cast<size_t>(py) * W + px;
+    float t = 0.f, yv[8];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        unpack8(__ldg(y + q0 + j * HW), yv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t += g[j * 8 + e] * yv[e];
+    }
+    t *= 1.0f / C;
+    const float rinv = r[i];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        unpack8(__ldg(y + q0 + j * HW), yv);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = lrelu_mask(yv[e], leak) * rinv * (g[j * 8 + e] - yv[e] * t);
+        ga[q0 + j * HW] = pack8(o);
+    }
+}
+int up2_bwd_pn_bwd_c8(const void* g_up, const void* y, const float* r, const float* extra_pre, const float* extra_w,
+                      void* ga, float leak, int B, int C, int H, int W, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * H * W;
+    const int blocks = nblocks(total, 128);
+#define NGAN_UP2B(CC)                                                                                           \
+    case CC:                                                                                                    \
+        up2_bwd_pn_bwd_kernel<CC><<<blocks, 128, 0, st>>>(static_cast<const uint4*>(g_up),                       \
+                                                          static_cast<const uint4*>(y), r, extra_pre, extra_w,  \
+                                                          static_cast<uint4*>(ga), leak, H, W, total);          \
+        break;
+    switch (C) {
+        NGAN_UP2B(16)
+        NGAN_UP2B(32)
+        NGAN_UP2B(64)
+        NGAN_UP2B(128)
+        default:
+            set_error("up2_bwd_pn_bwd: unsupported channel count %d", C);
+            return NGAN_ERR_UNSUPPORTED;
+    }
+#undef NGAN_UP2B
+    return check_launch("up2_bwd_pn_bwd");
+}
+
+// ------------------------------------------------------------------------------- 1-channel fp32 image ops
+__global__ void pool_image_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W, size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int OW = W / 2, OH = H / 2;
+    const int ox = static_cast<int>(i % OW), oy = static_cast<int>((i / OW) % OH);
+    const size_t b = i / (static_cast<size_t>(OW) * OH);
+    const float* p = x + b * H * W + static_cast<size_t>(2 * oy) * W + 2 * ox;
+    out[i] = 0.25f * (p[0] + p[1] + p[W] + p[W + 1]);
+}
+int pool_image(const float* x, float* out, int B, int H, int W, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * (H / 2) * (W / 2);
+    pool_image_kernel<<<nblocks(total, 256), 256, 0, st>>>(x, out, H, W, total);
+    return check_launch("pool_image");
+}
+// out[b, y, x] = scale * g[b, y/2, x/2]   (H, W are the OUTPUT dims)
+__global__ void unpool_image_kernel(const float* __restrict__ g, float* __restrict__ out, float scale, int H, int W,
+                                    size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = static_cast<int>(i % W), y = static_cast<int>((i / W) % H);
+    const size_t b = i / (static_cast<size_t>(W) * H);
+    out[i] = scale * g[b * (H / 2) * (W / 2) + static_cast<size_t>(y >> 1) * (W / 2) + (x >> 1)];
+}
+int unpool_image(const float* g, float* out, float scale, int B, int H, int W, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * H * W;
+    unpool_image_kernel<<<nblocks(total, 256), 256, 0, st>>>(g, out, scale, H, W, total);
+    return check_launch("unpool_image");
+}
+__global__ void up2_image_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W, size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int OW = 2 * W, OH = 2 * H;
+    const int ox = static_cast<int>(i % OW), oy = static_cast<int>((i / OW) % OH);
+    const size_t b = i / (static_cast<size_t>(OW) * OH);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    up2_src(oy, H, y0, y1, ly);
+    up2_src(ox, W, x0, x1, lx);
+    const float* p = x + b * H * W;
+    out[i] = (1.f - ly) * ((1.f - lx) * p[static_cast<size_t>(y0) * W + x0] + lx * p[static_cast<size_t>(y0) * W + x1]) +
+             ly * ((1.f - lx) * p[static_cast<size_t>(y1) * W + x0] + lx * p[static_cast<size_t>(y1) * W + x1]);
+}
+int up2_image(const float* x, float* out, int B, int H, int W, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * H * W * 4;
+    up2_image_kernel<<<nblocks(total, 256), 256, 0, st>>>(x, out, H, W, total);
+    return check_launch("up2_image");
+}
+// adjoint of up2_image: g is [B, 2H, 2W], out [B, H, W] = scale * U^T g
+__global__ void up2_image_bwd_kernel(const float* __restrict__ g, float* __restrict__ out, float scale, int H, int W,
+                                     size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int px = static_cast<int>(i % W), py = static_cast<int>((i / W) % H);
+    const size_t b = i / (static_cast<size_t>(W) * H);
+    const float* p = g + b * 4 * H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const float wy = up2_adj_w(2 * py - 1 + a, py, H);
+        if (wy == 0.f) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float wx = up2_adj_w(2 * px - 1 + c, px, W);
+            if (wx == 0.f) continue;
+            acc += wy * wx * p[static_cast<size_t>(2 * py - 1 + a) * (2 * W) + (2 * px - 1 + c)];
+        }
+    }
+    out[i] = scale * acc;
+}
+int up2_image_bwd(const float* g, float* out, float scale, int B, int H, int W, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * H * W;
+    up2_image_bwd_kernel<<<nblocks(total, 256), 256, 0, st>>>(g, out, scale, H, W, total);
+    return check_launch("up2_image_bwd");
+}
+__global__ void axpby_kernel(const float* __restrict__ a, float ca, const float* __restrict__ b, float cb,
+                             float* __restrict__ out, size_t n) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ca * a[i] + (b ? cb * b[i] : 0.f);
+}
+int axpby_f32(const float* a, float ca, const float* b, float cb, float* out, size_t n, cudaStream_t st) {
+    axpby_kernel<<<nblocks(n, 256), 256, 0, st>>>(a, ca, b, cb, out, n);
+    return check_launch("axpby_f32");
+}
+// a + alpha*(b - a): generator fade-in of the two ToImage branches (models.py:350)
+__global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha,
+                            float* __restrict__ out, size_t n) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + alpha * (b[i] - a[i]);
+}
+int lerp_f32(const float* a, const float* b, float alpha, float* out, size_t n, cudaStream_t st) {
+    lerp_kernel<<<nblocks(n, 256), 256, 0, st>>>(a, b, alpha, out, n);
+    return check_launch("lerp_f32");
+}
+// x_hat = eps_b * real + (1 - eps_b) * fake (loss_functions.py:171)
+__global__ void interp_kernel(const float* __restrict__ real, const float* __restrict__ fake,
+                              const float* __restrict__ eps, float* __restrict__ out, size_t per_sample, size_t n) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float e = eps[i / per_sample];
+    out[i] = e * real[i] + (1.f - e) * fake[i];
+}
+int interp_images(const float* real, const float* fake, const float* eps, float* out, int B, size_t per_sample,
+                  cudaStream_t st) {
+    const size_t n = static_cast<size_t>(B) * per_sample;
+    interp_kernel<<<nblocks(n, 256), 256, 0, st>>>(real, fake, eps, out, per_sample, n);
+    return check_launch("interp_images");
+}
+__global__ void scale_rows_kernel(const float* __restrict__ x, const float* __restrict__ coeff, float scale,
+                                  float* __restrict__ out, size_t per_sample, size_t n) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = scale * coeff[i / per_sample] * x[i];
+}
+int scale_rows_f32(const float* x, const float* coeff, float scale, float* out, int B, size_t per_sample,
+                   cudaStream_t st) {
+    const size_t n = static_cast<size_t>(B) * per_sample;
+    scale_rows_kernel<<<nblocks(n, 256), 256, 0, st>>>(x, coeff, scale, out, per_sample, n);
+    return check_launch("scale_rows_f32");
+}
+
+// ------------------------------------------------------------------------------- FromImage (models.py:156-165)
+// F[b, c, p] = w_c * xp[b, p] + b_c on the (already pooled, if the block pools) 1-channel image.
+__global__ void fromim_fwd_kernel(const float* __restrict__ xp, const float* __restrict__ w,
+                                  const float* __restrict__ bias, uint4* __restrict__ out, int C, size_t HW,
+                                  size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t b = i / HW, pix = i % HW;
+    const int nch = C / 8;
+    const float xv = xp[i];
+    for (int j = 0; j < nch; ++j) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __ldg(w + j * 8 + e) * xv + __ldg(bias + j * 8 + e);
+        out[(b * nch + j) * HW + pix] = pack8(o);
+    }
+}
+int fromim_fwd(const float* xp, const float* w, const float* b, void* out, int B, int C, int H, int W,
+               cudaStream_t st) {
+    const size_t HW = static_cast<size_t>(H) * W, total = B * HW;
+    fromim_fwd_kernel<<<nblocks(total, 256), 256, 0, st>>>(xp, w, b, static_cast<uint4*>(out), C, HW, total);
+    return check_launch("fromim_fwd");
+}
+// Discriminator fade-in (models.py:519-521): y = y_start + alpha*(y_end - y_start), y_start = FromIm_old(xp)
+__global__ void d_fade_fwd_kernel(const uint4* __restrict__ y_end, const float* __restrict__ xp,
+                                  const float* __restrict__ w, const float* __restrict__ bias, float alpha,
+                                  uint4* __restrict__ out, int C, size_t HW, size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t b = i / HW, pix = i % HW;
+    const int nch = C / 8;
+    const float xv = xp[i];
+    for (int j = 0; j < nch; ++j) {
+        float o[8], ye[8];
+        unpack8(__ldg(y_end + (b * nch + j) * HW + pix), ye);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float ys = __ldg(w + j * 8 + e) * xv + __ldg(bias + j * 8 + e);
+            o[e] = ys + alpha * (ye[e] - ys);
+        }
+        out[(b * nch + j) * HW + pix] = pack8(o);
+    }
+}
+int d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const float* b_old, float alpha, void* out,
+               int B, int C, int H, int W, cudaStream_t st) {
+    const size_t HW = static_cast<size_t>(H) * W, total = B * HW;
+    d_fade_fwd_kernel<<<nblocks(total, 256), 256, 0, st>>>(static_cast<const uint4*>(y_end), xp, w_old, b_old, alpha,
+                                                            static_cast<uint4*>(out), C, HW, total);
+    return check_launch("d_fade_fwd");
+}
+
+// Backward of FromImage: with G = gscale * g[(y,x) or (y/2,x/2)]:
+//   gw[c] += sum G_c * xp,  gb[c] += sum G_c,  g_img[b,p] (+)= sum_c w_c * G_c
+constexpr int kFromPix = 4;  // pixels per thread
+__global__ void fromim_bwd_kernel(const uint4* __restrict__ g, int unpool, float gscale, const float* __restrict__ xp,
+                                  const float* __restrict__ w, float* __restrict__ gw, float* __restrict__ gb,
+                                  float* __restrict__ g_img, int accumulate, int C, int H, int W, size_t total) {
+    extern __shared__ float sacc[];  // [2*C]: gw then gb
+    for (int k = threadIdx.x; k < 2 * C; k += blockDim.x) sacc[k] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t HW = static_cast<size_t>(H) * W;
+    const size_t gHW = unpool ? HW / 4 : HW;
+    const int nch = C / 8;
+    size_t pix[kFromPix], gq[kFromPix];
+    float xv[kFromPix], img[kFromPix];
+    bool ok[kFromPix];
+#pragma unroll
+    for (int p = 0; p < kFromPix; ++p) {
+        const size_t i = (static_cast<size_t>(blockIdx.x) * kFromPix + p) * blockDim.x + threadIdx.x;
+        ok[p] = i < total;
+        pix[p] = ok[p] ? i : 0;
+        const int px = static_cast<int>(pix[p] % W), py = static_cast<int>((pix[p] / W) % H);
+        const size_t b = pix[p] / HW;
+        gq[p] = unpool ? b * nch * gHW + static_cast<size_t>(py >> 1) * (W >> 1) + (px >> 1)
+                       : b * nch * HW + static_cast<size_t>(py) * W + px;
+        xv[p] = ok[p] ? xp[pix[p]] : 0.f;
+        img[p] = 0.f;
+    }
+    for (int j = 0; j < nch; ++j) {
+        float sw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int p = 0; p < kFromPix; ++p) {
+            if (!ok[p]) continue;
+            float gv[8];
+            unpack8(__ldg(g + gq[p] + j * gHW), gv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float G = gscale * gv[e];
+                sw[e] += G * xv[p];
+                sb[e] += G;
+                img[p] += __ldg(w + j * 8 + e) * G;
+            }
+        }
+        warp_accum8(sw, sacc + j * 8, lane);
+        warp_accum8(sb, sacc + C + j * 8, lane);
+    }
+    if (g_img) {
+#pragma unroll
+        for (int p = 0; p < kFromPix; ++p)
+            if (ok[p]) g_img[pix[p]] = (accumulate ? g_img[pix[p]] : 0.f) + img[p];
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < C; k += blockDim.x) {
+        if (gw) atomicAdd(gw + k, sacc[k]);
+        if (gb) atomicAdd(gb + k, sacc[C + k]);
+    }
+}
+int fromim_bwd(const void* g, int unpool, float gscale, const float* xp, const float* w, float* gw, float* gb,
+               float* g_img, int g_img_accumulate, int B, int C, int H, int W, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * H * W;
+    fromim_bwd_kernel<<<nblocks(total, 128 * kFromPix), 128, 2 * C * sizeof(float), st>>>(
+        static_cast<const uint4*>(g), unpool, gscale, xp, w, gw, gb, g_img, g_img_accumulate, C, H, W, total);
+    return check_launch("fromim_bwd");
+}
+// Double backward of FromImage's input-gradient: first order was g_xp = sum_c w_c * G_c.  With cotangent
+// X = in_scale * ghat_xp on g_xp:  ghat_out[c] = w_c * X (cotangent on G_c),  what[c] += sum X * G_c.
+__global__ void fromim_dbl_kernel(const float* __restrict__ ghat_xp, float in_scale, const uint4* __restrict__ g,
+                                  int unpool, float gscale, const float* __restrict__ w, uint4* __restrict__ ghat_out,
+                                  float* __restrict__ what, int C, int H, int W, size_t total) {
+    extern __shared__ float sacc[];  // [C]
+    for (int k = threadIdx.x; k < C; k += blockDim.x) sacc[k] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t HW = static_cast<size_t>(H) * W;
+    const size_t gHW = unpool ? HW / 4 : HW;
+    const int nch = C / 8;
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool ok = i < total;
+    const size_t ii = ok ? i : 0;
+    const int px = static_cast<int>(ii % W), py = static_cast<int>((ii / W) % H);
+    const size_t b = ii / HW;
+    const size_t q0 = b * nch * HW + static_cast<size_t>(py) * W + px;
+    const size_t g0 = unpool ? b * nch * gHW + static_cast<size_t>(py >> 1) * (W >> 1) + (px >> 1) : q0;
+    const float X = ok ? in_scale * ghat_xp[ii] : 0.f;
+    for (int j = 0; j < nch; ++j) {
+        float gv[8], o[8], sw[8];
+        unpack8(ok ? __ldg(g + g0 + j * gHW) : make_uint4(0, 0, 0, 0), gv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            o[e] = __ldg(w + j * 8 + e) * X;
+            sw[e] = X * gscale * gv[e];
+        }
+        if (ok && ghat_out) ghat_out[q0 + j * HW] = pack8(o);
+        warp_accum8(sw, sacc + j * 8, lane);
+    }
+    __syncthreads();
+    if (what)
+        for (int k = threadIdx.x; k < C; k += blockDim.x) atomicAdd(what + k, sacc[k]);
+}
+int fromim_dbl(const float* ghat_xp, float in_scale, const void* g, int unpool, float gscale, const float* w,
+               void* ghat_out, float* what, int B, int C, int H, int W, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * H * W;
+    fromim_dbl_kernel<<<nblocks(total, 128), 128, C * sizeof(float), st>>>(
+        ghat_xp, in_scale, static_cast<const uint4*>(g), unpool, gscale, w, static_cast<uint4*>(ghat_out), what, C, H,
+        W, total);
+    return check_launch("fromim_dbl");
+}
+
+// ------------------------------------------------------------------------------- ToImage (models.py:133-149)
+__global__ void toim_fwd_kernel(const uint4* __restrict__ y, const float* __restrict__ w, float* __restrict__ img,
+                                int C, size_t HW, size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t b = i / HW, pix = i % HW;
+    const int nch = C / 8;
+    float acc = 0.f;
+    for (int j = 0; j < nch; ++j) {
+        float yv[8];
+        unpack8(__ldg(y + (b * nch + j) * HW + pix), yv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc += __ldg(w + j * 8 + e) * yv[e];
+    }
+    img[i] = tanhf(acc);
+}
+int toim_fwd(const void* y, const float* w, float* img, int B, int C, int H, int W, cudaStream_t st) {
+    const size_t HW = static_cast<size_t>(H) * W, total = B * HW;
+    toim_fwd_kernel<<<nblocks(total, 256), 256, 0, st>>>(static_cast<const uint4*>(y), w, img, C, HW, total);
+    return check_launch("toim_fwd");
+}
+// Backward of tanh(conv1x1(y)): gpre = gscale*g_img*(1-img^2); gw[c] += sum gpre*y_c; gy_c = w_c*gpre, then
+// (if ga != null) the PixelNorm/LeakyReLU backward of the layer that produced y.
+__global__ void toim_bwd_kernel(const float* __restrict__ g_img, float gscale, const float* __restrict__ img,
+                                const uint4* __restrict__ y, const float* __restrict__ r, const float* __restrict__ w,
+                                uint4* __restrict__ ga, float* __restrict__ gpre_out, float* __restrict__ gw,
+                                float leak, int C, size_t HW, size_t total) {
+    extern __shared__ float sacc[];  // [C]
+    for (int k = threadIdx.x; k < C; k += blockDim.x) sacc[k] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool ok = i < total;
+    const size_t ii = ok ? i : 0;
+    const size_t b = ii / HW, pix = ii % HW;
+    const int nch = C / 8;
+    const float im = img[ii];
+    const float gpre = ok ? gscale * g_img[ii] * (1.f - im * im) : 0.f;
+    if (ok && gpre_out) gpre_out[ii] = gpre;
+    float t = 0.f;
+    for (int j = 0; j < nch; ++j) {
+        float yv[8], sw[8];
+        unpack8(__ldg(y + (b * nch + j) * HW + pix), yv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            sw[e] = gpre * yv[e];
+            t += __ldg(w + j * 8 + e) * yv[e];
+        }
+        warp_accum8(sw, sacc + j * 8, lane);
+    }
+    if (ga && ok) {
+        t *= gpre / C;
+        const float rinv = r[ii];
+        for (int j = 0; j < nch; ++j) {
+            float yv[8], o[8];
+            unpack8(__ldg(y + (b * nch + j) * HW + pix), yv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                o[e] = lrelu_mask(yv[e], leak) * rinv * (__ldg(w + j * 8 + e) * gpre - yv[e] * t);
+            ga[(b * nch + j) * HW + pix] = pack8(o);
+        }
+    }
+    __syncthreads();
+    if (gw)
+        for (int k = threadIdx.x; k < C; k += blockDim.x) atomicAdd(gw + k, sacc[k]);
+}
+int toim_bwd(const float* g_img, float gscale, const float* img, const void* y, const float* r, const float* w,
+             void* ga, float* gpre, float* gw, float leak, int B, int C, int H, int W, cudaStream_t st) {
+    const size_t HW = static_cast<size_t>(H) * W, total = B * HW;
+    toim_bwd_kernel<<<nblocks(total, 128), 128, C * sizeof(float), st>>>(
+        g_img, gscale, img, static_cast<const uint4*>(y), r, w, static_cast<uint4*>(ga), gpre, gw, leak, C, HW, total);
+    return check_launch("toim_bwd");
+}
+
+// ------------------------------------------------------------------------------- critic head (models.py:485-490)
+// score[b] = scale * sum_{c,p} w[c,p] * y[b,c,p] + bias, w in torch layout [1][C][S][S].
+__global__ void head_fwd_kernel(const uint4* __restrict__ y, const float* __restrict__ w,
+                                const float* __restrict__ bias, float scale, float* __restrict__ score, int C,
+                                int HW) {
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    const int nch = C / 8;
+    float acc = 0.f;
+    for (int k = threadIdx.x; k < nch * HW; k += blockDim.x) {
+        const int j = k / HW, pix = k % HW;
+        float yv[8];
+        unpack8(__ldg(y + static_cast<size_t>(b) * nch * HW + k), yv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc += __ldg(w + static_cast<size_t>(j * 8 + e) * HW + pix) * yv[e];
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) score[b] = scale * v + bias[0];
+    }
+}
+int head_fwd(const void* y, const float* w, const float* bias, float scale, float* score, int B, int C, int S,
+             cudaStream_t st) {
+    head_fwd_kernel<<<B, 256, 0, st>>>(static_cast<const uint4*>(y), w, bias, scale, score, C, S * S);
+    return check_launch("head_fwd");
+}
+// gy[b,c,p] = scale * w[c,p] * gout[b]; then PixelNorm/LeakyReLU backward of the layer that produced y.
+__global__ void head_bwd_pn_kernel(const float* __restrict__ gout, const float* __restrict__ w, float scale,
+                                   const uint4* __restrict__ y, const float* __restrict__ r, uint4* __restrict__ ga,
+                                   uint4* __restrict__ gy_out, float leak, int C, int HW, size_t total) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t b = i / HW;
+    const int pix = static_cast<int>(i % HW);
+    const int nch = C / 8;
+    const float go = scale * gout[b];
+    float t = 0.f;
+    for (int j = 0; j < nch; ++j) {
+        float yv[8];
+        unpack8(__ldg(y + (b * nch + j) * HW + pix), yv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t += __ldg(w + static_cast<size_t>(j * 8 + e) * HW + pix) * yv[e];
+    }
+    t *= go / C;
+    const float rinv = r[i];
+    for (int j = 0; j < nch; ++j) {
+        float yv[8], o[8], gv[8];
+        unpack8(__ldg(y + (b * nch + j) * HW + pix), yv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            gv[e] = go * __ldg(w + static_cast<size_t>(j * 8 + e) * HW + pix);
+            o[e] = lrelu_mask(yv[e], leak) * rinv * (gv[e] - yv[e] * t);
+        }
+        ga[(b * nch + j) * HW + pix] = pack8(o);
+        if (gy_out) gy_out[(b * nch + j) * HW + pix] = pack8(gv);
+    }
+}
+int head_bwd_pn(const float* gout, const float* w, float scale, const void* y, const float* r, void* ga,
+                void* gy_out, float leak, int B, int C, int S, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * S * S;
+    head_bwd_pn_kernel<<<nblocks(total, 128), 128, 0, st>>>(gout, w, scale, static_cast<const uint4*>(y), r,
+                                                             static_cast<uint4*>(ga), static_cast<uint4*>(gy_out),
+                                                             leak, C, S * S, total);
+    return check_launch("head_bwd_pn");
+}
+// gw[c,p] += scale * sum_b coeff[b] * t[b,c,p]: head weight gradient (t = y, coeff = gout) and its double-backward
+// twin (t = cotangent on gy, coeff = gout).
+__global__ void head_wgrad_kernel(const uint4* __restrict__ t, const float* __restrict__ coeff, float scale,
+                                  float* __restrict__ gw, int B, int C, int HW) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nch = C / 8;
+    if (k >= nch * HW) return;
+    const int j = k / HW, pix = k % HW;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < B; ++b) {
+        float tv[8];
+        unpack8(__ldg(t + static_cast<size_t>(b) * nch * HW + k), tv);
+        const float c = coeff[b];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += c * tv[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gw[static_cast<size_t>(j * 8 + e) * HW + pix] += scale * acc[e];
+}
+int head_wgrad(const void* t, const float* coeff, float scale, float* gw, int B, int C, int S, cudaStream_t st) {
+    const int n = (C / 8) * S * S;
+    head_wgrad_kernel<<<nblocks(n, 128), 128, 0, st>>>(static_cast<const uint4*>(t), coeff, scale, gw, B, C, S * S);
+    return check_launch("head_wgrad");
+}
+
+// gb[c] += sum over batch and pixels of ga[b,c,p]   (bias of the 128->128 conv, models.py:469-471)
+__global__ void bias_grad_c8_kernel(const uint4* __restrict__ ga, float* __restrict__ gb, int C, size_t HW,
+                                    size_t total) {
+    extern __shared__ float sacc[];
+    for (int k = threadIdx.x; k < C; k += blockDim.x) sacc[k] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool ok = i < total;
+    const size_t ii = ok ? i : 0;
+    const size_t b = ii / HW, pix = ii % HW;
+    const int nch = C / 8;
+    for (int j = 0; j < nch; ++j) {
+        float v[8];
+        unpack8(ok ? __ldg(ga + (b * nch + j) * HW + pix) : make_uint4(0, 0, 0, 0), v);
+        warp_accum8(v, sacc + j * 8, lane);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < C; k += blockDim.x) atomicAdd(gb + k, sacc[k]);
+}
+int bias_grad_c8(const void* ga, float* gb, int B, int C, int H, int W, cudaStream_t st) {
+    const size_t HW = static_cast<size_t>(H) * W, total = B * HW;
+    bias_grad_c8_kernel<<<nblocks(total, 256), 256, C * sizeof(float), st>>>(static_cast<const uint4*>(ga), gb, C, HW,
+                                                                             total);
+    return check_launch("bias_grad_c8");
+}
+
+// ------------------------------------------------------------------------------- loss reductions
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) s += red[k];
+    return s;
+}
+// D_W_loss (loss_functions.py:14-47): out3 = {D_loss, score_real, score_fake}; g_* = d(gscale*D_loss)/d score
+__global__ void wloss_kernel(const float* __restrict__ s_real, const float* __restrict__ s_fake, float drift,
+                             float* __restrict__ out3, float* __restrict__ g_real, float* __restrict__ g_fake,
+                             float gscale, int B) {
+    __shared__ float red[32];
+    float a = 0.f, f = 0.f, q = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        a += s_real[b];
+        f += s_fake[b];
+        q += s_real[b] * s_real[b];
+        if (g_real) g_real[b] = gscale * (-1.f + 2.f * drift * s_real[b]) / B;
+        if (g_fake) g_fake[b] = gscale / B;
+    }
+    a = block_sum(a, red);
+    f = block_sum(f, red);
+    q = block_sum(q, red);
+    if (threadIdx.x == 0) {
+        out3[1] = a / B;
+        out3[2] = f / B;
+        out3[0] = -a / B + f / B + drift * q / B;
+    }
+}
+int wloss_fwd(const float* s_real, const float* s_fake, float drift, float* out3, float* g_real, float* g_fake,
+              float gscale, int B, cudaStream_t st) {
+    wloss_kernel<<<1, 256, 0, st>>>(s_real, s_fake, drift, out3, g_real, g_fake, gscale, B);
+    return check_launch("wloss_fwd");
+}
+// G_W_loss (loss_functions.py:59-74)
+__global__ void gloss_kernel(const float* __restrict__ s_fake, float* __restrict__ out1, float* __restrict__ g_fake,
+                             float gscale, int B) {
+    __shared__ float red[32];
+    float f = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        f += s_fake[b];
+        if (g_fake) g_fake[b] = -gscale / B;
+    }
+    f = block_sum(f, red);
+    if (threadIdx.x == 0) out1[0] = -f / B;
+}
+int gloss_fwd(const float* s_fake, float* out1, float* g_fake, float gscale, int B, cudaStream_t st) {
+    gloss_kernel<<<1, 256, 0, st>>>(s_fake, out1, g_fake, gscale, B);
+    return check_launch("gloss_fwd");
+}
+// Gradient penalty (loss_functions.py:176): norm_b = norm_scale * ||g_b||_2, pen = lambda*mean((norm_b-1)^2),
+// coeff_b = gscale * d pen / d norm_b / norm_b  (so that d pen/d g_x = coeff_b * g_x).
+__global__ void gp_sumsq_kernel(const float* __restrict__ g, float* __restrict__ sumsq, size_t per_sample) {
+    __shared__ float red[32];
+    const int b = blockIdx.y;
+    const float* p = g + static_cast<size_t>(b) * per_sample;
+    float s = 0.f;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_sample;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        s += p[i] * p[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(sumsq + b, s);
+}
+__global__ void gp_finish_kernel(float* __restrict__ coeff /* in: sumsq */, float norm_scale, float lambda,
+                                 float* __restrict__ pen_out, float gscale, int B) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const float n = norm_scale * sqrtf(coeff[b]);
+        acc += (n - 1.f) * (n - 1.f);
+        coeff[b] = gscale * lambda * 2.f * (n - 1.f) / (B * n);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) pen_out[0] = lambda * acc / B;
+}
+int gp_loss(const float* g, float norm_scale, float lambda, float* pen_out, float* coeff_out, float gscale, int B,
+            size_t per_sample, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(coeff_out, 0, B * sizeof(float), st);
+    if (e != cudaSuccess) return check_cuda(e, "memset(gp)");
+    int bx = static_cast<int>((per_sample + 1023) / 1024);
+    if (bx > 64) bx = 64;
+    gp_sumsq_kernel<<<dim3(bx, B), 256, 0, st>>>(g, coeff_out, per_sample);
+    gp_finish_kernel<<<1, 256, 0, st>>>(coeff_out, norm_scale, lambda, pen_out, gscale, B);
+    return check_launch("gp_loss");
+}
+
+}  // namespace ngan

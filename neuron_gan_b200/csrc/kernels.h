@@ -1,0 +1,73 @@
+// Internal (C++) launcher declarations shared between the .cu files; the public C ABI is include/ngan_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ngan {
+
+enum ConvEpilogue { EPI_FWD_PN = 0, EPI_LINEAR = 1, EPI_BWD_PN = 2, EPI_DBL = 3 };
+
+// conv3x3_umma.cu
+int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, int cout, int H, int W, float scale,
+                     float leak, const float* bias, void* out0, void* out1, float* rout, const void* y,
+                     const float* r, const void* gy, const void* addin, cudaStream_t st);
+int prep_conv_weight(const float* w, void* fwd, void* dgrad, int cin, int cout, cudaStream_t st);
+
+// wgrad.cu
+int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int B, int cin, int cout, int H, int W,
+                  cudaStream_t st);
+
+// elementwise.cu
+int nchw_to_c8(const float* src, void* dst, int B, int C, int H, int W, cudaStream_t st);
+int c8_to_nchw(const void* src, float* dst, int B, int C, int H, int W, cudaStream_t st);
+int upsample2x_c8(const void* x, void* out, int B, int C, int H, int W, cudaStream_t st);
+int avgpool2_c8(const void* x, void* out, int B, int C, int H, int W, cudaStream_t st);
+int pn_bwd_c8(const void* g, int unpool, float gscale, const void* y, const float* r, const void* addin, void* ga,
+              void* gy_out, float leak, int B, int C, int H, int W, cudaStream_t st);
+int up2_bwd_pn_bwd_c8(const void* g_up, const void* y, const float* r, const float* extra_pre, const float* extra_w,
+                      void* ga, float leak, int B, int C, int H, int W, cudaStream_t st);
+int pool_image(const float* x, float* out, int B, int H, int W, cudaStream_t st);
+int unpool_image(const float* g, float* out, float scale, int B, int H, int W, cudaStream_t st);
+int up2_image(const float* x, float* out, int B, int H, int W, cudaStream_t st);
+int up2_image_bwd(const float* g, float* out, float scale, int B, int H, int W, cudaStream_t st);
+int lerp_f32(const float* a, const float* b, float alpha, float* out, size_t n, cudaStream_t st);
+int axpby_f32(const float* a, float ca, const float* b, float cb, float* out, size_t n, cudaStream_t st);
+int interp_images(const float* real, const float* fake, const float* eps, float* out, int B, size_t per_sample,
+                  cudaStream_t st);
+int fromim_fwd(const float* xp, const float* w, const float* b, void* out, int B, int C, int H, int W,
+               cudaStream_t st);
+int d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const float* b_old, float alpha, void* out,
+               int B, int C, int H, int W, cudaStream_t st);
+int fromim_bwd(const void* g, int unpool, float gscale, const float* xp, const float* w, float* gw, float* gb,
+               float* g_img, int g_img_accumulate, int B, int C, int H, int W, cudaStream_t st);
+int fromim_dbl(const float* ghat_xp, float in_scale, const void* g, int unpool, float gscale, const float* w,
+               void* ghat_out, float* what, int B, int C, int H, int W, cudaStream_t st);
+int toim_fwd(const void* y, const float* w, float* img, int B, int C, int H, int W, cudaStream_t st);
+int toim_bwd(const float* g_img, float gscale, const float* img, const void* y, const float* r, const float* w,
+             void* ga, float* gpre, float* gw, float leak, int B, int C, int H, int W, cudaStream_t st);
+int head_fwd(const void* y, const float* w, const float* bias, float scale, float* score, int B, int C, int S,
+             cudaStream_t st);
+int head_bwd_pn(const float* gout, const float* w, float scale, const void* y, const float* r, void* ga,
+                void* gy_out, float leak, int B, int C, int S, cudaStream_t st);
+int head_wgrad(const void* t, const float* coeff, float scale, float* gw, int B, int C, int S, cudaStream_t st);
+int bias_grad_c8(const void* ga, float* gb, int B, int C, int H, int W, cudaStream_t st);
+int wloss_fwd(const float* s_real, const float* s_fake, float drift, float* out3, float* g_real, float* g_fake,
+              float gscale, int B, cudaStream_t st);
+int gloss_fwd(const float* s_fake, float* out1, float* g_fake, float gscale, int B, cudaStream_t st);
+int gp_loss(const float* g, float norm_scale, float lambda, float* pen_out, float* coeff_out, float gscale, int B,
+            size_t per_sample, cudaStream_t st);
+int scale_rows_f32(const float* x, const float* coeff, float scale, float* out, int B, size_t per_sample,
+                   cudaStream_t st);
+
+// linear.cu
+int prep_linear_weight(const float* w, void* wb, size_t n, cudaStream_t st);
+int linear_fwd_pn(const float* z, const void* wb, float scale, float leak, void* y, float* r, int B, int K, int C,
+                  int S, cudaStream_t st);
+int linear_wgrad(const void* ga, const float* z, float scale, float* dw, int B, int K, int C, int S,
+                 cudaStream_t st);
+
+// adam.cu (AdamEntry has the layout of ngan_adam_tensor in include/ngan_b200.h)
+struct AdamEntry;
+int adam_multi_launch(const AdamEntry* entries, int n_tensors, float beta1, float beta2, float eps, cudaStream_t st);
+
+}  // namespace ngan

@@ -1,0 +1,200 @@
+// Weight gradient of the equalised-LR 3x3 convolution (what autograd's convolution_backward computes for
+// Conv2d_normalized, reference models.py:203-204), also used for the "wgrad of dgrad" term of the
+// gradient-penalty double backward:
+//     dW[co][ci][ky][kx] += scale * sum_{b,y,x} ga[b,co,y,x] * x[b,ci,y+ky-1,x+kx-1]
+//
+// GEMM view: M = co, N = ci (per tap), K = pixels.  COUT/CIN are as small as 16 here, below the M=64/128
+// granularity of tcgen05.mma, so this reduction runs on the warp-level tensor-core path (mma.sync
+// m16n8k16, bf16 -> fp32): every warp owns one 16(co) x 16(ci) x 9(tap) accumulator block in registers for
+// the whole kernel.  Operand tiles arrive by TMA (double-buffered, mbarrier-signalled) straight from the
+// C8-planar tensors; a C8 tile [pixel][8 channels] is the transpose of what mma wants, which is exactly what
+// ldmatrix.trans delivers, and the 9 taps are 9 shifted ldmatrix addresses into the same haloed x tile.
+// CTAs are persistent over pixel tiles (grid.x) and split the (co, ci) block space (grid.y); partial sums
+// are combined with fp32 atomics into the (pre-zeroed or accumulating) gradient tensor.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ngan {
+
+int make_c8_tensor_map(CUtensorMap* map, const void* base, int B, int C, int H, int W, int box_w, int box_h,
+                       int box_planes);
+
+struct WgradArgs {
+    int B, H, W, cin, cout;
+    int TW;               // tile width (multiple of 16); tile height is 8
+    int tiles_x, tiles_y, n_tiles;
+    int ci_g, co_g;       // channels of x / ga handled by one CTA
+    int n_ci_groups;
+    uint32_t x_stage_bytes, g_stage_bytes;
+    float scale;
+    float* dw;
+};
+
+constexpr int kWgTH = 8;
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                                  uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, "
+        "%2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                            const __grid_constant__ CUtensorMap tmap_g,
+                                                            const WgradArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    uint8_t* s_x[2] = {smem, smem + a.x_stage_bytes};
+    uint8_t* s_g[2] = {smem + 2 * a.x_stage_bytes, smem + 2 * a.x_stage_bytes + a.g_stage_bytes};
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * a.x_stage_bytes + 2 * a.g_stage_bytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = blockIdx.y;
+    const int ci_group = group % a.n_ci_groups, co_group = group / a.n_ci_groups;
+    const int n_ci_blk = a.ci_g / 16, n_co_blk = a.co_g / 16;
+    const int n_blk = n_ci_blk * n_co_blk;  // <= 8
+    const int rsplit = 8 / n_blk;
+    const int blk = warp % n_blk, rs = warp / n_blk;
+    const int cib = blk % n_ci_blk, cob = blk / n_ci_blk;
+
+    const int Wh = a.TW + 2;
+    const uint32_t x_plane = (kWgTH + 2) * Wh * 16, g_plane = kWgTH * a.TW * 16;
+    const uint32_t stage_bytes = (a.ci_g / 8) * x_plane + (a.co_g / 8) * g_plane;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_g);
+        mbar_init(bars + 0, 1);
+        mbar_init(bars + 1, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile, int stage) {
+        const int tx = tile % a.tiles_x;
+        const int ty = (tile / a.tiles_x) % a.tiles_y;
+        const int b = tile / (a.tiles_x * a.tiles_y);
+        mbar_arrive_expect_tx(bars + stage, stage_bytes);
+        tma_load_4d(s_x[stage], &tmap_x, bars + stage, (tx * a.TW - 1) * 2, ty * kWgTH - 1, ci_group * (a.ci_g / 8),
+                    b);
+        tma_load_4d(s_g[stage], &tmap_g, bars + stage, tx * a.TW * 2, ty * kWgTH, co_group * (a.co_g / 8), b);
+    };
+
+    float acc[9][2][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[t][n][k] = 0.f;
+
+    int it = 0;
+    if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < a.n_tiles) issue(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const int next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < a.n_tiles) issue(next, stage ^ 1);
+        mbar_wait(bars + stage, (it >> 1) & 1);
+
+        const uint32_t xb = smem_u32(s_x[stage]), gb = smem_u32(s_g[stage]);
+        // per-lane ldmatrix row addresses (matrix = lane/8, row = lane%8)
+        const int mi = lane >> 3, rowi = lane & 7;
+        // A (ga): matrix mi -> pixels +(mi/2)*8, co plane 2*cob + (mi%2)
+        const uint32_t a_lane = gb + (2 * cob + (mi & 1)) * g_plane + ((mi >> 1) * 8 + rowi) * 16;
+        // B (x):  matrix mi -> pixels +(mi%2)*8, ci plane 2*cib + (mi/2)
+        const uint32_t b_lane = xb + (2 * cib + (mi >> 1)) * x_plane + ((mi & 1) * 8 + rowi) * 16;
+
+        for (int r = rs; r < kWgTH; r += rsplit) {
+            for (int w0 = 0; w0 < a.TW; w0 += 16) {
+                uint32_t a0, a1, a2, a3;
+                ldmatrix_x4_trans(a_lane + (r * a.TW + w0) * 16, a0, a1, a2, a3);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap % 3;
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4_trans(b_lane + ((r + ky) * Wh + w0 + kx) * 16, b0, b1, b2, b3);
+                    mma_bf16_16816(acc[tap][0], a0, a1, a2, a3, b0, b1);
+                    mma_bf16_16816(acc[tap][1], a0, a1, a2, a3, b2, b3);
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with this stage before it is refilled two iterations later
+    }
+
+    // ---- flush: acc[tap][nb] = D[co = g (+8)][ci = nb*8 + 2t (+1)]
+    const int g = lane >> 2, t = lane & 3;
+    const int co0 = co_group * a.co_g + cob * 16, ci0 = ci_group * a.ci_g + cib * 16;
+    if (it > 0) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int co = co0 + g + (k >> 1) * 8;
+                    const int ci = ci0 + nb * 8 + 2 * t + (k & 1);
+                    atomicAdd(a.dw + (static_cast<size_t>(co) * a.cin + ci) * 9 + tap, a.scale * acc[tap][nb][k]);
+                }
+    }
+}
+
+int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int B, int cin, int cout, int H, int W,
+                  cudaStream_t st) {
+    if (cin % 16 || cout % 16 || H % kWgTH || W % 16) {
+        set_error("conv3x3_wgrad: unsupported shape cin=%d cout=%d H=%d W=%d", cin, cout, H, W);
+        return NGAN_ERR_UNSUPPORTED;
+    }
+    WgradArgs a;
+    a.B = B; a.H = H; a.W = W; a.cin = cin; a.cout = cout;
+    a.ci_g = cin < 64 ? cin : 64;
+    const int n_ci_blk = a.ci_g / 16;
+    int co_cap = 16 * (8 / n_ci_blk);
+    a.co_g = cout < co_cap ? cout : co_cap;
+    int n_blk = n_ci_blk * (a.co_g / 16);
+    if (8 % n_blk) {  // keep rsplit integral: shrink to a power-of-two block count
+        set_error("conv3x3_wgrad: block split %d does not divide 8", n_blk);
+        return NGAN_ERR_UNSUPPORTED;
+    }
+    a.n_ci_groups = cin / a.ci_g;
+    const int n_groups = a.n_ci_groups * (cout / a.co_g);
+    a.TW = W < 64 ? W : 64;
+    if (a.ci_g >= 64 && a.TW > 32) a.TW = 32;
+    a.tiles_x = W / a.TW;
+    a.tiles_y = H / kWgTH;
+    a.n_tiles = a.tiles_x * a.tiles_y * B;
+    const uint32_t x_plane = (kWgTH + 2) * (a.TW + 2) * 16, g_plane = kWgTH * a.TW * 16;
+    a.x_stage_bytes = ((a.ci_g / 8) * x_plane + 127) & ~127u;
+    a.g_stage_bytes = ((a.co_g / 8) * g_plane + 127) & ~127u;
+    a.scale = scale;
+    a.dw = dw;
+    const uint32_t smem_bytes = 2 * a.x_stage_bytes + 2 * a.g_stage_bytes + 16 + 128;
+
+    CUtensorMap tmx, tmg;
+    int rc = make_c8_tensor_map(&tmx, x, B, cin, H, W, a.TW + 2, kWgTH + 2, a.ci_g / 8);
+    if (rc) return rc;
+    rc = make_c8_tensor_map(&tmg, ga, B, cout, H, W, a.TW, kWgTH, a.co_g / 8);
+    if (rc) return rc;
+
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e =
+            cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(wgrad)");
+        configured = true;
+    }
+    int per_group = (2 * 148 + n_groups - 1) / n_groups;
+    if (per_group > a.n_tiles) per_group = a.n_tiles;
+    if (per_group < 1) per_group = 1;
+    conv3x3_wgrad_kernel<<<dim3(per_group, n_groups), 256, smem_bytes, st>>>(tmx, tmg, a);
+    return check_launch("conv3x3_wgrad");
+}
+
+}  // namespace ngan

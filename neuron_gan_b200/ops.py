@@ -1,0 +1,341 @@
+"""Tensor-level wrappers over the C ABI (include/ngan_b200.h).  torch is used for device memory and streams
+only: every function validates its tensors, takes raw device pointers and launches on the current stream.
+
+Feature maps are "c8" tensors: torch.bfloat16, shape [B, C//8, H, W, 8], contiguous (see csrc/common.cuh).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.NganError('neuron_gan_b200 kernels need CUDA tensors (there is no CPU fallback)')
+    if not t.is_contiguous():
+        raise _lib.NganError('non-contiguous tensor passed to a neuron_gan_b200 kernel')
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.NganError(f'expected {dtype}, got {t.dtype}')
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def c8_empty(B, C, H, W, device):
+    return torch.empty((B, C // 8, H, W, 8), dtype=BF16, device=device)
+
+
+def c8_dims(t):
+    B, nch, H, W, e = t.shape
+    assert e == 8 and t.dtype == BF16
+    return B, nch * 8, H, W
+
+
+# ------------------------------------------------------------------------------------------ layout
+def nchw_to_c8(x):
+    B, C, H, W = x.shape
+    out = c8_empty(B, C, H, W, x.device)
+    _lib.call('ngan_nchw_to_c8', _p(x, F32), _p(out), B, C, H, W, _stream())
+    return out
+
+
+def c8_to_nchw(x):
+    B, C, H, W = c8_dims(x)
+    out = torch.empty((B, C, H, W), dtype=F32, device=x.device)
+    _lib.call('ngan_c8_to_nchw', _p(x, BF16), _p(out), B, C, H, W, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ conv 3x3
+def prep_conv_weight(w, w_fwd=None, w_dgrad=None):
+    """w: fp32 [cout, cin, 3, 3] -> (fwd image, dgrad image), bf16 flat buffers of cout*cin*9 elements."""
+    cout, cin = w.shape[0], w.shape[1]
+    if w_fwd is None:
+        w_fwd = torch.empty(cout * cin * 9, dtype=BF16, device=w.device)
+    if w_dgrad is None:
+        w_dgrad = torch.empty(cout * cin * 9, dtype=BF16, device=w.device)
+    _lib.call('ngan_prep_conv_weight', _p(w, F32), _p(w_fwd, BF16), _p(w_dgrad, BF16), cin, cout, _stream())
+    return w_fwd, w_dgrad
+
+
+def conv3x3_fwd(x, w_fwd, bias, scale, leak, cout, want_r=True):
+    B, cin, H, W = c8_dims(x)
+    y = c8_empty(B, cout, H, W, x.device)
+    r = torch.empty((B, H, W), dtype=F32, device=x.device) if want_r else None
+    _lib.call('ngan_conv3x3_fwd', _p(x, BF16), _p(w_fwd, BF16), _p(bias, F32), scale, leak, _p(y), _p(r), B, cin,
+              cout, H, W, _stream())
+    return y, r
+
+
+def conv3x3_dgrad(ga, w_dgrad, scale, cin):
+    B, cout, H, W = c8_dims(ga)
+    gx = c8_empty(B, cin, H, W, ga.device)
+    _lib.call('ngan_conv3x3_dgrad', _p(ga, BF16), _p(w_dgrad, BF16), scale, _p(gx), B, cin, cout, H, W, _stream())
+    return gx
+
+
+def conv3x3_dgrad_pn(ga, w_dgrad, scale, leak, y_prev, r_prev, addin=None, want_gy=False):
+    B, cout, H, W = c8_dims(ga)
+    cin = c8_dims(y_prev)[1]
+    ga_prev = torch.empty_like(y_prev)
+    gy = torch.empty_like(y_prev) if want_gy else None
+    _lib.call('ngan_conv3x3_dgrad_pn', _p(ga, BF16), _p(w_dgrad, BF16), scale, leak, _p(y_prev, BF16),
+              _p(r_prev, F32), _p(addin, BF16) if addin is not None else None, _p(ga_prev), _p(gy), B, cin, cout, H,
+              W, _stream())
+    return ga_prev, gy
+
+
+def conv3x3_dbl(ghat_x, w_fwd, scale, leak, y, r, gy):
+    B, cin, H, W = c8_dims(ghat_x)
+    cout = c8_dims(y)[1]
+    ghat_y = torch.empty_like(y)
+    ahat = torch.empty_like(y)
+    _lib.call('ngan_conv3x3_dbl', _p(ghat_x, BF16), _p(w_fwd, BF16), scale, leak, _p(y, BF16), _p(r, F32),
+              _p(gy, BF16), _p(ghat_y), _p(ahat), B, cin, cout, H, W, _stream())
+    return ghat_y, ahat
+
+
+def conv3x3_wgrad(x, ga, scale, dw):
+    """dw (fp32 [cout, cin, 3, 3]) += scale * corr(x, ga)"""
+    B, cin, H, W = c8_dims(x)
+    cout = c8_dims(ga)[1]
+    assert dw.numel() == cout * cin * 9
+    _lib.call('ngan_conv3x3_wgrad', _p(x, BF16), _p(ga, BF16), scale, _p(dw, F32), B, cin, cout, H, W, _stream())
+
+
+def bias_grad(ga, gb):
+    B, C, H, W = c8_dims(ga)
+    _lib.call('ngan_bias_grad', _p(ga, BF16), _p(gb, F32), B, C, H, W, _stream())
+
+
+# ------------------------------------------------------------------------------------------ resampling
+def upsample2x(x):
+    B, C, H, W = c8_dims(x)
+    out = c8_empty(B, C, 2 * H, 2 * W, x.device)
+    _lib.call('ngan_upsample2x', _p(x, BF16), _p(out), B, C, H, W, _stream())
+    return out
+
+
+def avgpool2(x):
+    B, C, H, W = c8_dims(x)
+    out = c8_empty(B, C, H // 2, W // 2, x.device)
+    _lib.call('ngan_avgpool2', _p(x, BF16), _p(out), B, C, H, W, _stream())
+    return out
+
+
+def pn_bwd(g, y, r, gscale=1.0, unpool=False, addin=None, want_gy=False, leak=0.2):
+    B, C, H, W = c8_dims(y)
+    ga = torch.empty_like(y)
+    gy = torch.empty_like(y) if want_gy else None
+    _lib.call('ngan_pn_bwd', _p(g, BF16), int(unpool), gscale, _p(y, BF16), _p(r, F32),
+              _p(addin, BF16) if addin is not None else None, _p(ga), _p(gy), leak, B, C, H, W, _stream())
+    return ga, gy
+
+
+def up2_bwd_pn_bwd(g_up, y, r, extra_pre=None, extra_w=None, leak=0.2):
+    B, C, H, W = c8_dims(y)
+    ga = torch.empty_like(y)
+    _lib.call('ngan_up2_bwd_pn_bwd', _p(g_up, BF16), _p(y, BF16), _p(r, F32), _p(extra_pre, F32), _p(extra_w, F32),
+              _p(ga), leak, B, C, H, W, _stream())
+    return ga
+
+
+# ------------------------------------------------------------------------------------------ 1-channel images
+def pool_image(x):
+    B, H, W = x.shape[0], x.shape[-2], x.shape[-1]
+    out = torch.empty((B, H // 2, W // 2), dtype=F32, device=x.device)
+    _lib.call('ngan_pool_image', _p(x, F32), _p(out), B, H, W, _stream())
+    return out
+
+
+def unpool_image(g, scale):
+    B, h, w = g.shape
+    out = torch.empty((B, 2 * h, 2 * w), dtype=F32, device=g.device)
+    _lib.call('ngan_unpool_image', _p(g, F32), _p(out), scale, B, 2 * h, 2 * w, _stream())
+    return out
+
+
+def up2_image(x):
+    B, H, W = x.shape
+    out = torch.empty((B, 2 * H, 2 * W), dtype=F32, device=x.device)
+    _lib.call('ngan_up2_image', _p(x, F32), _p(out), B, H, W, _stream())
+    return out
+
+
+def up2_image_bwd(g, scale=1.0):
+    B, H2, W2 = g.shape
+    out = torch.empty((B, H2 // 2, W2 // 2), dtype=F32, device=g.device)
+    _lib.call('ngan_up2_image_bwd', _p(g, F32), _p(out), scale, B, H2 // 2, W2 // 2, _stream())
+    return out
+
+
+def lerp(a, b, alpha):
+    out = torch.empty_like(a)
+    _lib.call('ngan_lerp', _p(a, F32), _p(b, F32), alpha, _p(out), a.numel(), _stream())
+    return out
+
+
+def axpby(a, ca, b=None, cb=0.0, out=None):
+    out = torch.empty_like(a) if out is None else out
+    _lib.call('ngan_axpby', _p(a, F32), ca, _p(b, F32), cb, _p(out), a.numel(), _stream())
+    return out
+
+
+def interp_images(real, fake, eps):
+    out = torch.empty_like(real)
+    B = real.shape[0]
+    _lib.call('ngan_interp_images', _p(real, F32), _p(fake, F32), _p(eps, F32), _p(out), B, real.numel() // B,
+              _stream())
+    return out
+
+
+def scale_rows(x, coeff, scale=1.0):
+    out = torch.empty_like(x)
+    B = x.shape[0]
+    _lib.call('ngan_scale_rows', _p(x, F32), _p(coeff, F32), scale, _p(out), B, x.numel() // B, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ FromImage / ToImage
+def fromim_fwd(xp, w, b):
+    B, H, W = xp.shape
+    C = w.numel()
+    out = c8_empty(B, C, H, W, xp.device)
+    _lib.call('ngan_fromim_fwd', _p(xp, F32), _p(w, F32), _p(b, F32), _p(out), B, C, H, W, _stream())
+    return out
+
+
+def d_fade_fwd(y_end, xp, w_old, b_old, alpha):
+    B, C, H, W = c8_dims(y_end)
+    out = torch.empty_like(y_end)
+    _lib.call('ngan_d_fade_fwd', _p(y_end, BF16), _p(xp, F32), _p(w_old, F32), _p(b_old, F32), alpha, _p(out), B, C,
+              H, W, _stream())
+    return out
+
+
+def fromim_bwd(g, xp, w, gw, gb, gscale=1.0, unpool=False, g_img=None, accumulate=False):
+    B, H, W = xp.shape
+    C = w.numel()
+    _lib.call('ngan_fromim_bwd', _p(g, BF16), int(unpool), gscale, _p(xp, F32), _p(w, F32), _p(gw, F32), _p(gb, F32),
+              _p(g_img, F32), int(accumulate), B, C, H, W, _stream())
+
+
+def fromim_dbl(ghat_xp, g, w, what, in_scale=1.0, gscale=1.0, unpool=False, want_out=True):
+    B, H, W = ghat_xp.shape
+    C = w.numel()
+    out = c8_empty(B, C, H, W, ghat_xp.device) if want_out else None
+    _lib.call('ngan_fromim_dbl', _p(ghat_xp, F32), in_scale, _p(g, BF16), int(unpool), gscale, _p(w, F32), _p(out),
+              _p(what, F32), B, C, H, W, _stream())
+    return out
+
+
+def toim_fwd(y, w):
+    B, C, H, W = c8_dims(y)
+    img = torch.empty((B, H, W), dtype=F32, device=y.device)
+    _lib.call('ngan_toim_fwd', _p(y, BF16), _p(w, F32), _p(img), B, C, H, W, _stream())
+    return img
+
+
+def toim_bwd(g_img, img, y, r, w, gw, gscale=1.0, want_ga=True, want_gpre=False, leak=0.2):
+    B, C, H, W = c8_dims(y)
+    ga = torch.empty_like(y) if want_ga else None
+    gpre = torch.empty((B, H, W), dtype=F32, device=y.device) if want_gpre else None
+    _lib.call('ngan_toim_bwd', _p(g_img, F32), gscale, _p(img, F32), _p(y, BF16), _p(r, F32), _p(w, F32), _p(ga),
+              _p(gpre), _p(gw, F32), leak, B, C, H, W, _stream())
+    return ga, gpre
+
+
+# ------------------------------------------------------------------------------------------ critic head
+def head_fwd(y, w, bias, scale):
+    B, C, H, W = c8_dims(y)
+    score = torch.empty((B,), dtype=F32, device=y.device)
+    _lib.call('ngan_head_fwd', _p(y, BF16), _p(w, F32), _p(bias, F32), scale, _p(score), B, C, H, _stream())
+    return score
+
+
+def head_bwd_pn(gout, w, scale, y, r, want_gy=False, leak=0.2):
+    B, C, H, W = c8_dims(y)
+    ga = torch.empty_like(y)
+    gy = torch.empty_like(y) if want_gy else None
+    _lib.call('ngan_head_bwd_pn', _p(gout, F32), _p(w, F32), scale, _p(y, BF16), _p(r, F32), _p(ga), _p(gy), leak, B,
+              C, H, _stream())
+    return ga, gy
+
+
+def head_wgrad(t, coeff, scale, gw):
+    B, C, H, W = c8_dims(t)
+    _lib.call('ngan_head_wgrad', _p(t, BF16), _p(coeff, F32), scale, _p(gw, F32), B, C, H, _stream())
+
+
+# ------------------------------------------------------------------------------------------ generator stem
+def prep_linear_weight(w, out=None):
+    out = torch.empty(w.shape, dtype=BF16, device=w.device) if out is None else out
+    _lib.call('ngan_prep_linear_weight', _p(w, F32), _p(out, BF16), w.numel(), _stream())
+    return out
+
+
+def linear_fwd(z, w_bf16, scale, leak, C, S, want_r=True):
+    B, K = z.shape
+    y = c8_empty(B, C, S, S, z.device)
+    r = torch.empty((B, S, S), dtype=F32, device=z.device) if want_r else None
+    _lib.call('ngan_linear_fwd', _p(z, F32), _p(w_bf16, BF16), scale, leak, _p(y), _p(r), B, K, C, S, _stream())
+    return y, r
+
+
+def linear_wgrad(ga, z, scale, dw):
+    B, C, S, _ = c8_dims(ga)
+    _lib.call('ngan_linear_wgrad', _p(ga, BF16), _p(z, F32), scale, _p(dw, F32), B, z.shape[1], C, S, _stream())
+
+
+# ------------------------------------------------------------------------------------------ losses
+def wloss(s_real, s_fake, drift, gscale=1.0, want_grads=True):
+    B = s_real.numel()
+    out3 = torch.empty(3, dtype=F32, device=s_real.device)
+    g_real = torch.empty(B, dtype=F32, device=s_real.device) if want_grads else None
+    g_fake = torch.empty(B, dtype=F32, device=s_real.device) if want_grads else None
+    _lib.call('ngan_wloss', _p(s_real, F32), _p(s_fake, F32), drift, _p(out3), _p(g_real), _p(g_fake), gscale, B,
+              _stream())
+    return out3, g_real, g_fake
+
+
+def gloss(s_fake, gscale=1.0, want_grads=True):
+    B = s_fake.numel()
+    out1 = torch.empty(1, dtype=F32, device=s_fake.device)
+    g_fake = torch.empty(B, dtype=F32, device=s_fake.device) if want_grads else None
+    _lib.call('ngan_gloss', _p(s_fake, F32), _p(out1), _p(g_fake), gscale, B, _stream())
+    return out1, g_fake
+
+
+def gp_loss(g, norm_scale, lam, gscale=1.0):
+    B = g.shape[0]
+    pen = torch.empty(1, dtype=F32, device=g.device)
+    coeff = torch.empty(B, dtype=F32, device=g.device)
+    _lib.call('ngan_gp_loss', _p(g, F32), norm_scale, lam, _p(pen), _p(coeff), gscale, B, g.numel() // B, _stream())
+    return pen, coeff
+
+
+# ------------------------------------------------------------------------------------------ Adam
+def adam_multi(entries, beta1, beta2, eps):
+    """entries: list of dicts(p, g, m, v, shadow|None, step_size, inv_bc2_sqrt)"""
+    n = len(entries)
+    if n == 0:
+        return
+    arr = (_lib.AdamTensor * n)()
+    for i, e in enumerate(entries):
+        arr[i].p = e['p'].data_ptr()
+        arr[i].g = e['g'].data_ptr()
+        arr[i].m = e['m'].data_ptr()
+        arr[i].v = e['v'].data_ptr()
+        arr[i].shadow_bf16 = e['shadow'].data_ptr() if e.get('shadow') is not None else None
+        arr[i].n = e['p'].numel()
+        arr[i].step_size = e['step_size']
+        arr[i].inv_bc2_sqrt = e['inv_bc2_sqrt']
+    _lib.call('ngan_adam_multi', ctypes.cast(arr, ctypes.c_void_p), n, beta1, beta2, eps, _stream())

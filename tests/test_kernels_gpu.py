@@ -1,0 +1,313 @@
+"""Per-kernel parity on the B200: every C-ABI entry point against a plain PyTorch fp32 reference of the same
+op on identical (bf16-rounded) inputs.  Tolerance: relative L2 <= 1e-2 for bf16 outputs,
+tighter for fp32 outputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+LEAK = 0.2
+GAIN = math.sqrt(2.0 / (1.0 + LEAK * LEAK))
+
+
+def ops():
+    from neuron_gan_b200 import ops as o
+    return o
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20)).item()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    return bf(torch.randn(*shape, device='cuda', generator=g) * scale)
+
+
+def pn_ref(h):
+    r = torch.rsqrt((h * h).mean(1, keepdim=True) + 1e-8)
+    return h * r, r
+
+
+CONV_SHAPES = [  # B, cin, cout, H, W
+    (2, 16, 16, 16, 16), (1, 16, 16, 64, 64), (2, 16, 32, 32, 32), (2, 32, 16, 32, 32), (1, 32, 32, 128, 128),
+    (2, 32, 64, 32, 32), (2, 64, 32, 32, 32), (2, 64, 64, 32, 32), (2, 64, 128, 16, 16), (2, 128, 64, 32, 32),
+    (3, 128, 128, 16, 16), (1, 16, 16, 256, 256), (1, 16, 16, 40, 72),
+]
+
+
+def test_layout_roundtrip():
+    o = ops()
+    x = rnd(2, 32, 8, 12)
+    c8 = o.nchw_to_c8(x)
+    assert c8.shape == (2, 4, 8, 12, 8)
+    assert torch.equal(c8.float().permute(0, 1, 4, 2, 3).reshape(2, 32, 8, 12), x)
+    assert torch.equal(o.c8_to_nchw(c8), x)
+
+
+@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES)
+@pytest.mark.parametrize('use_bias', [False, True])
+def test_conv3x3_fwd(B, cin, cout, H, W, use_bias):
+    o = ops()
+    x = rnd(B, cin, H, W, seed=1)
+    w = rnd(cout, cin, 3, 3, seed=2, scale=GAIN / math.sqrt(cin * 9))
+    bias = rnd(cout, seed=3, scale=0.1) if use_bias else None
+    s = GAIN / math.sqrt(cin * 9)
+    h = F.leaky_relu(F.conv2d(s * x, w, bias, padding=1), LEAK)
+    y_ref, r_ref = pn_ref(h)
+    w_fwd, _ = o.prep_conv_weight(w)
+    y, r = o.conv3x3_fwd(o.nchw_to_c8(x), w_fwd, bias, s, LEAK, cout)
+    torch.cuda.synchronize()
+    assert rel(o.c8_to_nchw(y), y_ref) < 6e-3
+    assert rel(r, r_ref[:, 0]) < 2e-3
+
+
+@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES)
+def test_conv3x3_dgrad_and_pn(B, cin, cout, H, W):
+    o = ops()
+    ga = rnd(B, cout, H, W, seed=4)
+    w = rnd(cout, cin, 3, 3, seed=5, scale=GAIN / math.sqrt(cin * 9))
+    s = GAIN / math.sqrt(cin * 9)
+    gx_ref = s * F.conv_transpose2d(ga, w, padding=1)
+    _, w_dg = o.prep_conv_weight(w)
+    gx = o.conv3x3_dgrad(o.nchw_to_c8(ga), w_dg, s, cin)
+    assert rel(o.c8_to_nchw(gx), gx_ref) < 6e-3
+    # fused PixelNorm/LeakyReLU backward of the producing layer
+    h = rnd(B, cin, H, W, seed=6)
+    y_prev, r_prev = pn_ref(F.leaky_relu(h, LEAK))
+    y_prev = bf(y_prev)
+    addin = rnd(B, cin, H, W, seed=7, scale=0.1)
+    mask = torch.where(y_prev > 0, 1.0, LEAK)
+    ga_prev_ref = mask * r_prev * (gx_ref - y_prev * (gx_ref * y_prev).mean(1, keepdim=True)) + addin
+    ga_prev, gy = o.conv3x3_dgrad_pn(o.nchw_to_c8(ga), w_dg, s, LEAK, o.nchw_to_c8(y_prev),
+                                     r_prev[:, 0].contiguous(), addin=o.nchw_to_c8(addin), want_gy=True)
+    assert rel(o.c8_to_nchw(ga_prev), ga_prev_ref) < 8e-3
+    assert rel(o.c8_to_nchw(gy), gx_ref) < 6e-3
+
+
+@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES[:11])
+def test_conv3x3_double_backward(B, cin, cout, H, W):
+    """conv3x3_dbl against autograd's double backward of conv -> LeakyReLU -> PixelNorm."""
+    o = ops()
+    s = GAIN / math.sqrt(cin * 9)
+    w = rnd(cout, cin, 3, 3, seed=8, scale=GAIN / math.sqrt(cin * 9))
+    x = rnd(B, cin, H, W, seed=9)
+    a = (s * F.conv2d(x, w, padding=1)).detach().requires_grad_()
+    h = F.leaky_relu(a, LEAK)
+    r = torch.rsqrt((h * h).mean(1, keepdim=True) + 1e-8)
+    y = h * r
+    gy = rnd(B, cout, H, W, seed=10).requires_grad_()
+    ga, = torch.autograd.grad(y, a, gy, create_graph=True)
+    gx = s * F.conv_transpose2d(ga, w, padding=1)
+    ghat_x = rnd(B, cin, H, W, seed=11)
+    cot_gy, cot_a = torch.autograd.grad(gx, (gy, a), ghat_x)
+    w_fwd, _ = o.prep_conv_weight(w)
+    yb = bf(y.detach())
+    ghat_y, ahat = o.conv3x3_dbl(o.nchw_to_c8(ghat_x), w_fwd, s, LEAK, o.nchw_to_c8(yb), r.detach()[:, 0].contiguous(),
+                                 o.nchw_to_c8(gy.detach()))
+    assert rel(o.c8_to_nchw(ghat_y), cot_gy) < 1.5e-2
+    assert rel(o.c8_to_nchw(ahat), cot_a) < 2e-2
+
+
+@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES[:12])
+def test_conv3x3_wgrad(B, cin, cout, H, W):
+    o = ops()
+    x = rnd(B, cin, H, W, seed=12)
+    ga = rnd(B, cout, H, W, seed=13)
+    s = 0.37
+    dw_ref = s * torch.nn.grad.conv2d_weight(x, (cout, cin, 3, 3), ga, padding=1)
+    dw = torch.zeros(cout, cin, 3, 3, device='cuda')
+    o.conv3x3_wgrad(o.nchw_to_c8(x), o.nchw_to_c8(ga), s, dw)
+    assert rel(dw, dw_ref) < 2e-3
+    o.conv3x3_wgrad(o.nchw_to_c8(x), o.nchw_to_c8(ga), s, dw)          # accumulates
+    assert rel(dw, 2 * dw_ref) < 2e-3
+
+
+@pytest.mark.parametrize('C,H,W', [(16, 8, 8), (32, 16, 24), (128, 16, 16)])
+def test_resampling(C, H, W):
+    o = ops()
+    x = rnd(2, C, H, W, seed=14)
+    up = o.c8_to_nchw(o.upsample2x(o.nchw_to_c8(x)))
+    assert rel(up, F.interpolate(x, scale_factor=2, mode='bilinear')) < 4e-3
+    pool = o.c8_to_nchw(o.avgpool2(o.nchw_to_c8(x)))
+    assert rel(pool, F.avg_pool2d(x, 2)) < 4e-3
+    # adjoint of the upsample fused with PixelNorm/LeakyReLU backward
+    h = rnd(2, C, H, W, seed=15)
+    y, r = pn_ref(F.leaky_relu(h, LEAK))
+    y = bf(y)
+    g_up = rnd(2, C, 2 * H, 2 * W, seed=16)
+    xr = x.clone().requires_grad_()
+    g_low, = torch.autograd.grad(F.interpolate(xr, scale_factor=2, mode='bilinear'), xr, g_up)
+    extra_pre = rnd(2, H, W, seed=17)
+    extra_w = rnd(C, seed=18)
+    g_tot = g_low + extra_w.view(1, C, 1, 1) * extra_pre.unsqueeze(1)
+    mask = torch.where(y > 0, 1.0, LEAK)
+    ref = mask * r * (g_tot - y * (g_tot * y).mean(1, keepdim=True))
+    ga = o.up2_bwd_pn_bwd(o.nchw_to_c8(g_up), o.nchw_to_c8(y), r[:, 0].contiguous(), extra_pre, extra_w)
+    assert rel(o.c8_to_nchw(ga), ref) < 8e-3
+    # pn_bwd with un-pooling
+    g_pool = rnd(2, C, H // 2, W // 2, seed=19)
+    g_full = F.interpolate(g_pool, scale_factor=2, mode='nearest') * 0.25
+    addin = rnd(2, C, H, W, seed=20)
+    ref = mask * r * (g_full - y * (g_full * y).mean(1, keepdim=True)) + addin
+    ga, gy = o.pn_bwd(o.nchw_to_c8(g_pool), o.nchw_to_c8(y), r[:, 0].contiguous(), gscale=0.25, unpool=True,
+                      addin=o.nchw_to_c8(addin), want_gy=True)
+    assert rel(o.c8_to_nchw(ga), ref) < 8e-3
+    assert rel(o.c8_to_nchw(gy), g_full) < 4e-3
+
+
+def test_image_ops():
+    o = ops()
+    x = torch.randn(3, 16, 24, device='cuda')
+    assert torch.allclose(o.pool_image(x), F.avg_pool2d(x.unsqueeze(1), 2)[:, 0], atol=1e-6)
+    assert torch.allclose(o.up2_image(x), F.interpolate(x.unsqueeze(1), scale_factor=2, mode='bilinear')[:, 0], atol=1e-6)
+    g = torch.randn(3, 32, 48, device='cuda')
+    xr = x.clone().requires_grad_()
+    ref, = torch.autograd.grad(F.interpolate(xr.unsqueeze(1), scale_factor=2, mode='bilinear'), xr, g.unsqueeze(1))
+    assert torch.allclose(o.up2_image_bwd(g, 0.5), 0.5 * ref, atol=1e-5)
+    assert torch.allclose(o.unpool_image(x, 0.25), 0.25 * F.interpolate(x.unsqueeze(1), scale_factor=2)[:, 0])
+    y = torch.randn_like(x)
+    assert torch.allclose(o.lerp(x, y, 0.3), x + 0.3 * (y - x), atol=1e-6)
+    eps = torch.rand(3, device='cuda')
+    assert torch.allclose(o.interp_images(x, y, eps), eps.view(3, 1, 1) * x + (1 - eps.view(3, 1, 1)) * y, atol=1e-6)
+    assert torch.allclose(o.scale_rows(x, eps, 2.0), 2 * eps.view(3, 1, 1) * x, atol=1e-6)
+
+
+@pytest.mark.parametrize('C', [16, 128])
+def test_fromim_toim(C):
+    o = ops()
+    B, H, W = 2, 16, 16
+    xp = torch.randn(B, H, W, device='cuda')
+    w, b = torch.randn(C, device='cuda'), torch.randn(C, device='cuda')
+    f_ref = w.view(1, C, 1, 1) * xp.unsqueeze(1) + b.view(1, C, 1, 1)
+    assert rel(o.c8_to_nchw(o.fromim_fwd(xp, w, b)), f_ref) < 4e-3
+    y_end = rnd(B, C, H, W, seed=21)
+    fade = o.d_fade_fwd(o.nchw_to_c8(y_end), xp, w, b, 0.3)
+    assert rel(o.c8_to_nchw(fade), f_ref + 0.3 * (y_end - f_ref)) < 4e-3
+    g = rnd(B, C, H, W, seed=22)
+    gw, gb = torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda')
+    g_img = torch.empty(B, H, W, device='cuda')
+    o.fromim_bwd(o.nchw_to_c8(g), xp, w, gw, gb, gscale=0.5, g_img=g_img)
+    assert rel(gw, 0.5 * (g * xp.unsqueeze(1)).sum((0, 2, 3))) < 1e-4
+    assert rel(gb, 0.5 * g.sum((0, 2, 3))) < 1e-4
+    assert rel(g_img, 0.5 * (g * w.view(1, C, 1, 1)).sum(1)) < 1e-4
+    # double backward
+    ghat = torch.randn(B, H, W, device='cuda')
+    what = torch.zeros(C, device='cuda')
+    out = o.fromim_dbl(ghat, o.nchw_to_c8(g), w, what, in_scale=2.0, gscale=0.5)
+    assert rel(o.c8_to_nchw(out), 2.0 * w.view(1, C, 1, 1) * ghat.unsqueeze(1)) < 4e-3
+    assert rel(what, (2.0 * ghat.unsqueeze(1) * 0.5 * g).sum((0, 2, 3))) < 1e-4
+    # ToImage
+    h = rnd(B, C, H, W, seed=23)
+    y, r = pn_ref(F.leaky_relu(h, LEAK))
+    y = bf(y)
+    wt = torch.randn(C, device='cuda') * 0.2
+    img_ref = torch.tanh((y * wt.view(1, C, 1, 1)).sum(1))
+    img = o.toim_fwd(o.nchw_to_c8(y), wt)
+    assert torch.allclose(img, img_ref, atol=2e-5)
+    g_img = torch.randn(B, H, W, device='cuda')
+    gpre_ref = 0.7 * g_img * (1 - img_ref ** 2)
+    gy = wt.view(1, C, 1, 1) * gpre_ref.unsqueeze(1)
+    mask = torch.where(y > 0, 1.0, LEAK)
+    ga_ref = mask * r * (gy - y * (gy * y).mean(1, keepdim=True))
+    gw = torch.zeros(C, device='cuda')
+    ga, gpre = o.toim_bwd(g_img, img, o.nchw_to_c8(y), r[:, 0].contiguous(), wt, gw, gscale=0.7, want_gpre=True)
+    assert rel(gpre, gpre_ref) < 1e-4
+    assert rel(o.c8_to_nchw(ga), ga_ref) < 8e-3
+    assert rel(gw, (gpre_ref.unsqueeze(1) * y).sum((0, 2, 3))) < 1e-4
+
+
+def test_head():
+    o = ops()
+    B, C, S = 5, 128, 16
+    h = rnd(B, C, S, S, seed=24)
+    y, r = pn_ref(F.leaky_relu(h, LEAK))
+    y = bf(y)
+    w = torch.randn(1, C, S, S, device='cuda') * 0.01
+    bias = torch.randn(1, device='cuda')
+    s = GAIN / math.sqrt(C * S * S)
+    ref = F.conv2d(s * y, w, bias).flatten()
+    score = o.head_fwd(o.nchw_to_c8(y), w, bias, s)
+    assert torch.allclose(score, ref, rtol=1e-4, atol=1e-5)
+    gout = torch.randn(B, device='cuda')
+    gy_ref = s * w * gout.view(B, 1, 1, 1)
+    mask = torch.where(y > 0, 1.0, LEAK)
+    ga_ref = mask * r * (gy_ref - y * (gy_ref * y).mean(1, keepdim=True))
+    ga, gy = o.head_bwd_pn(gout, w, s, o.nchw_to_c8(y), r[:, 0].contiguous(), want_gy=True)
+    assert rel(o.c8_to_nchw(ga), ga_ref) < 8e-3
+    assert rel(o.c8_to_nchw(gy), gy_ref) < 4e-3
+    gw = torch.zeros_like(w)
+    o.head_wgrad(o.nchw_to_c8(y), gout, s, gw)
+    assert rel(gw, s * (y * gout.view(B, 1, 1, 1)).sum(0, keepdim=True)) < 1e-4
+    gb = torch.zeros(C, device='cuda')
+    o.bias_grad(o.nchw_to_c8(y), gb)
+    assert rel(gb, y.sum((0, 2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize('B', [3, 16, 40])
+def test_linear(B):
+    o = ops()
+    C, S, K = 128, 16, 512
+    w = rnd(C * S * S, K, seed=25, scale=GAIN / math.sqrt(K))
+    z = torch.randn(B, K, device='cuda')
+    z = z / z.norm(dim=1, keepdim=True)
+    s = GAIN / math.sqrt(K)
+    h = F.leaky_relu(F.linear(s * z, w), LEAK).unflatten(1, (C, S, S))
+    y_ref, r_ref = pn_ref(h)
+    wb = o.prep_linear_weight(w)
+    assert torch.equal(wb.float(), w)
+    y, r = o.linear_fwd(z, wb, s, LEAK, C, S)
+    assert rel(o.c8_to_nchw(y), y_ref) < 5e-3
+    assert rel(r, r_ref[:, 0]) < 1e-3
+    ga = rnd(B, C, S, S, seed=26)
+    dw = torch.zeros_like(w)
+    o.linear_wgrad(o.nchw_to_c8(ga), z, s, dw)
+    assert rel(dw, s * ga.flatten(1).t() @ z) < 1e-4
+
+
+def test_losses():
+    o = ops()
+    B = 16
+    sr, sf = torch.randn(B, device='cuda'), torch.randn(B, device='cuda')
+    out3, gr, gf = o.wloss(sr, sf, 1e-3)
+    ref = -sr.mean() + sf.mean() + 1e-3 * (sr ** 2).mean()
+    assert torch.allclose(out3, torch.stack([ref, sr.mean(), sf.mean()]), atol=1e-6)
+    assert torch.allclose(gr, (-1 + 2e-3 * sr) / B, atol=1e-7) and torch.allclose(gf, torch.full_like(gf, 1 / B))
+    out1, gf = o.gloss(sf)
+    assert torch.allclose(out1[0], -sf.mean(), atol=1e-6) and torch.allclose(gf, torch.full_like(gf, -1 / B))
+    g = (torch.randn(B, 32, 32, device='cuda') * 0.01).requires_grad_()
+    pen_ref = 10 * (((0.5 * g.flatten(1).norm(dim=1)) - 1) ** 2).mean()
+    gref, = torch.autograd.grad(pen_ref, g)
+    pen, coeff = o.gp_loss(g.detach(), 0.5, 10.0)
+    assert torch.allclose(pen[0], pen_ref, rtol=1e-5)
+    # d pen / d g = coeff_b * norm_scale^2 * g
+    assert torch.allclose(o.scale_rows(g.detach(), coeff, 0.25), gref, rtol=1e-4, atol=1e-8)
+
+
+def test_adam_multi():
+    o = ops()
+    torch.manual_seed(0)
+    shapes = [(128, 128, 3, 3), (16,), (1, 16, 1, 1), (1001,)]
+    ps = [torch.randn(s, device='cuda') for s in shapes]
+    ref = [torch.nn.Parameter(p.clone()) for p in ps]
+    opt = torch.optim.Adam(ref, lr=1e-3, betas=(0.5, 0.999))
+    ms, vs = [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps]
+    shadow = torch.empty(ps[0].shape, dtype=torch.bfloat16, device='cuda')
+    for step in range(1, 4):
+        gs = [torch.randn_like(p) for p in ps]
+        for q, g in zip(ref, gs):
+            q.grad = g
+        opt.step()
+        ent = [dict(p=p, g=g, m=m, v=v, shadow=shadow if i == 0 else None, step_size=1e-3 / (1 - 0.5 ** step),
+                    inv_bc2_sqrt=1 / math.sqrt(1 - 0.999 ** step)) for i, (p, g, m, v) in enumerate(zip(ps, gs, ms, vs))]
+        o.adam_multi(ent, 0.5, 0.999, 1e-8)
+    for p, q in zip(ps, ref):
+        assert torch.allclose(p, q.data, rtol=1e-5, atol=1e-6)
+    assert torch.equal(shadow, ps[0].to(torch.bfloat16))
