@@ -7,7 +7,7 @@ from neuron_gan_b200 import _lib
 
 def test_header_parses_and_all_symbols_are_exported():
     protos = _lib.parse_header()
-    assert len(protos) >= 40 and 'ngan_conv3x3_fwd' in protos and 'ngan_adam_multi' in protos
+    assert len(protos) >= 39 and 'ngan_conv3x3_fwd' in protos and 'ngan_adam_multi' in protos
     if not os.path.isfile(_lib.LIB_PATH):
         import __graft_entry__
         __graft_entry__.build()
