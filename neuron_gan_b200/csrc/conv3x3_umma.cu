@@ -32,7 +32,6 @@ struct ConvArgs {
     int nMT;
     int tmem_cols;
     int n_stage;
-    int desc_swap;         // debug (NGAN_DESC_SWAP=1): exchange the LBO/SBO descriptor fields
     uint32_t plane_bytes;  // (TH+2)*Wh*16
     float scale, leak;
     const __nv_bfloat16* wprep;  // [9][CIN/8][COUT][8]
@@ -102,10 +101,9 @@ __global__ void __launch_bounds__(128) conv3x3_umma_kernel(const __grid_constant
             for (int kc = 0; kc < CIN / 16; ++kc) {
                 const uint32_t a_addr = in_base + (2 * kc) * a.plane_bytes + tap_off;
                 const uint32_t b_addr = w_base + stage * W_TAP_BYTES + (2 * kc) * COUT * 16;
-                const uint64_t bdesc = a.desc_swap ? umma_desc(b_addr, 128, COUT * 16) : umma_desc(b_addr, COUT * 16, 128);
+                const uint64_t bdesc = umma_desc(b_addr, COUT * 16, 128);
                 for (int mt = 0; mt < a.nMT; ++mt) {
-                    const uint64_t adesc = a.desc_swap ? umma_desc(a_addr + mt * 128 * 16, 128, a.plane_bytes)
-                                                       : umma_desc(a_addr + mt * 128 * 16, a.plane_bytes, 128);
+                    const uint64_t adesc = umma_desc(a_addr + mt * 128 * 16, a.plane_bytes, 128);
                     umma_bf16(tmem_base + mt * COUT, adesc, bdesc, IDESC, (tap | kc) != 0);
                 }
             }
@@ -434,8 +432,6 @@ int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, 
     a.TH = plan.TH; a.TW = plan.TW; a.Wh = plan.Wh;
     a.nMT = plan.nMT; a.tmem_cols = plan.tmem_cols; a.n_stage = plan.n_stage;
     a.plane_bytes = plan.plane_bytes;
-    static const int swap = getenv("NGAN_DESC_SWAP") ? atoi(getenv("NGAN_DESC_SWAP")) : 0;
-    a.desc_swap = swap;
     a.scale = scale; a.leak = leak;
     a.wprep = static_cast<const __nv_bfloat16*>(wprep);
     a.bias = bias;
