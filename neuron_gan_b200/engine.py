@@ -1,0 +1,376 @@
+"""Network-level orchestration of the sm_100a kernels: forward, backward and the gradient-penalty double
+backward of Generator_PG / Discriminator_PG, written out by hand (no autograd inside).
+
+The reference gets all of this from ATen + autograd (reference models.py:344-353, 516-524 for the forwards;
+loss_functions.py:175 `autograd.grad(..., create_graph=True)` + train.py:365 `.backward()` for the rest).
+Here each pass is an explicit kernel sequence over saved activations:
+
+  * a conv + LeakyReLU + PixelNorm stage saves only its output y (bf16, it is the next stage's input anyway)
+    and the per-pixel PixelNorm scale r; the LeakyReLU mask is recovered from sign(y);
+  * backward: the data-gradient conv of stage l fuses the PixelNorm/LeakyReLU backward of stage l-1 in its
+    epilogue whenever no resampling sits between them, otherwise a pointwise kernel does the resample adjoint
+    + PixelNorm backward in one pass;
+  * double backward (D only): sweep 1 runs the "conv of the cotangent" kernels from the image side up to the
+    head and leaves, per stage, the cotangent to inject at its pre-activation; sweep 2 is the ordinary
+    backward with those injections.  Formulas: SURVEY.md section 8a row 3.
+
+Parameter gradients ACCUMULATE into the fp32 tensors of a `sink` (dict id(param) -> tensor).
+"""
+import weakref
+from types import SimpleNamespace
+
+import torch
+
+from . import ops
+
+F32 = torch.float32
+
+# ---------------------------------------------------------------------------------------------------------
+# bf16 operand images of the fp32 master weights, refreshed when the master changes
+# ---------------------------------------------------------------------------------------------------------
+_weight_cache = weakref.WeakKeyDictionary()
+
+
+def _wkey(w):
+    return (w._version, getattr(w, '_ngan_epoch', 0), w.data_ptr())
+
+
+def conv_images(conv):
+    """(forward image, data-gradient image) of a Conv2d_normalized 3x3 weight."""
+    w = conv.weight
+    ent = _weight_cache.get(w)
+    key = _wkey(w)
+    if ent is None or ent['key'] != key:
+        bufs = (ent['fwd'], ent['dgrad']) if ent is not None and ent['fwd'].device == w.device else (None, None)
+        fwd, dgrad = ops.prep_conv_weight(w.detach(), *bufs)
+        ent = {'key': key, 'fwd': fwd, 'dgrad': dgrad}
+        _weight_cache[w] = ent
+    return ent['fwd'], ent['dgrad']
+
+
+def linear_shadow(lin, allocate_only=False):
+    """bf16 copy of the generator's Linear_normalized weight (same [out, in] layout)."""
+    w = lin.weight
+    ent = _weight_cache.get(w)
+    key = _wkey(w)
+    if ent is None or ent['shadow'].device != w.device:
+        ent = {'key': None, 'shadow': torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)}
+        _weight_cache[w] = ent
+    if allocate_only:
+        return ent
+    if ent['key'] != key:
+        ops.prep_linear_weight(w.detach(), ent['shadow'])
+        ent['key'] = key
+    return ent['shadow']
+
+
+def mark_updated(param, shadow_is_fresh=False):
+    """Called by the fused optimiser after it changed `param` through a raw pointer."""
+    param._ngan_epoch = getattr(param, '_ngan_epoch', 0) + 1
+    if shadow_is_fresh:
+        ent = _weight_cache.get(param)
+        if ent is not None and 'shadow' in ent:
+            ent['key'] = _wkey(param)
+
+
+def _sink_get(sink, p):
+    return None if sink is None else sink[id(p)]
+
+
+def _flat(w):
+    return w.detach().reshape(-1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Generator
+# ---------------------------------------------------------------------------------------------------------
+def _clp(x, conv, leak, save):
+    y, r = ops.conv3x3_fwd(x, conv_images(conv)[0], conv.bias.detach() if conv.bias is not None else None,
+                           conv.scale_value, leak, conv.out_channels, want_r=save)
+    return y, r
+
+
+def _g_block_fwd(blk, y, leak, save):
+    xu = ops.upsample2x(y)
+    y1, r1 = _clp(xu, blk.conv1, leak, save)
+    y2, r2 = _clp(y1, blk.conv2, leak, save)
+    return SimpleNamespace(blk=blk, xu=xu if save else None, y1=y1 if save else None, r1=r1, y2=y2, r2=r2)
+
+
+def g_forward(net, z, save):
+    """Generator_PG.forward (reference models.py:344-353). z: [B, latent] fp32 -> (img [B, R, R] fp32, ctx)."""
+    leak = net.LeakyReLU_neg_slope
+    alpha = net.alpha_value()
+    lin, conv0 = net.layers[0], net.layers[4]
+    S, C0 = net.image_size_init, net.N_features_per_layer[0]
+    z = z.detach().to(F32).contiguous()
+    y0, r0 = ops.linear_fwd(z, linear_shadow(lin), lin.scale_value, leak, C0, S, want_r=save)
+    yc, rc = _clp(y0, conv0, leak, save)
+    recs, y, r = [], yc, rc
+    for blk in net.trunk_blocks():
+        rec = _g_block_fwd(blk, y, leak, save)
+        recs.append(rec)
+        y, r = rec.y2, rec.r2
+    ctx = (SimpleNamespace(z=z, y0=y0, r0=r0, yc=yc, rc=rc, recs=recs, alpha=alpha, new=None, toim=net.ToIm,
+                           toim_new=None) if save else None)
+    if alpha >= 1:
+        img = ops.toim_fwd(y, _flat(net.ToIm.weight))
+        if save:
+            ctx.img = img
+        return img, ctx
+    # fade-in: im_start = up(ToIm_old(x)), im_end = ToIm_new(block_new(x))      (models.py:347-350)
+    img_old = ops.toim_fwd(y, _flat(net.ToIm.weight))
+    new = _g_block_fwd(net.conv_block_list[0], y, leak, save)
+    img_end = ops.toim_fwd(new.y2, _flat(net.ToIm_list[0].weight))
+    img = ops.lerp(ops.up2_image(img_old), img_end, alpha)
+    if save:
+        ctx.new, ctx.img_old, ctx.img_end, ctx.toim_new = new, img_old, img_end, net.ToIm_list[0]
+    return img, ctx
+
+
+def _g_block_bwd(rec, ga2, y_prev, r_prev, leak, sink, extra_pre=None, extra_w=None):
+    """Backward through one generator block given ga2 (gradient at conv2's pre-activation); returns the
+    gradient at the pre-activation of the stage below (whose output y_prev was upsampled into this block)."""
+    c1, c2 = rec.blk.conv1, rec.blk.conv2
+    ops.conv3x3_wgrad(rec.y1, ga2, c2.scale_value, _sink_get(sink, c2.weight))
+    ga1, _ = ops.conv3x3_dgrad_pn(ga2, conv_images(c2)[1], c2.scale_value, leak, rec.y1, rec.r1)
+    ops.conv3x3_wgrad(rec.xu, ga1, c1.scale_value, _sink_get(sink, c1.weight))
+    g_up = ops.conv3x3_dgrad(ga1, conv_images(c1)[1], c1.scale_value, c1.in_channels)
+    return ops.up2_bwd_pn_bwd(g_up, y_prev, r_prev, extra_pre, extra_w, leak)
+
+
+def g_backward(net, ctx, g_img, sink):
+    """Gradient of the generator parameters given d loss / d image ([B, R, R] fp32)."""
+    leak = net.LeakyReLU_neg_slope
+    alpha = ctx.alpha
+    g_img = g_img.detach().to(F32).contiguous()
+    trunk_y, trunk_r = (ctx.recs[-1].y2, ctx.recs[-1].r2) if ctx.recs else (ctx.yc, ctx.rc)
+    if ctx.new is None:
+        ga, _ = ops.toim_bwd(g_img, ctx.img, trunk_y, trunk_r, _flat(ctx.toim.weight), _sink_get(sink, ctx.toim.weight),
+                             leak=leak)
+    else:
+        new, toim_new, toim_old = ctx.new, ctx.toim_new, ctx.toim
+        ga2, _ = ops.toim_bwd(g_img, ctx.img_end, new.y2, new.r2, _flat(toim_new.weight),
+                              _sink_get(sink, toim_new.weight), gscale=alpha, leak=leak)
+        g_old = ops.up2_image_bwd(g_img, 1.0 - alpha)
+        _, gpre_old = ops.toim_bwd(g_old, ctx.img_old, trunk_y, None, _flat(toim_old.weight),
+                                   _sink_get(sink, toim_old.weight), want_ga=False, want_gpre=True, leak=leak)
+        ga = _g_block_bwd(new, ga2, trunk_y, trunk_r, leak, sink, gpre_old, _flat(toim_old.weight))
+    for i in range(len(ctx.recs) - 1, -1, -1):
+        y_prev, r_prev = (ctx.recs[i - 1].y2, ctx.recs[i - 1].r2) if i > 0 else (ctx.yc, ctx.rc)
+        ga = _g_block_bwd(ctx.recs[i], ga, y_prev, r_prev, leak, sink)
+    lin, conv0 = net.layers[0], net.layers[4]
+    ops.conv3x3_wgrad(ctx.y0, ga, conv0.scale_value, _sink_get(sink, conv0.weight))
+    ga0, _ = ops.conv3x3_dgrad_pn(ga, conv_images(conv0)[1], conv0.scale_value, leak, ctx.y0, ctx.r0)
+    ops.linear_wgrad(ga0, ctx.z, lin.scale_value, _sink_get(sink, lin.weight))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Discriminator
+# ---------------------------------------------------------------------------------------------------------
+def d_forward(net, x, save):
+    """Discriminator_PG.forward (reference models.py:516-524). x: [B, R, R] fp32 -> (scores [B] fp32, ctx).
+
+    AvgPool2d(2) commutes with the 1x1 FromImage conv and the fade-in branch's bilinear x0.5 is the same 2x2
+    mean, so both branches start from one pooled 1-channel image `xp` and the
+    full-resolution F-channel tensor is never materialised."""
+    leak = net.LeakyReLU_neg_slope
+    alpha = net.alpha_value()
+    x = x.detach().to(F32).contiguous()
+    trunk = net.trunk_blocks()
+    pooled = net.N_layers > 1
+    xp = ops.pool_image(x) if pooled else x
+    stages = []
+
+    def block(blk, xin, pooled_in):
+        y1, r1 = _clp(xin, blk.conv1, leak, save)
+        y2, r2 = _clp(y1, blk.conv2, leak, save)
+        return SimpleNamespace(kind='block', blk=blk, xin=xin if save else None, xin_pooled=pooled_in,
+                               y1=y1 if save else None, r1=r1, y2=y2, r2=r2, out=y2, consumer_pooled=False)
+
+    if alpha < 1:
+        f_new = net.FromIm_list[-1].conv
+        F = ops.fromim_fwd(xp, _flat(f_new.weight), f_new.bias.detach())
+        stages.append(SimpleNamespace(kind='from', conv=f_new, out=F, consumer_pooled=False))
+        stages.append(block(net.conv_block_list[-1], F, False))
+        f_old = net.FromIm.conv
+        y = ops.d_fade_fwd(stages[-1].out, xp, _flat(f_old.weight), f_old.bias.detach(), alpha)
+        stages.append(SimpleNamespace(kind='fade', conv=f_old, out=y, consumer_pooled=False))
+        rest = trunk
+    else:
+        f_cur = net.FromIm.conv
+        F = ops.fromim_fwd(xp, _flat(f_cur.weight), f_cur.bias.detach())
+        stages.append(SimpleNamespace(kind='from', conv=f_cur, out=F, consumer_pooled=False))
+        rest = trunk
+        if trunk:  # the first trunk block's AvgPool is already folded into xp
+            stages.append(block(trunk[0], F, False))
+            rest = trunk[1:]
+    for blk in rest:
+        stages[-1].consumer_pooled = True
+        stages.append(block(blk, ops.avgpool2(stages[-1].out), True))
+    last_conv, head = net.last_conv(), net.head_conv()
+    yl, rl = _clp(stages[-1].out, last_conv, leak, save)
+    scores = ops.head_fwd(yl, head.weight.detach(), head.bias.detach(), head.scale_value)
+    if not save:
+        return scores, None
+    ctx = SimpleNamespace(xp=xp, pooled=pooled, alpha=alpha, stages=stages, last_x=stages[-1].out, yl=yl, rl=rl,
+                          B=x.shape[0])
+    return scores, ctx
+
+
+def d_backward(net, ctx, gout, sink, addins=None, want_gxp=False, record=None):
+    """Backward through the critic.
+
+    gout   : d loss / d score [B] fp32, or None for sweep 2 of the double backward (no head contribution).
+    sink   : parameter-gradient accumulators, or None to skip every weight/bias gradient (input gradient only).
+    addins : per-stage cotangents injected at the pre-activations (from d_double_backward_sweep1).
+    record : SimpleNamespace to fill with the first-order gradients the double backward needs.
+    Returns g_xp, the gradient wrt the pooled image `xp` ([B, h, w] fp32) when want_gxp (callers un-pool it)."""
+    leak = net.LeakyReLU_neg_slope
+    alpha = ctx.alpha
+    last, head = net.last_conv(), net.head_conv()
+    rec = record is not None
+    ad = addins or {}
+    if gout is not None:
+        gout = gout.detach().to(F32).contiguous()
+        ga_l, gy_l = ops.head_bwd_pn(gout, head.weight.detach(), head.scale_value, ctx.yl, ctx.rl, want_gy=rec,
+                                     leak=leak)
+        if sink is not None:
+            ops.head_wgrad(ctx.yl, gout, head.scale_value, _sink_get(sink, head.weight))
+            _sink_get(sink, head.bias).add_(gout.sum())
+    else:
+        ga_l, gy_l = ad['last'], None
+    if rec:
+        record.last = SimpleNamespace(gy=gy_l, ga=ga_l)
+        record.gout = gout
+        record.stages = {}
+    if sink is not None:
+        ops.conv3x3_wgrad(ctx.last_x, ga_l, last.scale_value, _sink_get(sink, last.weight))
+        ops.bias_grad(ga_l, _sink_get(sink, last.bias))
+
+    top = ctx.stages[-1]
+    if top.kind == 'block':
+        a2 = ad.get(id(top), (None, None))[1]
+        ga2, gy2 = ops.conv3x3_dgrad_pn(ga_l, conv_images(last)[1], last.scale_value, leak, top.y2, top.r2, addin=a2,
+                                        want_gy=rec)
+        incoming = ('ga', ga2, gy2)
+    else:
+        incoming = ('g', ops.conv3x3_dgrad(ga_l, conv_images(last)[1], last.scale_value, last.in_channels), 1.0,
+                    False)
+
+    # `incoming` is the gradient handed to the stage being visited: either ('ga', ga2, gy2) -- already through the
+    # PixelNorm/LeakyReLU backward -- or ('g', tensor, scale, unpool): scale * (AvgPool adjoint if unpool)(tensor)
+    # is the gradient wrt the stage's output.
+    g_xp = None
+    for st in reversed(ctx.stages):
+        if st.kind == 'block':
+            c1, c2 = st.blk.conv1, st.blk.conv2
+            a1, a2 = ad.get(id(st), (None, None))
+            if incoming[0] == 'ga':
+                _, ga2, gy2 = incoming
+                recv_unpool = False
+            else:
+                _, g, gs, recv_unpool = incoming
+                ga2, gy2 = ops.pn_bwd(g, st.y2, st.r2, gscale=gs * (0.25 if recv_unpool else 1.0),
+                                      unpool=recv_unpool, addin=a2, want_gy=rec, leak=leak)
+            if sink is not None:
+                ops.conv3x3_wgrad(st.y1, ga2, c2.scale_value, _sink_get(sink, c2.weight))
+            ga1, gy1 = ops.conv3x3_dgrad_pn(ga2, conv_images(c2)[1], c2.scale_value, leak, st.y1, st.r1, addin=a1,
+                                            want_gy=rec)
+            if sink is not None:
+                ops.conv3x3_wgrad(st.xin, ga1, c1.scale_value, _sink_get(sink, c1.weight))
+            if rec:
+                record.stages[id(st)] = SimpleNamespace(gy1=gy1, ga1=ga1, gy2=gy2, ga2=ga2, recv_unpool=recv_unpool)
+            incoming = ('g', ops.conv3x3_dgrad(ga1, conv_images(c1)[1], c1.scale_value, c1.in_channels), 1.0,
+                        st.xin_pooled)
+        else:
+            _, g, gs, unpool = incoming
+            gs_eff = gs * (0.25 if unpool else 1.0)
+            if rec:
+                record.stages[id(st)] = SimpleNamespace(g=g, unpool=unpool, gscale=gs_eff)
+            need_img = want_gxp
+            if need_img and g_xp is None:
+                g_xp = torch.empty_like(ctx.xp)
+                accumulate = False
+            else:
+                accumulate = True
+            w = _flat(st.conv.weight)
+            if st.kind == 'fade':
+                if sink is not None or need_img:
+                    ops.fromim_bwd(g, ctx.xp, w, _sink_get(sink, st.conv.weight), _sink_get(sink, st.conv.bias),
+                                   gscale=gs_eff * (1.0 - alpha), unpool=unpool, g_img=g_xp if need_img else None,
+                                   accumulate=accumulate)
+                incoming = ('g', g, gs * alpha, unpool)
+            else:  # 'from'
+                if sink is not None or need_img:
+                    ops.fromim_bwd(g, ctx.xp, w, _sink_get(sink, st.conv.weight), _sink_get(sink, st.conv.bias),
+                                   gscale=gs_eff, unpool=unpool, g_img=g_xp if need_img else None,
+                                   accumulate=accumulate)
+    return g_xp
+
+
+def d_double_backward_sweep1(net, ctx, record, ghat_xp, sink):
+    """Sweep 1 of the gradient-penalty double backward: propagate the cotangent on the first-order input
+    gradient (ghat_xp, [B, h, w] fp32, living on the pooled image) from the image side up to the head.
+    Accumulates the "wgrad of dgrad" terms into `sink` and returns the per-stage injections for sweep 2."""
+    leak = net.LeakyReLU_neg_slope
+    alpha = ctx.alpha
+    addins = {}
+    cur = None
+    ghat_xp = ghat_xp.contiguous()
+    for st in ctx.stages:
+        r = record.stages[id(st)]
+        if st.kind == 'from':
+            cur = ops.fromim_dbl(ghat_xp, r.g, _flat(st.conv.weight), _sink_get(sink, st.conv.weight), in_scale=1.0,
+                                 gscale=r.gscale, unpool=r.unpool)
+            if r.unpool:            # cannot happen with the reference's topology, kept for completeness
+                cur = ops.avgpool2(cur)
+        elif st.kind == 'block':
+            c1, c2 = st.blk.conv1, st.blk.conv2
+            ops.conv3x3_wgrad(cur, r.ga1, c1.scale_value, _sink_get(sink, c1.weight))
+            gh1, ah1 = ops.conv3x3_dbl(cur, conv_images(c1)[0], c1.scale_value, leak, st.y1, st.r1, r.gy1)
+            ops.conv3x3_wgrad(gh1, r.ga2, c2.scale_value, _sink_get(sink, c2.weight))
+            gh2, ah2 = ops.conv3x3_dbl(gh1, conv_images(c2)[0], c2.scale_value, leak, st.y2, st.r2, r.gy2)
+            addins[id(st)] = (ah1, ah2)
+            cur = gh2          # cotangent on gy2; the fade stage (if next) applies alpha and the pooling itself
+            nxt = ctx.stages.index(st) + 1
+            to_fade = nxt < len(ctx.stages) and ctx.stages[nxt].kind == 'fade'
+            if r.recv_unpool and not to_fade:
+                cur = ops.avgpool2(cur)
+        else:  # 'fade': first-order g_y reached FromIm_old with (1-alpha) and the new block with alpha
+            w_old = _flat(st.conv.weight)
+            ops.fromim_dbl(ghat_xp, r.g, w_old, _sink_get(sink, st.conv.weight), in_scale=1.0,
+                           gscale=r.gscale * (1.0 - alpha), unpool=r.unpool, want_out=False)
+            zero_b = torch.zeros_like(st.conv.bias)
+            cur = ops.d_fade_fwd(cur, ghat_xp, w_old, zero_b, alpha)   # alpha*cur + (1-alpha)*w_old*ghat_xp
+            if r.unpool:
+                cur = ops.avgpool2(cur)
+    last, head = net.last_conv(), net.head_conv()
+    ops.conv3x3_wgrad(cur, record.last.ga, last.scale_value, _sink_get(sink, last.weight))
+    gh_l, ah_l = ops.conv3x3_dbl(cur, conv_images(last)[0], last.scale_value, leak, ctx.yl, ctx.rl, record.last.gy)
+    ops.head_wgrad(gh_l, record.gout, head.scale_value, _sink_get(sink, head.weight))
+    addins['last'] = ah_l
+    return addins
+
+
+def d_grad_penalty(net, x_hat, lam, sink, gscale=1.0):
+    """The whole gradient-penalty term (reference loss_functions.py:157-180) for an already interpolated batch:
+    forward, first-order input gradient, penalty, and -- when `sink` is given -- its parameter gradients
+    (scaled by gscale).  Returns (penalty [1] fp32, callable that runs the double backward into a sink)."""
+    scores, ctx = d_forward(net, x_hat, save=True)
+    B = ctx.B
+    ones = torch.ones(B, dtype=F32, device=scores.device)
+    record = SimpleNamespace()
+    g_xp = d_backward(net, ctx, ones, None, want_gxp=True, record=record)
+    ns = 0.5 if ctx.pooled else 1.0       # ||unpool(g)/4|| = ||g|| / 2
+    pen, coeff = ops.gp_loss(g_xp, ns, float(lam), gscale=1.0)
+
+    def backward(into, scale=1.0, scale_tensor=None):
+        c = coeff if scale_tensor is None else coeff * scale_tensor
+        ghat_xp = ops.scale_rows(g_xp, c, ns * ns * scale)
+        addins = d_double_backward_sweep1(net, ctx, record, ghat_xp, into)
+        d_backward(net, ctx, None, into, addins=addins)
+
+    if sink is not None:
+        backward(sink, gscale)
+    return pen, backward, (g_xp, ctx)

@@ -306,6 +306,14 @@ def wloss(s_real, s_fake, drift, gscale=1.0, want_grads=True):
     return out3, g_real, g_fake
 
 
+def wloss_into(s_real, s_fake, drift, g_real, g_fake, gscale=1.0):
+    """wloss writing the per-sample score gradients into caller-provided (contiguous) slices."""
+    out3 = torch.empty(3, dtype=F32, device=s_real.device)
+    _lib.call('ngan_wloss', _p(s_real, F32), _p(s_fake, F32), drift, _p(out3), _p(g_real, F32), _p(g_fake, F32),
+              gscale, s_real.numel(), _stream())
+    return out3, g_real, g_fake
+
+
 def gloss(s_fake, gscale=1.0, want_grads=True):
     B = s_fake.numel()
     out1 = torch.empty(1, dtype=F32, device=s_fake.device)

@@ -1,0 +1,175 @@
+"""The subset of the reference's utils.py that the hot path and its callers import by name
+(train.py:20-21, loss_functions.py:3, eval.py:6): latent sampling, checkpointing, sample generation.
+Plotting / video / memory logging (reference utils.py:228-343, 360-543, 614-788) are out of scope."""
+import datetime
+import os
+import pickle
+
+import numpy as np
+import torch
+from torch import nn
+
+# ----------------------------------------------------------------------------------------------- training
+Latent_vecs_memo = {}
+
+
+def sample_latent_vec(size: tuple, seed=None, mode='randn', device=torch.device('cpu')):
+    """Latent batch, drawn on the CPU generator for reproducibility and then moved (reference utils.py:57-92):
+    'randn' -> clamp(+-5) -> rows L2-normalised (uniform on the hypersphere); 'rand' -> U(-1, 1).
+    With `seed`, the global RNG state is saved/restored and the result memoised by (size, mode, seed)."""
+    device = torch.device(device)
+    if seed is not None:
+        key = (size, mode, seed)
+        if key in Latent_vecs_memo:
+            return Latent_vecs_memo[key].to(device)
+        rng_state = torch.get_rng_state()
+        torch.manual_seed(seed)
+    if mode == 'rand':
+        z = 2 * torch.rand(*size, device='cpu') - 1
+    elif mode == 'randn':
+        z = torch.randn(*size, device='cpu').clamp(-5, 5)
+        z = z / z.norm(p=2, dim=1, keepdim=True)
+    else:
+        raise ValueError('{} is not supported'.format(mode))
+    if seed is not None:
+        torch.set_rng_state(rng_state)
+        Latent_vecs_memo[key] = z
+    if device.type != 'cpu':
+        z = z.to(device)
+    return z
+
+
+def get_saved_attrs(model):
+    return {a: getattr(model, a) for a in getattr(model, 'saved_attrs', [])}
+
+
+def set_saved_attrs(model, saved_attrs_dict):
+    for name, value in saved_attrs_dict.items():
+        if hasattr(model, name):
+            setattr(model, name, value)
+        else:
+            raise ValueError('{} is not an attribute of {}', name, model)
+    return saved_attrs_dict
+
+
+class Checkpointer:
+    """Reference-format .pth checkpoints (reference utils.py:124-223): keys epoch, Generator_state,
+    Generator_attrs, Discriminator_state, Discriminator_attrs, lr, Loss_real, Loss_fake, Loss_G, Loss_D.
+    No optimiser state, like the reference.  `load_state(filename)` reads the weights from `filename`
+    (the reference re-reads self.filename there, utils.py:213-215, which is a bug)."""
+
+    def __init__(self, Generator_net, Discriminator_net, lr: float, filename: str, N_epochs=100, verbose=True,
+                 device=torch.device('cpu'), extra_checkpoint_period=50e3):
+        self.Generator_net = Generator_net
+        self.Discriminator_net = Discriminator_net
+        self.lr = lr
+        self.filename = filename
+        self.epoch = 0
+        self.Loss_real = np.zeros(N_epochs)
+        self.Loss_fake = np.zeros(N_epochs)
+        self.Loss_G = np.zeros(N_epochs)
+        self.Loss_D = np.zeros(N_epochs)
+        self.verbose = verbose
+        self.device = device
+        self.extra_checkpoint_period = extra_checkpoint_period
+
+    def save_state(self, epoch):
+        self.epoch = epoch
+        ckpt = {'epoch': self.epoch,
+                'Generator_state': self.Generator_net.state_dict(),
+                'Generator_attrs': get_saved_attrs(self.Generator_net),
+                'Discriminator_state': self.Discriminator_net.state_dict(),
+                'Discriminator_attrs': get_saved_attrs(self.Discriminator_net),
+                'lr': self.lr,
+                'Loss_real': self.Loss_real[:epoch], 'Loss_fake': self.Loss_fake[:epoch],
+                'Loss_G': self.Loss_G[:epoch], 'Loss_D': self.Loss_D[:epoch]}
+        torch.save(ckpt, self.filename)
+        if epoch % self.extra_checkpoint_period == 0:
+            base, ext = os.path.splitext(self.filename)
+            torch.save(ckpt, base + '_{:d}k'.format(int(epoch / 1000)) + ext)
+        if self.verbose:
+            print('Training state at epoch {} saved in {}.'.format(self.epoch, self.filename))
+
+    def load_state(self, filename=None):
+        source = self.filename if filename is None else filename
+        ckpt = torch.load(source, map_location=self.device, weights_only=False)
+        if filename is None:
+            self.epoch = ckpt['epoch']
+            self.Loss_real[:self.epoch] = ckpt['Loss_real']
+            self.Loss_fake[:self.epoch] = ckpt['Loss_fake']
+            self.Loss_G[:self.epoch] = ckpt['Loss_G']
+            self.Loss_D[:self.epoch] = ckpt['Loss_D']
+        if 'Generator_attrs' in ckpt and 'Discriminator_attrs' in ckpt:
+            gen_attrs = {k: v for k, v in ckpt['Generator_attrs'].items() if k in self.Generator_net.saved_attrs}
+            dis_attrs = {k: v for k, v in ckpt['Discriminator_attrs'].items()
+                         if k in self.Discriminator_net.saved_attrs}
+            if hasattr(self.Generator_net, 'set_resolution'):
+                res, alpha = gen_attrs['image_size'], float(gen_attrs['alpha'])
+                self.Generator_net.set_resolution(res, alpha)
+                self.Discriminator_net.set_resolution(res, alpha)
+            dev_g = next(self.Generator_net.parameters()).device
+            for attrs in (gen_attrs, dis_attrs):
+                if torch.is_tensor(attrs.get('alpha')):
+                    attrs['alpha'] = attrs['alpha'].to(dev_g)
+            set_saved_attrs(self.Generator_net, gen_attrs)
+            set_saved_attrs(self.Discriminator_net, dis_attrs)
+        gen = self.Generator_net.from_state_dict(source, verbose=False)
+        dis = self.Discriminator_net.from_state_dict(source, verbose=False)
+        self.Generator_net.load_state_dict(gen.state_dict(), strict=False)
+        self.Discriminator_net.load_state_dict(dis.state_dict(), strict=False)
+        if self.verbose and filename is None:
+            print('Loaded training state from {}'.format(self.filename))
+        elif self.verbose:
+            print('Loaded weights from {}'.format(filename))
+
+
+def save_vars(variables: dict, directory='./saved_vars', verbose=True):
+    """NaN-guard dump (reference utils.py:308-342): pickles the tensors / numbers found in `variables`."""
+    os.makedirs(directory, exist_ok=True)
+    stamp = datetime.datetime.now().strftime('%Y%m%d_%H%M%S')
+    path = os.path.join(directory, f'vars_{stamp}.pkl')
+    keep = {}
+    for k, v in variables.items():
+        if torch.is_tensor(v):
+            keep[k] = v.detach().cpu()
+        elif isinstance(v, (int, float, str, np.ndarray)):
+            keep[k] = v
+    with open(path, 'wb') as f:
+        pickle.dump(keep, f)
+    if verbose:
+        print(f'Variables saved in:\n{path}')
+    return path
+
+
+# ----------------------------------------------------------------------------------------------- testing
+def gen_samples(Generator: nn.Module, N_images=16, seed=None, chunk=256):
+    """Generator-only inference (reference utils.py:346-355), chunked so 4096 samples at 512x512 fit."""
+    dev = next(Generator.parameters()).device
+    z_latent = sample_latent_vec((N_images, Generator.latent_dim), seed=seed, device=dev)
+    with torch.no_grad():
+        images = torch.cat([Generator(z_latent[i:i + chunk]) for i in range(0, N_images, chunk)]).detach()
+    return images, z_latent
+
+
+def plot_gen_samples(Generator: nn.Module, eval_noise=None, N_images=16, seed=None, filename=None):
+    """Sample grid PNG (reference utils.py:568-610): nearest-upsample to image_size_max, nrow=round(sqrt(N)),
+    normalize=True.  Needs `filename` (the reference's matplotlib display path is out of scope)."""
+    was_training = Generator.training
+    Generator.train(False)
+    if eval_noise is None:
+        images, _ = gen_samples(Generator, N_images, seed=seed)
+    else:
+        with torch.no_grad():
+            images = Generator(eval_noise).detach()
+        N_images = images.size(0)
+    Generator.train(was_training)
+    n_rows = int(np.round(np.sqrt(N_images)))
+    images = images.cpu()
+    if images.size(-1) != Generator.image_size_max:
+        size = (Generator.image_size_max, Generator.image_size_max)
+        images = nn.functional.interpolate(images, size=size)
+    if filename is None:
+        raise ValueError('plot_gen_samples needs a filename (interactive display is not part of this build)')
+    import torchvision
+    torchvision.utils.save_image(images, filename, nrow=n_rows, normalize=True)
+    return images
