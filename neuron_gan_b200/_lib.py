@@ -63,8 +63,39 @@ def load():
     return lib
 
 
+# kernels launched per C-ABI call (everything not listed launches exactly one)
+_LAUNCHES = {'ngan_gp_loss': 2}
+launch_count = 0          # running count of kernels launched through this binding (bench.py reads it)
+_profile = None           # when a list: (name, int args, start event, end event) per call
+
+
+def start_profile():
+    """Record a CUDA event pair around every call (bench.py's per-kernel timing pass; perturbs throughput)."""
+    global _profile
+    _profile = []
+
+
+def stop_profile():
+    """Returns [(name, int-args tuple, milliseconds)] and disables profiling. Synchronises."""
+    global _profile
+    import torch
+    torch.cuda.synchronize()
+    out = [(n, a, e0.elapsed_time(e1)) for n, a, e0, e1 in _profile]
+    _profile = None
+    return out
+
+
 def call(name, *args):
+    global launch_count
     lib = load()
+    if _profile is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise NganError(f'{name} failed ({rc}): {lib.ngan_last_error().decode()}')
+    launch_count += _LAUNCHES.get(name, 1)
+    if _profile is not None:
+        e1.record()
+        _profile.append((name, tuple(a for a in args if isinstance(a, int)), e0, e1))

@@ -128,7 +128,7 @@ class _WLossFn(Function):
         ctx.g = torch.cat([g_real, g_fake]).unsqueeze(1)
         ctx.B = B
         ctx.set_materialize_grads(False)
-        return out3[0], out3[1], out3[2]
+        return out3[0].clone(), out3[1].clone(), out3[2].clone()   # callers do `D_loss += pen` in place
 
     @staticmethod
     @once_differentiable

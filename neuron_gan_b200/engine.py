@@ -28,7 +28,19 @@ F32 = torch.float32
 # ---------------------------------------------------------------------------------------------------------
 # bf16 operand images of the fp32 master weights, refreshed when the master changes
 # ---------------------------------------------------------------------------------------------------------
-_weight_cache = weakref.WeakKeyDictionary()
+_weight_cache = {}          # id(param) -> entry; entries die with their parameter
+
+
+def _cache_get(w):
+    ent = _weight_cache.get(id(w))
+    return ent if ent is not None and ent['ref']() is w else None
+
+
+def _cache_set(w, ent):
+    if _cache_get(w) is None:
+        weakref.finalize(w, _weight_cache.pop, id(w), None)
+    ent['ref'] = weakref.ref(w)
+    _weight_cache[id(w)] = ent
 
 
 def _wkey(w):
@@ -38,24 +50,24 @@ def _wkey(w):
 def conv_images(conv):
     """(forward image, data-gradient image) of a Conv2d_normalized 3x3 weight."""
     w = conv.weight
-    ent = _weight_cache.get(w)
+    ent = _cache_get(w)
     key = _wkey(w)
     if ent is None or ent['key'] != key:
         bufs = (ent['fwd'], ent['dgrad']) if ent is not None and ent['fwd'].device == w.device else (None, None)
         fwd, dgrad = ops.prep_conv_weight(w.detach(), *bufs)
         ent = {'key': key, 'fwd': fwd, 'dgrad': dgrad}
-        _weight_cache[w] = ent
+        _cache_set(w, ent)
     return ent['fwd'], ent['dgrad']
 
 
 def linear_shadow(lin, allocate_only=False):
     """bf16 copy of the generator's Linear_normalized weight (same [out, in] layout)."""
     w = lin.weight
-    ent = _weight_cache.get(w)
+    ent = _cache_get(w)
     key = _wkey(w)
     if ent is None or ent['shadow'].device != w.device:
         ent = {'key': None, 'shadow': torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)}
-        _weight_cache[w] = ent
+        _cache_set(w, ent)
     if allocate_only:
         return ent
     if ent['key'] != key:
@@ -68,7 +80,7 @@ def mark_updated(param, shadow_is_fresh=False):
     """Called by the fused optimiser after it changed `param` through a raw pointer."""
     param._ngan_epoch = getattr(param, '_ngan_epoch', 0) + 1
     if shadow_is_fresh:
-        ent = _weight_cache.get(param)
+        ent = _cache_get(param)
         if ent is not None and 'shadow' in ent:
             ent['key'] = _wkey(param)
 

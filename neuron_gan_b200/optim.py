@@ -33,7 +33,7 @@ class FusedAdam(torch.optim.Optimizer):
                 t = st['step']
                 shadow = None
                 if p.dim() == 2:              # the generator's Linear weight keeps a same-layout bf16 shadow
-                    ent = engine._weight_cache.get(p)
+                    ent = engine._cache_get(p)
                     if ent is not None and 'shadow' in ent:
                         shadow = ent['shadow']
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()

@@ -73,6 +73,37 @@ def conv_scale(weight: torch.Tensor, leak: float) -> float:
 
 
 # ----------------------------------------------------------------------------------------------
+# optional emulation of the CUDA path's storage precision (test aid, off by default)
+# ----------------------------------------------------------------------------------------------
+_EMULATE_BF16 = False
+
+
+class emulate_bf16:
+    """Context manager: round conv/linear weights and every stored feature map to bf16 (straight-through in
+    backward), i.e. the places where the CUDA path keeps bf16 in HBM.  With it the oracle reproduces the
+    LeakyReLU-mask flips that bf16 operands cause, so end-to-end GRADIENTS of the CUDA path can be compared
+    at a few-percent tolerance; without it only losses and per-layer outputs are comparable.
+    The reference itself is fp32: this mode is never used for the reference-pinned golden checks."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        global _EMULATE_BF16
+        self.prev, _EMULATE_BF16 = _EMULATE_BF16, self.on
+
+    def __exit__(self, *exc):
+        global _EMULATE_BF16
+        _EMULATE_BF16 = self.prev
+
+
+def _q(x):
+    if not _EMULATE_BF16:
+        return x
+    return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
+
+
+# ----------------------------------------------------------------------------------------------
 # building blocks
 # ----------------------------------------------------------------------------------------------
 
@@ -85,18 +116,21 @@ def pixel_norm(x: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
 def eq_conv(x, w, b=None, pad=1, leak=0.2):
     """Conv2d_normalized.forward (models.py:203-204): conv(scale * x, W) + b; bias is not scaled."""
     s = torch.tensor(conv_scale(w, leak), dtype=x.dtype)
+    if _EMULATE_BF16 and pad == 1:         # the 3x3 convs run on bf16 operands; the SxS head keeps fp32 weights
+        w = _q(w)
     return F.conv2d(s * x, w, b, stride=1, padding=pad)
 
 
 def eq_linear(z, w, leak=0.2):
     """Linear_normalized.forward (models.py:240-241), no bias in G (models.py:299-300)."""
     s = torch.tensor(he_gain(leak) / math.sqrt(w.shape[1]), dtype=z.dtype)
-    return F.linear(s * z, w)
+    return F.linear(s * z, _q(w))
 
 
 def up2(x):
     """Interpolate(scale_factor=2, mode='bilinear') (models.py:78-89, 257, 335)."""
-    return F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=None)
+    y = F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=None)
+    return _q(y) if x.shape[1] > 1 else y      # feature maps are stored in bf16, 1-channel images in fp32
 
 
 def down2_bilinear(x):
@@ -106,12 +140,12 @@ def down2_bilinear(x):
 
 def clp(x, w, b, leak):
     """conv -> LeakyReLU -> PixelNorm (models.py:261-268, 312-316, 469-473)."""
-    return pixel_norm(F.leaky_relu(eq_conv(x, w, b, 1, leak), leak))
+    return _q(pixel_norm(F.leaky_relu(eq_conv(x, w, b, 1, leak), leak)))
 
 
 def scale_block(x, w1, w2, up: bool, leak):
     """Conv2d_scale_block (models.py:245-268): resample first, then two conv/lrelu/PN stages."""
-    x = up2(x) if up else F.avg_pool2d(x, 2)
+    x = up2(x) if up else _q(F.avg_pool2d(x, 2))
     return clp(clp(x, w1, None, leak), w2, None, leak)
 
 
@@ -136,7 +170,7 @@ def g_forward(p: dict, z, n_layers: int, alpha: float, arch: Arch):
     alpha < 1: levels 0..n-2 are the stable trunk, level n-1 is being faded in."""
     leak, s0, f0 = arch.leak, arch.size_init, arch.gen_features[0]
     x = eq_linear(z, p['lin.w'], leak).unflatten(1, (f0, s0, s0))          # models.py:299-302
-    x = pixel_norm(F.leaky_relu(x, leak))                                   # models.py:310-311
+    x = _q(pixel_norm(F.leaky_relu(x, leak)))                               # models.py:310-311
     x = clp(x, p['conv0.w'], None, leak)                                    # models.py:312-316
     n_trunk = n_layers - 1 if alpha >= 1 else n_layers - 2
     for i in range(1, n_trunk + 1):
@@ -156,11 +190,13 @@ def d_forward(p: dict, x, n_layers: int, alpha: float, arch: Arch):
     if alpha >= 1:
         y = from_image(x, p[f'from{top}.w'], p[f'from{top}.b'])             # models.py:524
         first_blk = top
+        if first_blk == L - 1:
+            y = _q(y)         # (bf16 emulation only) no block follows: FromImage's output is what gets stored
     else:
         y_start = from_image(down2_bilinear(x), p[f'from{top + 1}.w'], p[f'from{top + 1}.b'])
         y_end = scale_block(from_image(x, p[f'from{top}.w'], p[f'from{top}.b']),
                             p[f'blk{top}.w1'], p[f'blk{top}.w2'], False, leak)
-        y = y_start + alpha * (y_end - y_start)                             # models.py:519-521
+        y = _q(y_start + alpha * (y_end - y_start))                         # models.py:519-521
         first_blk = top + 1
     for i in range(first_blk, L - 1):
         y = scale_block(y, p[f'blk{i}.w1'], p[f'blk{i}.w2'], False, leak)

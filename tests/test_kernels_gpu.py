@@ -224,9 +224,10 @@ def test_fromim_toim(C):
     assert rel(gw, (gpre_ref.unsqueeze(1) * y).sum((0, 2, 3))) < 1e-4
 
 
-def test_head():
+@pytest.mark.parametrize('B', [1, 5])
+def test_head(B):
     o = ops()
-    B, C, S = 5, 128, 16
+    C, S = 128, 16
     h = rnd(B, C, S, S, seed=24)
     y, r = pn_ref(F.leaky_relu(h, LEAK))
     y = bf(y)
