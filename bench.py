@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument('--cpu-batch', type=int, default=0, help='batch of the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true', help='skip the per-kernel timing pass (roofline)')
+    ap.add_argument('--dump-kernels', default='', help='write the full per-kernel table of the timing pass here')
     return ap.parse_args()
 
 
@@ -264,6 +265,23 @@ def run_b200(args):
             e[1] += 1
         total = sum(e[0] for e in agg.values())
         top = sorted(agg.values(), key=lambda e: -e[0])
+        if args.dump_kernels:
+            fam = {}
+            for tot, cnt, name, a in top:
+                f = fam.setdefault(name, [0.0, 0])
+                f[0] += tot
+                f[1] += cnt
+            with open(args.dump_kernels, 'w') as fh:
+                fh.write(f'# per-kernel CUDA-event timing pass, {n_prof} steps, total {total / n_prof:.3f} ms/step\n')
+                fh.write('# family,share,ms_per_step,launches_per_step\n')
+                for name, (tot, cnt) in sorted(fam.items(), key=lambda kv: -kv[1][0]):
+                    fh.write(f'{name},{tot / total:.4f},{tot / n_prof:.4f},{cnt // n_prof}\n')
+                fh.write('# kernel,dims,share,launches_per_step,avg_us,GBps,TFLOPs\n')
+                for tot, cnt, name, a in top:
+                    by, fl = algorithmic_bytes(name, a), conv_flops(name, a)
+                    avg_s = tot / cnt * 1e-3
+                    fh.write(f'{name},{"x".join(map(str, a[-5:]))},{tot / total:.4f},{cnt // n_prof},{avg_s * 1e6:.1f},'
+                             f'{by / avg_s / 1e9 if by else 0:.0f},{fl / avg_s / 1e12 if fl else 0:.1f}\n')
         for tot, cnt, name, a in top[:8]:
             by, fl = algorithmic_bytes(name, a), conv_flops(name, a)
             avg_s = tot / cnt * 1e-3

@@ -129,9 +129,14 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
         __syncthreads();  // everyone is done with this stage before it is refilled two iterations later
     }
 
-    // ---- flush: acc[tap][nb] = D[co = g (+8)][ci = nb*8 + 2t (+1)]
+    // ---- flush: acc[tap][nb] = D[co = g (+8)][ci = nb*8 + 2t (+1)].  The row-split warps of a block first
+    // combine in shared memory (the operand stages are drained by now), then the CTA issues one global atomic
+    // per output element.
+    float* s_red = reinterpret_cast<float*>(smem);   // [n_blk][9][16][16]
     const int g = lane >> 2, t = lane & 3;
-    const int co0 = co_group * a.co_g + cob * 16, ci0 = ci_group * a.ci_g + cib * 16;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_blk * 2304; i += blockDim.x) s_red[i] = 0.f;
+    __syncthreads();
     if (it > 0) {
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap)
@@ -139,10 +144,19 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
             for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int co = co0 + g + (k >> 1) * 8;
-                    const int ci = ci0 + nb * 8 + 2 * t + (k & 1);
-                    atomicAdd(a.dw + (static_cast<size_t>(co) * a.cin + ci) * 9 + tap, a.scale * acc[tap][nb][k]);
+                    const int co = g + (k >> 1) * 8;
+                    const int ci = nb * 8 + 2 * t + (k & 1);
+                    atomicAdd(s_red + ((blk * 9 + tap) * 16 + co) * 16 + ci, acc[tap][nb][k]);
                 }
+    }
+    __syncthreads();
+    if (it > 0) {
+        for (int i = threadIdx.x; i < n_blk * 2304; i += blockDim.x) {
+            const int ci = i & 15, co = (i >> 4) & 15, tap = (i >> 8) % 9, b = i / 2304;
+            const int co_abs = co_group * a.co_g + (b / n_ci_blk) * 16 + co;
+            const int ci_abs = ci_group * a.ci_g + (b % n_ci_blk) * 16 + ci;
+            atomicAdd(a.dw + (static_cast<size_t>(co_abs) * a.cin + ci_abs) * 9 + tap, a.scale * s_red[i]);
+        }
     }
 }
 
@@ -175,7 +189,9 @@ int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int B, 
     a.g_stage_bytes = ((a.co_g / 8) * g_plane + 127) & ~127u;
     a.scale = scale;
     a.dw = dw;
-    const uint32_t smem_bytes = 2 * a.x_stage_bytes + 2 * a.g_stage_bytes + 16 + 128;
+    const uint32_t stage_total = 2 * a.x_stage_bytes + 2 * a.g_stage_bytes + 16;
+    const uint32_t red_bytes = static_cast<uint32_t>(n_blk) * 2304 * sizeof(float);   // flush buffer aliases the stages
+    const uint32_t smem_bytes = (stage_total > red_bytes ? stage_total : red_bytes) + 128;
 
     CUtensorMap tmx, tmg;
     int rc = make_c8_tensor_map(&tmx, x, B, cin, H, W, a.TW + 2, kWgTH + 2, a.ci_g / 8);

@@ -87,7 +87,8 @@ def test_train_step_losses_match_reference(golden, key):
             seen.add(name)
             ratio = p.grad.double().norm().item() / max(refg[name]['norm'], 1e-30)
             worst = max(worst, abs(ratio - 1))
-            assert 0.2 < ratio < 5.0, (name, ratio)       # conditioning-limited, see the emulating-oracle test
+            lo, hi = (0.4, 2.5) if res <= 128 else (0.1, 10.0)    # conditioning-limited at depth, see the
+            assert lo < ratio < hi, (name, ratio)                 # emulating-oracle test for the tight check
         assert seen == set(refg.keys())
     print(f'{key}: worst grad-norm deviation {worst:.3%}; stats {stats}')
     # after the two Adam steps the parameters moved like the reference's
