@@ -354,42 +354,44 @@ static int pow2_cols(int n) {
     return c;
 }
 
-static bool plan_tiles(int H, int W, int cin, int cout, TilePlan* p) {
+static bool plan_tiles(int B, int H, int W, int cin, int cout, TilePlan* p) {
     const int kSmemMax = 220 * 1024, kSmemSoft = 108 * 1024;
     const int w_tap = cin * cout * 2;
     int TW = W < 64 ? W : 64;
     int Wh = TW + 2;
+    const int tiles_x = (W + TW - 1) / TW;
     int mt_cap = 256 / cout;
     if (mt_cap < 1) mt_cap = 1;
     if (mt_cap > 8) mt_cap = 8;
-    int th_max = (mt_cap * 128) / Wh;
-    if (th_max < 1) th_max = 1;
-    if (th_max > H) th_max = H;
-    for (int th_cap = th_max; th_cap >= 1; --th_cap) {
-        int n_tiles = (H + th_cap - 1) / th_cap;
-        int TH = (H + n_tiles - 1) / n_tiles;
-        uint32_t plane = static_cast<uint32_t>(TH + 2) * Wh * 16;
-        uint32_t in_bytes = ((cin / 8) * plane + 256 + 127) & ~127u;
-        uint32_t fixed = in_bytes + 128 /*align slack*/ + (2 + 2 * kMaxStages) * 8 + 16;
-        int budget = (fixed + 2 * w_tap <= (uint32_t)kSmemSoft) ? kSmemSoft : kSmemMax;
+    bool have = false;
+    // Largest tile first; shrink the tile (fewer M-tiles per CTA) while the grid would leave SMs idle.
+    for (int mt = mt_cap; mt >= 1; --mt) {
+        int th_cap = (mt * 128) / Wh;
+        if (th_cap < 1) th_cap = 1;
+        if (th_cap > H) th_cap = H;
+        const int n_tiles = (H + th_cap - 1) / th_cap;
+        const int TH = (H + n_tiles - 1) / n_tiles;
+        const uint32_t plane = static_cast<uint32_t>(TH + 2) * Wh * 16;
+        const uint32_t in_bytes = ((cin / 8) * plane + 256 + 127) & ~127u;
+        const uint32_t fixed = in_bytes + 128 /*align slack*/ + (2 + 2 * kMaxStages) * 8 + 16;
+        const int budget = (fixed + 2 * w_tap <= (uint32_t)kSmemSoft) ? kSmemSoft : kSmemMax;
         int stages = (budget - (int)fixed) / w_tap;
         if (stages > 9) stages = 9;
-        if (stages < 2) {
-            if (th_cap == 1) return false;
-            continue;
-        }
+        const int nMT = (TH * Wh + 127) / 128;
+        const int cols = pow2_cols(nMT * cout);
+        if (stages < 2 || cols > 512) continue;
         p->TH = TH;
         p->TW = TW;
         p->Wh = Wh;
-        p->nMT = (TH * Wh + 127) / 128;
-        p->tmem_cols = pow2_cols(p->nMT * cout);
-        if (p->tmem_cols > 512) continue;
+        p->nMT = nMT;
+        p->tmem_cols = cols;
         p->n_stage = stages;
         p->plane_bytes = plane;
         p->smem_bytes = fixed + stages * w_tap;
-        return true;
+        have = true;
+        if (static_cast<long long>(B) * n_tiles * tiles_x >= 148) break;
     }
-    return false;
+    return have;
 }
 
 template <int CIN, int COUT, int EPI>
@@ -420,7 +422,7 @@ int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, 
                      float leak, const float* bias, void* out0, void* out1, float* rout, const void* y,
                      const float* r, const void* gy, const void* addin, cudaStream_t st) {
     TilePlan plan;
-    if (!plan_tiles(H, W, cin, cout, &plan)) {
+    if (!plan_tiles(B, H, W, cin, cout, &plan)) {
         set_error("conv3x3: no tile plan for H=%d W=%d cin=%d cout=%d", H, W, cin, cout);
         return NGAN_ERR_UNSUPPORTED;
     }

@@ -42,9 +42,12 @@ __global__ void __launch_bounds__(256) linear_fwd_pn_kernel(const float* __restr
     float* sr = sa + C * kLinBT;  // [kLinBT]
     const int p = blockIdx.x, b0 = blockIdx.y * kLinBT;
     const int nb = min(kLinBT, B - b0);
+    // sz[bb][j][lane] = scale * z[b0+bb][lane*KPL + j]: lane-interleaved so the inner product below reads
+    // consecutive banks (a plain [bb][k] layout makes the 32 lanes stride 16 floats: 16-way bank conflicts)
     for (int i = threadIdx.x; i < kLinBT * K; i += blockDim.x) {
-        const int bb = i / K;
-        sz[i] = bb < nb ? z[static_cast<size_t>(b0 + bb) * K + (i % K)] * scale : 0.f;
+        const int bb = i / K, k = i % K;
+        const float v = bb < nb ? z[static_cast<size_t>(b0 + bb) * K + k] * scale : 0.f;
+        sz[bb * K + (k % (K / 32)) * 32 + k / (K / 32)] = v;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -56,10 +59,10 @@ __global__ void __launch_bounds__(256) linear_fwd_pn_kernel(const float* __restr
         for (int q = 0; q < KPL / 8; ++q) unpack8(__ldg(reinterpret_cast<const uint4*>(row) + q), wv + q * 8);
 #pragma unroll 4
         for (int bb = 0; bb < kLinBT; ++bb) {
-            const float* zz = sz + bb * K + lane * KPL;
+            const float* zz = sz + bb * K + lane;
             float acc = 0.f;
 #pragma unroll
-            for (int k = 0; k < KPL; ++k) acc += wv[k] * zz[k];
+            for (int k = 0; k < KPL; ++k) acc += wv[k] * zz[k * 32];
             acc = warp_sum(acc);
             if (lane == 0) sa[c * kLinBT + bb] = acc > 0.f ? acc : leak * acc;
         }

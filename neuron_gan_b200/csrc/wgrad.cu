@@ -206,8 +206,11 @@ int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int B, 
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(wgrad)");
         configured = true;
     }
+    // CTAs per channel group: fill the machine, but keep >= 8 tiles per CTA when the problem is small so the
+    // per-CTA flush (n_blk * 2304 atomics) does not dominate the few MMAs a tile needs.
     int per_group = (2 * 148 + n_groups - 1) / n_groups;
-    if (per_group > a.n_tiles) per_group = a.n_tiles;
+    const int by_work = (a.n_tiles + 7) / 8;
+    if (per_group > by_work) per_group = by_work;
     if (per_group < 1) per_group = 1;
     conv3x3_wgrad_kernel<<<dim3(per_group, n_groups), 256, smem_bytes, st>>>(tmx, tmg, a);
     return check_launch("conv3x3_wgrad");
