@@ -40,6 +40,7 @@ CONV_SHAPES = [  # B, cin, cout, H, W
     (2, 16, 16, 16, 16), (1, 16, 16, 64, 64), (2, 16, 32, 32, 32), (2, 32, 16, 32, 32), (1, 32, 32, 128, 128),
     (2, 32, 64, 32, 32), (2, 64, 32, 32, 32), (2, 64, 64, 32, 32), (2, 64, 128, 16, 16), (2, 128, 64, 32, 32),
     (3, 128, 128, 16, 16), (1, 16, 16, 256, 256), (1, 16, 16, 40, 72),
+    (9, 16, 16, 256, 256), (40, 32, 32, 64, 64), (48, 64, 64, 32, 32),     # several tiles per persistent CTA
 ]
 
 
@@ -116,7 +117,7 @@ def test_conv3x3_double_backward(B, cin, cout, H, W):
     assert rel(o.c8_to_nchw(ahat), cot_a) < 2e-2
 
 
-@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES[:12])
+@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES[:12] + CONV_SHAPES[13:14])
 def test_conv3x3_wgrad(B, cin, cout, H, W):
     o = ops()
     x = rnd(B, cin, H, W, seed=12)
