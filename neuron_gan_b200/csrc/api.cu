@@ -39,9 +39,16 @@ using namespace ngan;
         }                              \
     } while (0)
 
+namespace ngan { extern long long* g_conv_trace; }
+
 extern "C" {
 
 int ngan_version(void) { return 100; }
+// undocumented debug hook (NGAN_CONV_TRACE=1): copies the clock64() trace of the last folded-conv launch
+int ngan_debug_conv_trace(long long* host_out) {
+    if (!ngan::g_conv_trace) return -1;
+    return check_cuda(cudaMemcpy(host_out, ngan::g_conv_trace, 32 * 8 * sizeof(long long), cudaMemcpyDeviceToHost), "trace");
+}
 const char* ngan_last_error(void) { return g_err; }
 
 int ngan_nchw_to_c8(const float* src, void* dst, int B, int C, int H, int W, void* stream) {

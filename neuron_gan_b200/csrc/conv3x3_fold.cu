@@ -1,0 +1,410 @@
+// 3x3 convolution for the narrow layers (CIN*COUT <= 4096, i.e. the 16/32/64-channel layers that carry almost
+// all pixels of the 128^2..512^2 phases): persistent, warp-specialised, with the three horizontal taps folded
+// into the MMA's N dimension.
+//
+// Why folding: with N = COUT = 16 a tcgen05.mma (M=128, K=16) needs only 8 tensor cycles but must fetch a 4 KB
+// A slice from shared memory; the per-tap kernel re-reads the input tile nine times and ends up bound by the
+// shared-memory operand path (measured: 10 % tensor-pipe activity, 49 % of HBM bandwidth at 512^2).  Here one
+// MMA computes, for every haloed pixel q, the products with all three horizontal taps at once:
+//
+//     D'[m, kx*COUT + co] = sum_{ky, ci} X[q(m) + ky*Wh, ci] * W[co][ci][ky][kx]        (N = 3*COUT, 3 MMAs per K=16)
+//     out[m, co]          = D'[m, co] + D'[m+1, COUT + co] + D'[m+2, 2*COUT + co]       (epilogue)
+//
+// The vertical taps stay on the A side as descriptor start offsets (rows of the flattened haloed tile, as in
+// conv3x3_umma.cu); the horizontal taps become a shift between accumulator ROWS, i.e. TMEM lanes, which the
+// epilogue resolves with two warp shuffles per value.  Tiles are 30 pixels wide in a 32-wide haloed row, so one
+// warp owns exactly one tile row and lanes 30/31 -- the ones a shuffle cannot serve -- are halo columns anyway.
+// The input tile is fetched from shared memory 3x instead of 9x and each MMA does 3x the work.
+//
+// Roles (one CTA per SM, persistent over tiles): warp 0 = TMA producer (ring of haloed input tiles; the folded
+// weight image is loaded once per CTA), warps 1-2 = MMA issuers, one per TMEM accumulator buffer (even / odd
+// tiles), warps 3..18 = four epilogue groups draining the buffers (TMEM -> registers -> fused tail -> HBM).
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "conv_args.cuh"
+#include "kernels.h"
+
+namespace ngan {
+
+constexpr int kFoldTW = 30, kFoldWh = 32;
+constexpr int kFoldEpiGroups = 4;
+constexpr int kFoldMaxStages = 12;
+constexpr uint32_t kFoldBarBytes = (5 + 2 * kFoldMaxStages) * 8 + 16;
+constexpr int kFoldThreads = 96 + 128 * kFoldEpiGroups;   // producer + 2 MMA warps + epilogue groups
+
+// Fused pointwise tail on one output pixel held in registers (o[c] = raw accumulator sums).
+template <int COUT, int EPI>
+__device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool valid, size_t q0, size_t p0, size_t HW) {
+    constexpr int NCH = COUT / 8;
+    const float inv_c = 1.0f / COUT;
+    if constexpr (EPI == EPI_FWD_PN) {
+        float ss = 0.f;
+        float k;      // multiplier that turns the values kept in o[] into the PixelNorm output
+        float rinv;   // PixelNorm scale of the true pre-norm activation h = lrelu(scale*acc + bias)
+        if (a.bias == nullptr) {
+            // lrelu and PixelNorm commute with the positive scale: normalise lrelu(acc) directly
+            // (mean(h^2) + eps = scale^2 * (mean(v^2) + eps/scale^2)); saves one multiply per channel.
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) {
+                const float v = fmaxf(o[c], a.leak * o[c]);
+                ss = fmaf(v, v, ss);
+                o[c] = v;
+            }
+            const float inv_s = 1.0f / a.scale;
+            k = rsqrtf(ss * inv_c + 1e-8f * inv_s * inv_s);
+            rinv = k * inv_s;
+        } else {
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) {
+                const float x = fmaf(a.scale, o[c], __ldg(a.bias + c));
+                const float v = fmaxf(x, a.leak * x);
+                ss = fmaf(v, v, ss);
+                o[c] = v;
+            }
+            k = rinv = rsqrtf(ss * inv_c + 1e-8f);
+        }
+        if (valid) {
+            uint4* out = reinterpret_cast<uint4*>(a.out0) + q0;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[j * 8 + e] *= k;
+                out[j * HW] = pack8(o + j * 8);
+            }
+            if (a.rout) a.rout[p0] = rinv;
+        }
+    } else if constexpr (EPI == EPI_LINEAR) {
+        if (valid) {
+            uint4* out = reinterpret_cast<uint4*>(a.out0);
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[j * 8 + e] *= a.scale;
+                out[q0 + j * HW] = pack8(o + j * 8);
+            }
+        }
+    } else if constexpr (EPI == EPI_BWD_PN) {
+        // ga = mask(y) * r * (g - y*mean_c(g*y)) (+ addin), g = scale*acc     [SURVEY.md 8a row 3]
+        if (!valid) return;
+        const uint4* yq = reinterpret_cast<const uint4*>(a.y);
+        uint4 yp[NCH];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) yp[j] = __ldg(yq + q0 + j * HW);
+        const float rinv = __ldg(a.r + p0);
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            float yv[8];
+            unpack8(yp[j], yv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                o[j * 8 + e] *= a.scale;
+                t += o[j * 8 + e] * yv[e];
+            }
+        }
+        t *= inv_c;
+        uint4* out = reinterpret_cast<uint4*>(a.out0);
+        uint4* out1 = reinterpret_cast<uint4*>(a.out1);
+        const uint4* aq = reinterpret_cast<const uint4*>(a.addin);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            float yv[8], ad[8], ga[8];
+            unpack8(yp[j], yv);
+            if (aq) unpack8(__ldg(aq + q0 + j * HW), ad);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                ga[e] = lrelu_mask(yv[e], a.leak) * rinv * (o[j * 8 + e] - yv[e] * t) + (aq ? ad[e] : 0.f);
+            out[q0 + j * HW] = pack8(ga);
+            if (out1) out1[q0 + j * HW] = pack8(o + j * 8);
+        }
+    } else {  // EPI_DBL, formulas in conv3x3_umma.cu / SURVEY.md 8a row 3
+        if (!valid) return;
+        const uint4* yq = reinterpret_cast<const uint4*>(a.y);
+        const uint4* gq = reinterpret_cast<const uint4*>(a.gy);
+        uint4 yp[NCH], gp[NCH];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            yp[j] = __ldg(yq + q0 + j * HW);
+            gp[j] = __ldg(gq + q0 + j * HW);
+        }
+        const float rinv = __ldg(a.r + p0);
+        float t = 0.f, u = 0.f, w = 0.f;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            float yv[8], gv[8];
+            unpack8(yp[j], yv);
+            unpack8(gp[j], gv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float gh = lrelu_mask(yv[e], a.leak) * a.scale * o[j * 8 + e];
+                o[j * 8 + e] = gh;
+                t += gv[e] * yv[e];
+                u += gh * yv[e];
+                w += gh * gv[e];
+            }
+        }
+        t *= inv_c;
+        u *= inv_c;
+        w *= inv_c;
+        const float k3 = w - 3.f * u * t;
+        uint4* out0 = reinterpret_cast<uint4*>(a.out0);
+        uint4* out1 = reinterpret_cast<uint4*>(a.out1);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            float yv[8], gv[8], o0[8], o1[8];
+            unpack8(yp[j], yv);
+            unpack8(gp[j], gv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float gh = o[j * 8 + e];
+                o0[e] = rinv * (gh - yv[e] * u);
+                o1[e] = -lrelu_mask(yv[e], a.leak) * rinv * rinv * (t * gh + u * gv[e] + k3 * yv[e]);
+            }
+            out0[q0 + j * HW] = pack8(o0);
+            out1[q0 + j * HW] = pack8(o1);
+        }
+    }
+}
+
+template <int CIN, int COUT, int EPI>
+__global__ void __launch_bounds__(kFoldThreads) conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                    const ConvArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int NF = 3 * COUT;                       // MMA N: (kx, co)
+    constexpr uint32_t W_BYTES = 9 * CIN * COUT * 2;   // [3 ky][CIN/8][NF][8] bf16
+    constexpr uint32_t IDESC = umma_idesc_bf16(128, NF);
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const uint32_t in_bytes = (CIN / 8) * a.plane_bytes;   // plane = (TH+2)*32*16, a multiple of 128
+    uint8_t* s_in = smem;
+    uint8_t* s_w = smem + a.n_stage * in_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + ((W_BYTES + 127) & ~127u));
+    uint64_t* bar_w = bars;
+    uint64_t* bar_full = bars + 1;            // [n_stage <= kFoldMaxStages]
+    uint64_t* bar_empty = bars + 1 + kFoldMaxStages;
+    uint64_t* bar_acc_full = bars + 1 + 2 * kFoldMaxStages;        // [2]
+    uint64_t* bar_acc_empty = bars + 3 + 2 * kFoldMaxStages;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kFoldMaxStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t buf_cols = a.tmem_cols / 2;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmap);
+        mbar_init(bar_w, 1);
+        for (int s = 0; s < a.n_stage; ++s) {
+            mbar_init(bar_full + s, 1);
+            mbar_init(bar_empty + s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_acc_full + s, 1);
+            mbar_init(bar_acc_empty + s, 4 * kFoldEpiGroups);   // one arrival per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_w, W_BYTES);
+            bulk_load_1d(s_w, a.wprep, W_BYTES, bar_w);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+                const int stage = it % a.n_stage;
+                if (it >= a.n_stage) mbar_wait(bar_empty + stage, ((it / a.n_stage) - 1) & 1);
+                const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
+                const int tile_y = t2 / a.tiles_x, tile_x = t2 - tile_y * a.tiles_x;
+                if ((a.debug & 4) && it >= a.n_stage) {
+                    mbar_arrive(bar_full + stage);       // timing experiment: reuse whatever is in the stage
+                    continue;
+                }
+                mbar_arrive_expect_tx(bar_full + stage, in_bytes);
+                tma_load_4d(s_in + stage * in_bytes, &tmap, bar_full + stage, (tile_x * kFoldTW - 1) * 2,
+                            tile_y * a.TH - 1, 0, b);
+            }
+        }
+    } else if (warp <= 2) {
+        // Two MMA-issuing warps, one per accumulator buffer (even / odd tiles): while one is parked in the
+        // mbarrier waits of its next tile (a few hundred cycles each, even when already complete) the other
+        // keeps the tensor core fed.
+        if (lane == 0) {
+            mbar_wait(bar_w, 0);
+            const uint32_t w_base = smem_u32(s_w);
+            for (int it = warp - 1, tile = blockIdx.x + (warp - 1) * gridDim.x; tile < a.n_tiles;
+                 tile += 2 * gridDim.x, it += 2) {
+                const int stage = it % a.n_stage, buf = it & 1;
+                const bool trace = a.dbg_clock && blockIdx.x == 0 && it < 32;
+                if (trace) a.dbg_clock[it * 8 + 0] = clock64();
+                if (it >= 2) mbar_wait(bar_acc_empty + buf, ((it >> 1) - 1) & 1);
+                if (trace) a.dbg_clock[it * 8 + 1] = clock64();
+                mbar_wait(bar_full + stage, (it / a.n_stage) & 1);
+                tc_fence_after();
+                if (trace) a.dbg_clock[it * 8 + 2] = clock64();
+                const uint32_t in_base = smem_u32(s_in + stage * in_bytes);
+                const uint32_t acc = tmem_base + buf * buf_cols;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    if (a.debug & 1) break;
+#pragma unroll
+                    for (int kc = 0; kc < CIN / 16; ++kc) {
+                        const uint32_t a_addr = in_base + (2 * kc) * a.plane_bytes + ky * kFoldWh * 16;
+                        const uint64_t bdesc = umma_desc(w_base + (ky * (CIN / 8) + 2 * kc) * NF * 16, NF * 16, 128);
+                        uint64_t adesc = umma_desc(a_addr, a.plane_bytes, 128);
+                        for (int mt = 0; mt < a.nMT; ++mt) {
+                            umma_bf16(acc + mt * NF, adesc, bdesc, IDESC, (ky | kc) != 0);
+                            adesc += (128 * 16) >> 4;      // next M-tile: 128 rows further (start-address field)
+                        }
+                    }
+                }
+                if (trace) a.dbg_clock[it * 8 + 3] = clock64();
+                umma_commit(bar_empty + stage);
+                umma_commit(bar_acc_full + buf);
+                if (trace) a.dbg_clock[it * 8 + 4] = clock64();
+            }
+        }
+    } else {
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+        const int group = (warp - 3) >> 2;         // epilogue group: M-tiles are interleaved between the groups
+        const size_t HW = static_cast<size_t>(a.H) * a.W;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
+            const int tile_y = t2 / a.tiles_x, tile_x = t2 - tile_y * a.tiles_x;
+            const bool trace = a.dbg_clock && blockIdx.x == 0 && it < 32 && warp == 3 && lane == 0;
+            if (trace) a.dbg_clock[it * 8 + 5] = clock64();
+            mbar_wait(bar_acc_full + buf, (it >> 1) & 1);
+            __syncwarp();
+            tc_fence_after();
+            if (trace) a.dbg_clock[it * 8 + 6] = clock64();
+            const int ox = tile_x * kFoldTW + lane;
+            for (int mt = group; mt < ((a.debug & 2) ? 0 : a.nMT); mt += kFoldEpiGroups) {
+                const int rr = mt * 4 + quad;      // row of the tile (Wh = 32: one warp = one row)
+                const int oy = tile_y * a.TH + rr;
+                const bool valid = (lane < kFoldTW) && (rr < a.TH) && (oy < a.H) && (ox < a.W);
+                const uint32_t taddr = tmem_base + buf * buf_cols + (static_cast<uint32_t>(quad * 32) << 16) + mt * NF;
+                float o[COUT], v1[16], v2[16];
+#pragma unroll
+                for (int c0 = 0; c0 < COUT; c0 += 16) {
+                    tmem_ld16_nowait(taddr + c0, o + c0);
+                    tmem_ld16_nowait(taddr + COUT + c0, v1);
+                    tmem_ld16_nowait(taddr + 2 * COUT + c0, v2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        o[c0 + i] += __shfl_down_sync(0xffffffffu, v1[i], 1) + __shfl_down_sync(0xffffffffu, v2[i], 2);
+                }
+                const size_t q0 = static_cast<size_t>(b) * (COUT / 8) * HW + static_cast<size_t>(oy) * a.W + ox;
+                const size_t p0 = static_cast<size_t>(b) * HW + static_cast<size_t>(oy) * a.W + ox;
+                conv_tail<COUT, EPI>(a, o, valid, q0, p0, HW);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty + buf);
+            if (trace) a.dbg_clock[it * 8 + 7] = clock64();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+long long* g_conv_trace = nullptr;
+static int pow2_cols(int n) {
+    int c = 32;
+    while (c < n) c <<= 1;
+    return c;
+}
+
+template <int CIN, int COUT, int EPI>
+static int launch_fold(const CUtensorMap& tmap, const ConvArgs& a, uint32_t smem_bytes, int n_ctas, cudaStream_t st) {
+    auto kern = conv3x3_fold_kernel<CIN, COUT, EPI>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv3x3_fold)");
+        configured = true;
+    }
+    kern<<<n_ctas, kFoldThreads, smem_bytes, st>>>(tmap, a);
+    return check_launch("conv3x3_fold");
+}
+
+#define NGAN_FOLD_CASE(CI, CO)                                                                       \
+    if (cin == CI && cout == CO) {                                                                   \
+        switch (epi) {                                                                               \
+            case EPI_FWD_PN: return launch_fold<CI, CO, EPI_FWD_PN>(tmap, a, smem_bytes, n_ctas, st); \
+            case EPI_LINEAR: return launch_fold<CI, CO, EPI_LINEAR>(tmap, a, smem_bytes, n_ctas, st); \
+            case EPI_BWD_PN: return launch_fold<CI, CO, EPI_BWD_PN>(tmap, a, smem_bytes, n_ctas, st); \
+            case EPI_DBL: return launch_fold<CI, CO, EPI_DBL>(tmap, a, smem_bytes, n_ctas, st);       \
+        }                                                                                            \
+    }
+
+int conv3x3_fold_dispatch(int epi, const void* x, ConvArgs a, int B, int cin, int cout, int H, int W,
+                          cudaStream_t st) {
+    const int NF = 3 * cout;
+    // M-tiles (4 tile rows each) per CTA tile: two accumulator buffers of nMT*NF columns must fit in 512 columns
+    int nMT = 256 / NF;
+    if (nMT > 4) nMT = 4;
+    if (nMT < 1) nMT = 1;
+    const int tiles_x = (W + kFoldTW - 1) / kFoldTW;
+    // shrink tiles while the grid cannot give every SM a couple of tiles
+    while (nMT > 1 && static_cast<long long>(B) * ((H + 4 * nMT - 1) / (4 * nMT)) * tiles_x < 2 * 148) --nMT;
+    int TH = 4 * nMT;
+    if (TH > H) TH = (H + 3) / 4 * 4;
+    nMT = TH / 4;
+    static const int dbg = getenv("NGAN_CONV_DEBUG") ? atoi(getenv("NGAN_CONV_DEBUG")) : 0;
+    a.debug = dbg;
+    static long long* dbg_buf = nullptr;
+    if (getenv("NGAN_CONV_TRACE") && !dbg_buf) cudaMalloc(&dbg_buf, 32 * 8 * sizeof(long long));
+    a.dbg_clock = dbg_buf;
+    g_conv_trace = dbg_buf;
+    a.TH = TH; a.TW = kFoldTW; a.Wh = kFoldWh; a.nMT = nMT;
+    a.tmem_cols = pow2_cols(2 * nMT * NF);
+    if (a.tmem_cols > 512) {
+        set_error("conv3x3_fold: TMEM budget exceeded (cout=%d)", cout);
+        return NGAN_ERR_UNSUPPORTED;
+    }
+    a.plane_bytes = static_cast<uint32_t>(TH + 2) * kFoldWh * 16;
+    a.tiles_x = tiles_x;
+    a.tiles_y = (H + TH - 1) / TH;
+    a.n_tiles = a.tiles_x * a.tiles_y * B;
+    const uint32_t in_bytes = (cin / 8) * a.plane_bytes;
+    const uint32_t w_bytes = ((9u * cin * cout * 2) + 127) & ~127u;
+    // Deep ring: HBM needs ~100 KB of loads in flight per SM to run at full rate (latency x bandwidth), so the
+    // producer keeps as many haloed tiles outstanding as shared memory allows.
+    static const int max_stages = getenv("NGAN_FOLD_STAGES") ? atoi(getenv("NGAN_FOLD_STAGES")) : kFoldMaxStages;
+    int stages = max_stages < kFoldMaxStages ? max_stages : kFoldMaxStages;
+    while (stages > 2 && 128 + stages * in_bytes + w_bytes + kFoldBarBytes > 200u * 1024) --stages;
+    a.n_stage = stages;
+    const uint32_t smem_bytes = 128 + stages * in_bytes + w_bytes + kFoldBarBytes;
+    if (smem_bytes > 227u * 1024) {
+        set_error("conv3x3_fold: shared memory budget exceeded (cin=%d cout=%d)", cin, cout);
+        return NGAN_ERR_UNSUPPORTED;
+    }
+    const int n_ctas = a.n_tiles < 148 ? a.n_tiles : 148;
+
+    CUtensorMap tmap;
+    int rc = make_c8_tensor_map(&tmap, x, B, cin, H, W, kFoldWh, TH + 2, cin / 8);
+    if (rc) return rc;
+    NGAN_FOLD_CASE(16, 16)
+    NGAN_FOLD_CASE(16, 32)
+    NGAN_FOLD_CASE(32, 16)
+    NGAN_FOLD_CASE(32, 32)
+    NGAN_FOLD_CASE(32, 64)
+    NGAN_FOLD_CASE(64, 32)
+    NGAN_FOLD_CASE(64, 64)
+    set_error("conv3x3_fold: unsupported channel pair %d -> %d", cin, cout);
+    return NGAN_ERR_UNSUPPORTED;
+}
+
+}  // namespace ngan

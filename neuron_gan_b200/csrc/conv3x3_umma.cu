@@ -22,29 +22,10 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "conv_args.cuh"
 #include "kernels.h"
 
 namespace ngan {
-
-struct ConvArgs {
-    int B, H, W;
-    int TH, TW, Wh;
-    int nMT;
-    int tmem_cols;
-    int n_stage;
-    int tiles_x, tiles_y, n_tiles;  // persistent kernel: tile grid over (B, rows, cols)
-    uint32_t plane_bytes;  // (TH+2)*Wh*16
-    float scale, leak;
-    const __nv_bfloat16* wprep;  // [9][CIN/8][COUT][8]
-    const float* bias;           // FWD: [COUT] or null
-    __nv_bfloat16* out0;
-    __nv_bfloat16* out1;
-    float* rout;
-    const __nv_bfloat16* y;
-    const float* r;
-    const __nv_bfloat16* gy;
-    const __nv_bfloat16* addin;
-};
 
 constexpr int kMaxStages = 9;
 
@@ -293,8 +274,7 @@ __global__ void __launch_bounds__(128) conv3x3_umma_kernel(const __grid_constant
     }
 
     // ---- epilogue: every thread owns one accumulator row (= one output pixel, all COUT channels)
-    mbar_wait(bar_mma, 0);
-    __syncwarp();
+    mbar_wait_warp(bar_mma, 0, lane);
     tc_fence_after();
 
     conv_epilogue<COUT, EPI>(a, tmem_base, warp, lane, b, tile_x, tile_y);
@@ -304,126 +284,6 @@ __global__ void __launch_bounds__(128) conv3x3_umma_kernel(const __grid_constant
     if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
-
-// ------------------------------------------------------------------------------------------------------------
-// Persistent, warp-specialised variant for layers whose nine weight slabs fit in shared memory together
-// (CIN*COUT <= 4096): one CTA per SM slot loops over tiles; warp 0 streams haloed input tiles through a ring
-// of TMA stages, warp 1 issues the MMAs into one of two TMEM accumulator buffers, warps 2-5 drain the other
-// buffer through the fused epilogue.  Load, MMA and epilogue of consecutive tiles overlap.
-constexpr int kPersistThreads = 192;
-
-template <int CIN, int COUT, int EPI>
-__global__ void __launch_bounds__(kPersistThreads) conv3x3_umma_persist_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                                               const ConvArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    constexpr uint32_t W_BYTES = 9 * CIN * COUT * 2;
-    constexpr uint32_t IDESC = umma_idesc_bf16(128, COUT);
-
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    const uint32_t in_bytes = (CIN / 8) * a.plane_bytes;
-    const uint32_t stage_stride = (in_bytes + 256 + 127) & ~127u;
-    // Input stages first, weights after them: the last M-tile of a stage reads up to ~2 KB past the tile it was
-    // given (rows that are dropped in the epilogue); that over-read must stay inside this CTA's allocation.
-    uint8_t* s_in = smem;
-    uint8_t* s_w = smem + a.n_stage * stage_stride;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + ((W_BYTES + 127) & ~127u));
-    uint64_t* bar_w = bars;
-    uint64_t* bar_full = bars + 1;               // [n_stage]
-    uint64_t* bar_empty = bars + 1 + 4;          // [n_stage]
-    uint64_t* bar_acc_full = bars + 1 + 8;       // [2]
-    uint64_t* bar_acc_empty = bars + 1 + 10;     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t buf_cols = a.tmem_cols / 2;
-
-    if (threadIdx.x == 0) {
-        prefetch_tmap(&tmap);
-        mbar_init(bar_w, 1);
-        for (int s = 0; s < a.n_stage; ++s) {
-            mbar_init(bar_full + s, 1);
-            mbar_init(bar_empty + s, 1);
-        }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(bar_acc_full + s, 1);
-            mbar_init(bar_acc_empty + s, 4);     // one arrival per epilogue warp
-        }
-        mbar_fence_init();
-    }
-    __syncwarp();
-    if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const int tiles_per_img = a.tiles_x * a.tiles_y;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(bar_w, W_BYTES);
-            bulk_load_1d(s_w, a.wprep, W_BYTES, bar_w);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-                const int stage = it % a.n_stage;
-                if (it >= a.n_stage) mbar_wait(bar_empty + stage, ((it / a.n_stage) - 1) & 1);
-                const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
-                const int tile_y = t2 / a.tiles_x, tile_x = t2 - tile_y * a.tiles_x;
-                mbar_arrive_expect_tx(bar_full + stage, in_bytes);
-                tma_load_4d(s_in + stage * stage_stride, &tmap, bar_full + stage, (tile_x * a.TW - 1) * 2,
-                            tile_y * a.TH - 1, 0, b);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            mbar_wait(bar_w, 0);
-            const uint32_t w_base = smem_u32(s_w);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-                const int stage = it % a.n_stage, buf = it & 1;
-                if (it >= 2) mbar_wait(bar_acc_empty + buf, ((it >> 1) - 1) & 1);
-                mbar_wait(bar_full + stage, (it / a.n_stage) & 1);
-                tc_fence_after();
-                const uint32_t in_base = smem_u32(s_in + stage * stage_stride);
-                const uint32_t acc = tmem_base + buf * buf_cols;
-#pragma unroll 1
-                for (int tap = 0; tap < 9; ++tap) {
-                    const uint32_t tap_off = ((tap / 3) * a.Wh + (tap % 3)) * 16;
-#pragma unroll
-                    for (int kc = 0; kc < CIN / 16; ++kc) {
-                        const uint32_t a_addr = in_base + (2 * kc) * a.plane_bytes + tap_off;
-                        const uint64_t bdesc =
-                            umma_desc(w_base + (tap * (CIN / 8) + 2 * kc) * COUT * 16, COUT * 16, 128);
-                        for (int mt = 0; mt < a.nMT; ++mt) {
-                            const uint64_t adesc = umma_desc(a_addr + mt * 128 * 16, a.plane_bytes, 128);
-                            umma_bf16(acc + mt * COUT, adesc, bdesc, IDESC, (tap | kc) != 0);
-                        }
-                    }
-                }
-                umma_commit(bar_empty + stage);      // input stage reusable once these MMAs retire
-                umma_commit(bar_acc_full + buf);     // accumulators ready for the epilogue
-            }
-        }
-    } else {
-        const int quad = warp & 3;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
-            const int tile_y = t2 / a.tiles_x, tile_x = t2 - tile_y * a.tiles_x;
-            mbar_wait(bar_acc_full + buf, (it >> 1) & 1);
-            __syncwarp();
-            tc_fence_after();
-            conv_epilogue<COUT, EPI>(a, tmem_base + buf * buf_cols, quad, lane, b, tile_x, tile_y);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc_empty + buf);
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
-}
 
 // ------------------------------------------------------------------------------------------ host side
 
@@ -526,55 +386,6 @@ static bool plan_tiles(int B, int H, int W, int cin, int cout, TilePlan* p) {
     return have;
 }
 
-static bool plan_persistent(int B, int H, int W, int cin, int cout, TilePlan* p, int* n_ctas) {
-    const uint32_t w_bytes = ((9u * cin * cout * 2) + 127) & ~127u;
-    if (cin * cout > 4096) return false;
-    const int TW = W < 64 ? W : 64, Wh = TW + 2;
-    const int tiles_x = (W + TW - 1) / TW;
-    int mt_cap = 128 / cout;                 // two accumulator buffers of <= 128 columns each
-    if (mt_cap < 1) mt_cap = 1;
-    if (mt_cap > 8) mt_cap = 8;
-    for (int mt = mt_cap; mt >= 1; --mt) {
-        int th_cap = (mt * 128) / Wh;
-        if (th_cap < 1) th_cap = 1;
-        if (th_cap > H) th_cap = H;
-        const int n_ty = (H + th_cap - 1) / th_cap;
-        const int TH = (H + n_ty - 1) / n_ty;
-        const uint32_t plane = static_cast<uint32_t>(TH + 2) * Wh * 16;
-        const uint32_t stage = ((cin / 8) * plane + 256 + 127) & ~127u;
-        const long long n_tiles = static_cast<long long>(B) * n_ty * tiles_x;
-        if (n_tiles < 2 * 148 && mt > 1) continue;       // keep the tiles small enough to give every SM work
-        for (int stages = 3; stages >= 2; --stages) {
-            const uint32_t total = 128 + w_bytes + stages * stage + 17 * 8 + 16;
-            if (total > (stages == 3 ? 112u : 220u) * 1024) continue;
-            p->TH = TH; p->TW = TW; p->Wh = Wh;
-            p->nMT = (TH * Wh + 127) / 128;
-            p->tmem_cols = pow2_cols(2 * pow2_cols(p->nMT * cout) < 64 ? 64 : 2 * pow2_cols(p->nMT * cout));
-            p->n_stage = stages;
-            p->plane_bytes = plane;
-            p->smem_bytes = total;
-            const int per_sm = total <= 112 * 1024 && p->tmem_cols <= 256 ? 2 : 1;
-            *n_ctas = static_cast<int>(n_tiles < 148 * per_sm ? n_tiles : 148 * per_sm);
-            return true;
-        }
-    }
-    return false;
-}
-
-template <int CIN, int COUT, int EPI>
-static int launch_conv_persist(const CUtensorMap& tmap, const ConvArgs& a, const TilePlan& p, int n_ctas,
-                               cudaStream_t st) {
-    auto kern = conv3x3_umma_persist_kernel<CIN, COUT, EPI>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv3x3 persistent)");
-        configured = true;
-    }
-    kern<<<n_ctas, kPersistThreads, p.smem_bytes, st>>>(tmap, a);
-    return check_launch("conv3x3_umma_persist");
-}
-
 template <int CIN, int COUT, int EPI>
 static int launch_conv(const CUtensorMap& tmap, const ConvArgs& a, const TilePlan& p, cudaStream_t st) {
     auto kern = conv3x3_umma_kernel<CIN, COUT, EPI>;
@@ -589,16 +400,6 @@ static int launch_conv(const CUtensorMap& tmap, const ConvArgs& a, const TilePla
     return check_launch("conv3x3_umma");
 }
 
-#define NGAN_CONV_PCASE(CI, CO)                                                                          \
-    if (cin == CI && cout == CO) {                                                                       \
-        switch (epi) {                                                                                   \
-            case EPI_FWD_PN: return launch_conv_persist<CI, CO, EPI_FWD_PN>(tmap, a, plan, n_ctas, st);  \
-            case EPI_LINEAR: return launch_conv_persist<CI, CO, EPI_LINEAR>(tmap, a, plan, n_ctas, st);  \
-            case EPI_BWD_PN: return launch_conv_persist<CI, CO, EPI_BWD_PN>(tmap, a, plan, n_ctas, st);  \
-            case EPI_DBL: return launch_conv_persist<CI, CO, EPI_DBL>(tmap, a, plan, n_ctas, st);        \
-        }                                                                                                \
-    }
-
 #define NGAN_CONV_CASE(CI, CO)                                                                    \
     if (cin == CI && cout == CO) {                                                                \
         switch (epi) {                                                                            \
@@ -612,26 +413,11 @@ static int launch_conv(const CUtensorMap& tmap, const ConvArgs& a, const TilePla
 int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, int cout, int H, int W, float scale,
                      float leak, const float* bias, void* out0, void* out1, float* rout, const void* y,
                      const float* r, const void* gy, const void* addin, cudaStream_t st) {
-    TilePlan plan;
-    int n_ctas = 0;
-    static const bool no_persist = getenv("NGAN_NO_PERSISTENT") != nullptr;
-    const bool persistent = !no_persist && plan_persistent(B, H, W, cin, cout, &plan, &n_ctas);
-    if (!persistent && !plan_tiles(B, H, W, cin, cout, &plan)) {
-        set_error("conv3x3: no tile plan for H=%d W=%d cin=%d cout=%d", H, W, cin, cout);
-        return NGAN_ERR_UNSUPPORTED;
-    }
-    CUtensorMap tmap;
-    int rc = make_c8_tensor_map(&tmap, x, B, cin, H, W, plan.Wh, plan.TH + 2, cin / 8);
-    if (rc) return rc;
     ConvArgs a;
     a.B = B; a.H = H; a.W = W;
-    a.TH = plan.TH; a.TW = plan.TW; a.Wh = plan.Wh;
-    a.nMT = plan.nMT; a.tmem_cols = plan.tmem_cols; a.n_stage = plan.n_stage;
-    a.tiles_x = (W + plan.TW - 1) / plan.TW;
-    a.tiles_y = (H + plan.TH - 1) / plan.TH;
-    a.n_tiles = a.tiles_x * a.tiles_y * B;
-    a.plane_bytes = plan.plane_bytes;
     a.scale = scale; a.leak = leak;
+    a.debug = 0;
+    a.dbg_clock = nullptr;
     a.wprep = static_cast<const __nv_bfloat16*>(wprep);
     a.bias = bias;
     a.out0 = static_cast<__nv_bfloat16*>(out0);
@@ -641,22 +427,22 @@ int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, 
     a.r = r;
     a.gy = static_cast<const __nv_bfloat16*>(gy);
     a.addin = static_cast<const __nv_bfloat16*>(addin);
-    if (persistent) {
-        NGAN_CONV_PCASE(16, 16)
-        NGAN_CONV_PCASE(16, 32)
-        NGAN_CONV_PCASE(32, 16)
-        NGAN_CONV_PCASE(32, 32)
-        NGAN_CONV_PCASE(32, 64)
-        NGAN_CONV_PCASE(64, 32)
-        NGAN_CONV_PCASE(64, 64)
+    if (conv_uses_folded_kernel(cin, cout)) return conv3x3_fold_dispatch(epi, x, a, B, cin, cout, H, W, st);
+
+    TilePlan plan;
+    if (!plan_tiles(B, H, W, cin, cout, &plan)) {
+        set_error("conv3x3: no tile plan for H=%d W=%d cin=%d cout=%d", H, W, cin, cout);
+        return NGAN_ERR_UNSUPPORTED;
     }
-    NGAN_CONV_CASE(16, 16)
-    NGAN_CONV_CASE(16, 32)
-    NGAN_CONV_CASE(32, 16)
-    NGAN_CONV_CASE(32, 32)
-    NGAN_CONV_CASE(32, 64)
-    NGAN_CONV_CASE(64, 32)
-    NGAN_CONV_CASE(64, 64)
+    CUtensorMap tmap;
+    int rc = make_c8_tensor_map(&tmap, x, B, cin, H, W, plan.Wh, plan.TH + 2, cin / 8);
+    if (rc) return rc;
+    a.TH = plan.TH; a.TW = plan.TW; a.Wh = plan.Wh;
+    a.nMT = plan.nMT; a.tmem_cols = plan.tmem_cols; a.n_stage = plan.n_stage;
+    a.tiles_x = (W + plan.TW - 1) / plan.TW;
+    a.tiles_y = (H + plan.TH - 1) / plan.TH;
+    a.n_tiles = a.tiles_x * a.tiles_y * B;
+    a.plane_bytes = plan.plane_bytes;
     NGAN_CONV_CASE(64, 128)
     NGAN_CONV_CASE(128, 64)
     NGAN_CONV_CASE(128, 128)
@@ -668,16 +454,26 @@ int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, 
 // fp32 master weight [COUT][CIN][3][3] (torch layout, reference models.py:172-181) ->
 //   fwd   image bf16 [9][CIN/8][COUT][8]   : B(n=co, k=(tap, ci)) for y = conv(x, W)
 //   dgrad image bf16 [9][COUT/8][CIN][8]   : B(n=ci, k=(tap', co)) with tap' = 8 - tap (flipped), dx = convT(g, W)
+// or, when conv_uses_folded_kernel(cin, cout), the kx-folded images [3][K/8][3*N][8] of conv3x3_fold.cu.
 __global__ void prep_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
-                                        __nv_bfloat16* __restrict__ dgrad, int cin, int cout) {
+                                        __nv_bfloat16* __restrict__ dgrad, int cin, int cout, int folded) {
     const int n = cin * cout * 9;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int tap = i % 9;
         const int ci = (i / 9) % cin;
         const int co = i / (9 * cin);
         const __nv_bfloat16 v = __float2bfloat16(w[i]);
-        if (fwd) fwd[((static_cast<size_t>(tap) * (cin / 8) + ci / 8) * cout + co) * 8 + (ci % 8)] = v;
-        if (dgrad) dgrad[((static_cast<size_t>(8 - tap) * (cout / 8) + co / 8) * cin + ci) * 8 + (co % 8)] = v;
+        if (!folded) {
+            if (fwd) fwd[((static_cast<size_t>(tap) * (cin / 8) + ci / 8) * cout + co) * 8 + (ci % 8)] = v;
+            if (dgrad) dgrad[((static_cast<size_t>(8 - tap) * (cout / 8) + co / 8) * cin + ci) * 8 + (co % 8)] = v;
+        } else {
+            // folded image [ky][K/8][(kx, n)][8]: the three horizontal taps of a row share one MMA (N = 3*n)
+            const int ky = tap / 3, kx = tap % 3;
+            if (fwd) fwd[((static_cast<size_t>(ky) * (cin / 8) + ci / 8) * (3 * cout) + kx * cout + co) * 8 + (ci % 8)] = v;
+            if (dgrad)
+                dgrad[((static_cast<size_t>(2 - ky) * (cout / 8) + co / 8) * (3 * cin) + (2 - kx) * cin + ci) * 8 +
+                      (co % 8)] = v;
+        }
     }
 }
 
@@ -686,7 +482,8 @@ int prep_conv_weight(const float* w, void* fwd, void* dgrad, int cin, int cout, 
     int blocks = (n + 255) / 256;
     if (blocks > 592) blocks = 592;
     prep_conv_weight_kernel<<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(fwd),
-                                                    static_cast<__nv_bfloat16*>(dgrad), cin, cout);
+                                                    static_cast<__nv_bfloat16*>(dgrad), cin, cout,
+                                                    conv_uses_folded_kernel(cin, cout) ? 1 : 0);
     return check_launch("prep_conv_weight");
 }
 
