@@ -180,7 +180,9 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        # short collective timeout: a rank that falls out of step must fail in minutes, not hold the box
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=120))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -226,6 +228,7 @@ def run_b200(args):
     t1 = time.perf_counter()
     ms = e0.elapsed_time(e1) / args.steps
     launches = (_lib.launch_count - launches0) // args.steps
+    graph_replay = bool(step._graphs)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     last_stats = TrainStep.stats_dict(stats.cpu())
     TrainStep.check_nan(list(stats.cpu()))
@@ -236,8 +239,7 @@ def run_b200(args):
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
-        x = host[i % n_pool].to(dev, non_blocking=True)
-        s = step(x)                      # draws z, z, eps, z on the CPU generator and copies them
+        s = step(host[i % n_pool])       # pinned host images -> H2D; draws z, z, eps, z on the CPU generator -> H2D
         s_host = s.cpu()                 # the reference's six .item() calls, as one packed read
         TrainStep.check_nan(list(s_host))
     f1.record()
@@ -252,11 +254,18 @@ def run_b200(args):
     # ---- per-kernel timing pass (events around every launch; perturbs throughput, so it is separate)
     roofline, kernels = None, []
     if rank == 0 and not args.no_profile:
+        from neuron_gan_b200 import engine
+        dp_was, step.dp = step.dp, False      # rank 0 alone runs this pass: no collective may be issued in it
+        graph_was, step.use_graph = step.use_graph, False     # kernel by kernel, on one stream, events around each
+        engine._Side.enabled = False
+        fork_was, step.fork_chains = step.fork_chains, False
         _lib.start_profile()
         n_prof = 2
         for i in range(n_prof):
             step(devx[i % n_pool], draws[i % n_pool])
         prof = _lib.stop_profile()
+        step.dp, step.use_graph, step.fork_chains = dp_was, graph_was, fork_was
+        engine._Side.enabled = True
         agg = {}
         for name, a, dt in prof:
             k = (name, a[-5:] if name.startswith('ngan_conv3x3') else a[-4:])
@@ -321,6 +330,7 @@ def run_b200(args):
             'config': {'workload': workload_name(res, alpha), 'resolution': res, 'alpha': alpha, 'batch_per_gpu': B,
                        'global_batch': B * world, 'parallelism': f'dp{world}',
                        'l2': 'per-step activation working set (GBs) exceeds the 126 MB L2; 4 rotating input batches',
+                       'launch': 'cuda-graph replay, wgrad kernels on a forked stream' if graph_replay else 'eager',
                        'losses': last_stats, 'peak_mem_GB': round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)},
             'e2e': {'value': round(B * world / (ms_e2e * 1e-3), 2), 'unit': 'images/s', 'ms_per_step': round(ms_e2e, 4),
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 20},

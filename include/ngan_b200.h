@@ -129,6 +129,10 @@ int ngan_gloss(const float* s_fake, float* out1, float* g_fake, float gscale, in
 int ngan_gp_loss(const float* g, float norm_scale, float lambda, float* pen, float* coeff, float gscale, int B,
                  long long per_sample, void* stream);
 
+/* stats[5] = {D_loss + pen, score_real, score_fake, G_loss, pen}: train.py:362 and the six .item() reads of
+ * train.py:389-394 as one packed device tensor */
+int ngan_pack_stats(const float* out3, const float* out1, const float* pen, float* stats, void* stream);
+
 /* ---- multi-tensor Adam, train.py:220-225 (torch.optim.Adam semantics, one step count per parameter) ---- */
 typedef struct {
     float* p;            /* parameter, fp32, 16-byte aligned */
@@ -139,6 +143,8 @@ typedef struct {
     long long n;
     float step_size;     /* lr / (1 - beta1^t), t = this parameter's step count after the update */
     float inv_bc2_sqrt;  /* 1 / sqrt(1 - beta2^t) */
+    const float* dyn;    /* optional DEVICE pointer to {step_size, inv_bc2_sqrt}; when non-NULL it overrides the two
+                            fields above at run time (lets a launch captured in a CUDA graph follow the step count) */
 } ngan_adam_tensor;
 int ngan_adam_multi(const ngan_adam_tensor* tensors, int n_tensors, float beta1, float beta2, float eps,
                     void* stream);

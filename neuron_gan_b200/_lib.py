@@ -15,7 +15,7 @@ class AdamTensor(ctypes.Structure):
     """Mirror of ngan_adam_tensor."""
     _fields_ = [('p', ctypes.c_void_p), ('g', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p),
                 ('shadow_bf16', ctypes.c_void_p), ('n', ctypes.c_longlong), ('step_size', ctypes.c_float),
-                ('inv_bc2_sqrt', ctypes.c_float)]
+                ('inv_bc2_sqrt', ctypes.c_float), ('dyn', ctypes.c_void_p)]
 
 
 def parse_header(path=HEADER_PATH):

@@ -35,6 +35,7 @@ class _GeneratorFn(Function):
     def backward(ctx, g_img):
         sink = _zeros_sink(ctx.plist)
         engine.g_backward(ctx.net, ctx.ectx, g_img[:, 0].contiguous(), sink)
+        engine.side_join()
         ctx.ectx = None
         return (None, None, None) + tuple(sink[id(p)] for p in ctx.plist)
 
@@ -57,6 +58,7 @@ class _CriticBackwardFn(Function):
         rec = SimpleNamespace() if record else None
         sink = _zeros_sink(plist) if want_pgrads else None
         g_xp = engine.d_backward(net, ectx, gout[:, 0].contiguous(), sink, want_gxp=want_gx, record=rec)
+        engine.side_join()
         ctx.holder, ctx.rec = holder, rec
         ctx.set_materialize_grads(False)
         gx = None
@@ -81,6 +83,7 @@ class _CriticBackwardFn(Function):
         sink = _zeros_sink(plist)
         addins = engine.d_double_backward_sweep1(net, ectx, ctx.rec, ghat_xp, sink)
         engine.d_backward(net, ectx, None, sink, addins=addins)
+        engine.side_join()
         return (None, None, None, None, None) + tuple(sink[id(p)] for p in plist)
 
 
@@ -170,6 +173,7 @@ class _GradPenaltyFn(Function):
     def backward(ctx, g_pen):
         sink = _zeros_sink(ctx.plist)
         ctx.closure(sink, 1.0, scale_tensor=g_pen)
+        engine.side_join()
         ctx.closure = None
         return (None, None, None, None) + tuple(sink[id(p)] for p in ctx.plist)
 

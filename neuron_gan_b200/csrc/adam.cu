@@ -11,7 +11,7 @@
 
 namespace ngan {
 
-constexpr int kAdamMaxTensors = 64;
+constexpr int kAdamMaxTensors = 48;   // 48 x 64 B: the table travels in (4 KB) kernel-parameter space
 struct AdamEntry {
     float* p;
     const float* g;
@@ -21,6 +21,8 @@ struct AdamEntry {
     long long n;
     float step_size;      // lr / (1 - beta1^t)
     float inv_bc2_sqrt;   // 1 / sqrt(1 - beta2^t)
+    const float* dyn;     // optional device pointer to {step_size, inv_bc2_sqrt}: overrides the two fields above, so a
+                          // launch captured in a CUDA graph picks up the values of the current step at replay
 };
 struct AdamTable {
     AdamEntry e[kAdamMaxTensors];
@@ -29,6 +31,8 @@ struct AdamTable {
 __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ AdamTable tab, float beta1,
                                                          float beta2, float eps) {
     const AdamEntry& t = tab.e[blockIdx.y];
+    const float step_size = t.dyn ? __ldg(t.dyn) : t.step_size;
+    const float inv_bc2_sqrt = t.dyn ? __ldg(t.dyn + 1) : t.inv_bc2_sqrt;
     const long long n4 = t.n >> 2;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -39,7 +43,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
 #define NGAN_ADAM1(c)                                                      \
     m.c = m.c + (1.f - beta1) * (g.c - m.c);                               \
     v.c = beta2 * v.c + (1.f - beta2) * g.c * g.c;                         \
-    p.c = p.c - t.step_size * (m.c / (sqrtf(v.c) * t.inv_bc2_sqrt + eps));
+    p.c = p.c - step_size * (m.c / (sqrtf(v.c) * inv_bc2_sqrt + eps));
         NGAN_ADAM1(x) NGAN_ADAM1(y) NGAN_ADAM1(z) NGAN_ADAM1(w)
         reinterpret_cast<float4*>(t.p)[i] = p;
         reinterpret_cast<float4*>(t.m)[i] = m;
@@ -59,7 +63,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
             float m = t.m[i], v = t.v[i], p = t.p[i];
             m = m + (1.f - beta1) * (g - m);
             v = beta2 * v + (1.f - beta2) * g * g;
-            p = p - t.step_size * (m / (sqrtf(v) * t.inv_bc2_sqrt + eps));
+            p = p - step_size * (m / (sqrtf(v) * inv_bc2_sqrt + eps));
             t.p[i] = p; t.m[i] = m; t.v[i] = v;
             if (t.shadow) t.shadow[i] = __float2bfloat16(p);
         }
@@ -85,7 +89,7 @@ int adam_multi_launch(const AdamEntry* entries, int n_tensors, float beta1, floa
             return NGAN_ERR_INVALID;
         }
     }
-    for (int i = n_tensors; i < kAdamMaxTensors; ++i) tab.e[i] = AdamEntry{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0.f};
+    for (int i = n_tensors; i < kAdamMaxTensors; ++i) tab.e[i] = AdamEntry{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0.f, nullptr};
     long long bx = (max_n / 4 + 255) / 256;
     if (bx > 148 * 8) bx = 148 * 8;
     if (bx < 1) bx = 1;

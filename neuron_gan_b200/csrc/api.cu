@@ -220,6 +220,10 @@ int ngan_gloss(const float* s_fake, float* out1, float* g_fake, float gscale, in
     NGAN_REQUIRE(s_fake && out1 && B > 0, "gloss: bad arguments");
     return gloss_fwd(s_fake, out1, g_fake, gscale, B, S(stream));
 }
+int ngan_pack_stats(const float* out3, const float* out1, const float* pen, float* stats, void* stream) {
+    NGAN_REQUIRE(out3 && out1 && pen && stats, "pack_stats: null pointer");
+    return pack_stats(out3, out1, pen, stats, S(stream));
+}
 int ngan_gp_loss(const float* g, float norm_scale, float lambda, float* pen, float* coeff, float gscale, int B,
                  long long per_sample, void* stream) {
     NGAN_REQUIRE(g && pen && coeff && B > 0 && per_sample > 0, "gp_loss: bad arguments");

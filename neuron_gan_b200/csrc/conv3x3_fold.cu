@@ -29,10 +29,16 @@
 namespace ngan {
 
 constexpr int kFoldTW = 30, kFoldWh = 32;
-constexpr int kFoldEpiGroups = 4;
+// epilogue groups of 4 warps (one warp per TMEM lane quadrant); the 64-channel epilogues need > 96 registers
+// per thread (as does the 32-channel double-backward one), so those kernels run two groups (352 threads)
+// instead of four (608)
+template <int COUT, int EPI> struct FoldCfg {
+    static constexpr int kEpiGroups = (COUT >= 64 || (COUT >= 32 && EPI == EPI_DBL)) ? 2 : 4;
+    static constexpr int kThreads = 96 + 128 * kEpiGroups;   // producer + 2 MMA warps + epilogue groups
+};
 constexpr int kFoldMaxStages = 12;
-constexpr uint32_t kFoldBarBytes = (5 + 2 * kFoldMaxStages) * 8 + 16;
-constexpr int kFoldThreads = 96 + 128 * kFoldEpiGroups;   // producer + 2 MMA warps + epilogue groups
+constexpr int kFoldMaxAcc = 8;            // accumulator buffers in TMEM (ring between MMA issuers and epilogue)
+constexpr uint32_t kFoldBarBytes = (1 + 2 * kFoldMaxStages + 2 * kFoldMaxAcc) * 8 + 16;
 
 // Fused pointwise tail on one output pixel held in registers (o[c] = raw accumulator sums).
 template <int COUT, int EPI>
@@ -87,17 +93,19 @@ __device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool vali
         }
     } else if constexpr (EPI == EPI_BWD_PN) {
         // ga = mask(y) * r * (g - y*mean_c(g*y)) (+ addin), g = scale*acc     [SURVEY.md 8a row 3]
+        // Wide layers (COUT > 16) re-load y in the second pass (an L1 hit) instead of holding it in registers.
         if (!valid) return;
-        const uint4* yq = reinterpret_cast<const uint4*>(a.y);
-        uint4 yp[NCH];
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) yp[j] = __ldg(yq + q0 + j * HW);
+        constexpr bool kKeep = COUT <= 16;
+        const uint4* yq = reinterpret_cast<const uint4*>(a.y) + q0;
+        uint4 yp[kKeep ? NCH : 1];
         const float rinv = __ldg(a.r + p0);
         float t = 0.f;
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
+            const uint4 yj = __ldg(yq + j * HW);
+            if constexpr (kKeep) yp[j] = yj;
             float yv[8];
-            unpack8(yp[j], yv);
+            unpack8(yj, yv);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 o[j * 8 + e] *= a.scale;
@@ -111,7 +119,7 @@ __device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool vali
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
             float yv[8], ad[8], ga[8];
-            unpack8(yp[j], yv);
+            if constexpr (kKeep) unpack8(yp[j], yv); else unpack8(__ldg(yq + j * HW), yv);
             if (aq) unpack8(__ldg(aq + q0 + j * HW), ad);
 #pragma unroll
             for (int e = 0; e < 8; ++e)
@@ -121,21 +129,22 @@ __device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool vali
         }
     } else {  // EPI_DBL, formulas in conv3x3_umma.cu / SURVEY.md 8a row 3
         if (!valid) return;
-        const uint4* yq = reinterpret_cast<const uint4*>(a.y);
-        const uint4* gq = reinterpret_cast<const uint4*>(a.gy);
-        uint4 yp[NCH], gp[NCH];
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-            yp[j] = __ldg(yq + q0 + j * HW);
-            gp[j] = __ldg(gq + q0 + j * HW);
-        }
+        constexpr bool kKeep = COUT <= 16;
+        const uint4* yq = reinterpret_cast<const uint4*>(a.y) + q0;
+        const uint4* gq = reinterpret_cast<const uint4*>(a.gy) + q0;
+        uint4 yp[kKeep ? NCH : 1], gp[kKeep ? NCH : 1];
         const float rinv = __ldg(a.r + p0);
         float t = 0.f, u = 0.f, w = 0.f;
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
+            const uint4 yj = __ldg(yq + j * HW), gj = __ldg(gq + j * HW);
+            if constexpr (kKeep) {
+                yp[j] = yj;
+                gp[j] = gj;
+            }
             float yv[8], gv[8];
-            unpack8(yp[j], yv);
-            unpack8(gp[j], gv);
+            unpack8(yj, yv);
+            unpack8(gj, gv);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const float gh = lrelu_mask(yv[e], a.leak) * a.scale * o[j * 8 + e];
@@ -154,8 +163,13 @@ __device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool vali
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
             float yv[8], gv[8], o0[8], o1[8];
-            unpack8(yp[j], yv);
-            unpack8(gp[j], gv);
+            if constexpr (kKeep) {
+                unpack8(yp[j], yv);
+                unpack8(gp[j], gv);
+            } else {
+                unpack8(__ldg(yq + j * HW), yv);
+                unpack8(__ldg(gq + j * HW), gv);
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const float gh = o[j * 8 + e];
@@ -168,13 +182,19 @@ __device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool vali
     }
 }
 
-template <int CIN, int COUT, int EPI>
-__global__ void __launch_bounds__(kFoldThreads) conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap,
+// NKX = 3: the three horizontal taps are folded into the MMA's N dimension (N = 3*COUT, 3 MMAs per K = 16 slice,
+//          the epilogue reads 3*COUT accumulator columns per pixel and combines them with warp shuffles);
+// NKX = 1: one MMA per tap (N = COUT, 9 MMAs per K = 16 slice, A start address shifted by kx pixels), plain epilogue.
+// Both read the same folded weight image [3 ky][CIN/8][3*COUT (kx, co)][8].
+template <int CIN, int COUT, int EPI, int NKX>
+__global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                     const ConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    constexpr int NF = 3 * COUT;                       // MMA N: (kx, co)
+    constexpr int NF = 3 * COUT;                       // rows of the weight image per (ky, k-group): (kx, co)
+    constexpr int NMMA = NKX == 3 ? NF : COUT;         // MMA N
     constexpr uint32_t W_BYTES = 9 * CIN * COUT * 2;   // [3 ky][CIN/8][NF][8] bf16
-    constexpr uint32_t IDESC = umma_idesc_bf16(128, NF);
+    constexpr uint32_t IDESC = umma_idesc_bf16(128, NMMA);
+    constexpr int kFoldEpiGroups = FoldCfg<COUT, EPI>::kEpiGroups;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const uint32_t in_bytes = (CIN / 8) * a.plane_bytes;   // plane = (TH+2)*32*16, a multiple of 128
@@ -184,12 +204,15 @@ __global__ void __launch_bounds__(kFoldThreads) conv3x3_fold_kernel(const __grid
     uint64_t* bar_w = bars;
     uint64_t* bar_full = bars + 1;            // [n_stage <= kFoldMaxStages]
     uint64_t* bar_empty = bars + 1 + kFoldMaxStages;
-    uint64_t* bar_acc_full = bars + 1 + 2 * kFoldMaxStages;        // [2]
-    uint64_t* bar_acc_empty = bars + 3 + 2 * kFoldMaxStages;       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kFoldMaxStages);
+    uint64_t* bar_acc_full = bars + 1 + 2 * kFoldMaxStages;        // [n_acc <= kFoldMaxAcc]
+    uint64_t* bar_acc_empty = bar_acc_full + kFoldMaxAcc;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + kFoldMaxAcc);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t buf_cols = a.tmem_cols / 2;
+    // warp index through a shuffle: tells the compiler it is warp-uniform, so everything derived from it (tile
+    // counters, descriptors) stays in uniform registers and the UTCHMMA / UTMALDG issue needs no per-lane loop
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t buf_cols = a.nMT * NMMA;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmap);
@@ -198,7 +221,7 @@ __global__ void __launch_bounds__(kFoldThreads) conv3x3_fold_kernel(const __grid
             mbar_init(bar_full + s, 1);
             mbar_init(bar_empty + s, 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < a.n_acc; ++s) {
             mbar_init(bar_acc_full + s, 1);
             mbar_init(bar_acc_empty + s, 4 * kFoldEpiGroups);   // one arrival per epilogue warp
         }
@@ -209,7 +232,7 @@ __global__ void __launch_bounds__(kFoldThreads) conv3x3_fold_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int tiles_per_img = a.tiles_x * a.tiles_y;
 
     if (warp == 0) {
@@ -232,43 +255,51 @@ __global__ void __launch_bounds__(kFoldThreads) conv3x3_fold_kernel(const __grid
             }
         }
     } else if (warp <= 2) {
-        // Two MMA-issuing warps, one per accumulator buffer (even / odd tiles): while one is parked in the
-        // mbarrier waits of its next tile (a few hundred cycles each, even when already complete) the other
-        // keeps the tensor core fed.
-        if (lane == 0) {
-            mbar_wait(bar_w, 0);
-            const uint32_t w_base = smem_u32(s_w);
-            for (int it = warp - 1, tile = blockIdx.x + (warp - 1) * gridDim.x; tile < a.n_tiles;
-                 tile += 2 * gridDim.x, it += 2) {
-                const int stage = it % a.n_stage, buf = it & 1;
-                const bool trace = a.dbg_clock && blockIdx.x == 0 && it < 32;
-                if (trace) a.dbg_clock[it * 8 + 0] = clock64();
-                if (it >= 2) mbar_wait(bar_acc_empty + buf, ((it >> 1) - 1) & 1);
-                if (trace) a.dbg_clock[it * 8 + 1] = clock64();
-                mbar_wait(bar_full + stage, (it / a.n_stage) & 1);
-                tc_fence_after();
-                if (trace) a.dbg_clock[it * 8 + 2] = clock64();
+        // Two MMA-issuing warps taking alternate tiles: while one is parked in the mbarrier waits of its next
+        // tile the other keeps the tensor core fed.  The loop is warp-uniform; one elected lane issues.
+        mbar_wait_warp(bar_w, 0, lane);
+        const uint32_t w_base = smem_u32(s_w);
+        for (int it = warp - 1;; it += 2) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            if (tile >= a.n_tiles) break;
+            const int stage = it % a.n_stage, buf = it % a.n_acc, use = it / a.n_acc;
+            const bool trace = a.dbg_clock && blockIdx.x == 0 && it < 32 && lane == 0;
+            if (trace) a.dbg_clock[it * 8 + 0] = clock64();
+            if (use > 0) mbar_wait_warp(bar_acc_empty + buf, (use - 1) & 1, lane);
+            if (trace) a.dbg_clock[it * 8 + 1] = clock64();
+            mbar_wait_warp(bar_full + stage, (it / a.n_stage) & 1, lane);
+            tc_fence_after();
+            if (trace) a.dbg_clock[it * 8 + 2] = clock64();
+            if (elect_one()) {
                 const uint32_t in_base = smem_u32(s_in + stage * in_bytes);
                 const uint32_t acc = tmem_base + buf * buf_cols;
+                const uint32_t a_hi = umma_desc_hi(128), b_hi = umma_desc_hi(128);
+                if (!(a.debug & 1)) {
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    if (a.debug & 1) break;
+                    for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-                    for (int kc = 0; kc < CIN / 16; ++kc) {
-                        const uint32_t a_addr = in_base + (2 * kc) * a.plane_bytes + ky * kFoldWh * 16;
-                        const uint64_t bdesc = umma_desc(w_base + (ky * (CIN / 8) + 2 * kc) * NF * 16, NF * 16, 128);
-                        uint64_t adesc = umma_desc(a_addr, a.plane_bytes, 128);
-                        for (int mt = 0; mt < a.nMT; ++mt) {
-                            umma_bf16(acc + mt * NF, adesc, bdesc, IDESC, (ky | kc) != 0);
-                            adesc += (128 * 16) >> 4;      // next M-tile: 128 rows further (start-address field)
+                        for (int kx = 0; kx < (NKX == 3 ? 1 : 3); ++kx) {
+#pragma unroll
+                            for (int kc = 0; kc < CIN / 16; ++kc) {
+                                const uint32_t a_addr =
+                                    in_base + (2 * kc) * a.plane_bytes + (ky * kFoldWh + kx) * 16;
+                                const uint32_t b_addr = w_base + ((ky * (CIN / 8) + 2 * kc) * NF + kx * COUT) * 16;
+                                const uint32_t b_lo = umma_desc_lo(b_addr, NF * 16);
+                                uint32_t a_lo = umma_desc_lo(a_addr, a.plane_bytes);
+#pragma unroll 4
+                                for (int mt = 0; mt < a.nMT; ++mt) {
+                                    umma_bf16_2x32(acc + mt * NMMA, a_lo, a_hi, b_lo, b_hi, IDESC, (ky | kx | kc) != 0);
+                                    a_lo += (128 * 16) >> 4;      // next M-tile: 128 rows further (start-address field)
+                                }
+                            }
                         }
                     }
                 }
-                if (trace) a.dbg_clock[it * 8 + 3] = clock64();
                 umma_commit(bar_empty + stage);
                 umma_commit(bar_acc_full + buf);
-                if (trace) a.dbg_clock[it * 8 + 4] = clock64();
             }
+            __syncwarp();
+            if (trace) a.dbg_clock[it * 8 + 3] = clock64();
         }
     } else {
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
@@ -276,31 +307,39 @@ __global__ void __launch_bounds__(kFoldThreads) conv3x3_fold_kernel(const __grid
         const size_t HW = static_cast<size_t>(a.H) * a.W;
         int it = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
+            const int buf = it % a.n_acc;
             const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
             const int tile_y = t2 / a.tiles_x, tile_x = t2 - tile_y * a.tiles_x;
             const bool trace = a.dbg_clock && blockIdx.x == 0 && it < 32 && warp == 3 && lane == 0;
             if (trace) a.dbg_clock[it * 8 + 5] = clock64();
-            mbar_wait(bar_acc_full + buf, (it >> 1) & 1);
-            __syncwarp();
+            mbar_wait_warp(bar_acc_full + buf, (it / a.n_acc) & 1, lane);
             tc_fence_after();
             if (trace) a.dbg_clock[it * 8 + 6] = clock64();
             const int ox = tile_x * kFoldTW + lane;
-            for (int mt = group; mt < ((a.debug & 2) ? 0 : a.nMT); mt += kFoldEpiGroups) {
+            // M-tiles of consecutive tiles rotate over the groups (with one M-tile per tile, tiles alternate)
+            const int mt0 = (group + kFoldEpiGroups - (it * a.nMT) % kFoldEpiGroups) % kFoldEpiGroups;
+            for (int mt = mt0; mt < ((a.debug & 2) ? 0 : a.nMT); mt += kFoldEpiGroups) {
                 const int rr = mt * 4 + quad;      // row of the tile (Wh = 32: one warp = one row)
                 const int oy = tile_y * a.TH + rr;
                 const bool valid = (lane < kFoldTW) && (rr < a.TH) && (oy < a.H) && (ox < a.W);
-                const uint32_t taddr = tmem_base + buf * buf_cols + (static_cast<uint32_t>(quad * 32) << 16) + mt * NF;
-                float o[COUT], v1[16], v2[16];
+                const uint32_t taddr = tmem_base + buf * buf_cols + (static_cast<uint32_t>(quad * 32) << 16) + mt * NMMA;
+                float o[COUT];
+                if constexpr (NKX == 3) {
+                    float v1[16], v2[16];
 #pragma unroll
-                for (int c0 = 0; c0 < COUT; c0 += 16) {
-                    tmem_ld16_nowait(taddr + c0, o + c0);
-                    tmem_ld16_nowait(taddr + COUT + c0, v1);
-                    tmem_ld16_nowait(taddr + 2 * COUT + c0, v2);
+                    for (int c0 = 0; c0 < COUT; c0 += 16) {
+                        tmem_ld16_nowait(taddr + c0, o + c0);
+                        tmem_ld16_nowait(taddr + COUT + c0, v1);
+                        tmem_ld16_nowait(taddr + 2 * COUT + c0, v2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            o[c0 + i] += __shfl_down_sync(0xffffffffu, v1[i], 1) + __shfl_down_sync(0xffffffffu, v2[i], 2);
+                    }
+                } else {
+#pragma unroll
+                    for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16_nowait(taddr + c0, o + c0);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        o[c0 + i] += __shfl_down_sync(0xffffffffu, v1[i], 1) + __shfl_down_sync(0xffffffffu, v2[i], 2);
                 }
                 const size_t q0 = static_cast<size_t>(b) * (COUT / 8) * HW + static_cast<size_t>(oy) * a.W + ox;
                 const size_t p0 = static_cast<size_t>(b) * HW + static_cast<size_t>(oy) * a.W + ox;
@@ -326,33 +365,42 @@ static int pow2_cols(int n) {
     return c;
 }
 
-template <int CIN, int COUT, int EPI>
+template <int CIN, int COUT, int EPI, int NKX>
 static int launch_fold(const CUtensorMap& tmap, const ConvArgs& a, uint32_t smem_bytes, int n_ctas, cudaStream_t st) {
-    auto kern = conv3x3_fold_kernel<CIN, COUT, EPI>;
+    auto kern = conv3x3_fold_kernel<CIN, COUT, EPI, NKX>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv3x3_fold)");
         configured = true;
     }
-    kern<<<n_ctas, kFoldThreads, smem_bytes, st>>>(tmap, a);
+    kern<<<n_ctas, FoldCfg<COUT, EPI>::kThreads, smem_bytes, st>>>(tmap, a);
     return check_launch("conv3x3_fold");
 }
 
-#define NGAN_FOLD_CASE(CI, CO)                                                                       \
-    if (cin == CI && cout == CO) {                                                                   \
-        switch (epi) {                                                                               \
-            case EPI_FWD_PN: return launch_fold<CI, CO, EPI_FWD_PN>(tmap, a, smem_bytes, n_ctas, st); \
-            case EPI_LINEAR: return launch_fold<CI, CO, EPI_LINEAR>(tmap, a, smem_bytes, n_ctas, st); \
-            case EPI_BWD_PN: return launch_fold<CI, CO, EPI_BWD_PN>(tmap, a, smem_bytes, n_ctas, st); \
-            case EPI_DBL: return launch_fold<CI, CO, EPI_DBL>(tmap, a, smem_bytes, n_ctas, st);       \
-        }                                                                                            \
+#define NGAN_FOLD_CASE_K(CI, CO, K)                                                                       \
+    switch (epi) {                                                                                      \
+        case EPI_FWD_PN: return launch_fold<CI, CO, EPI_FWD_PN, K>(tmap, a, smem_bytes, n_ctas, st);      \
+        case EPI_LINEAR: return launch_fold<CI, CO, EPI_LINEAR, K>(tmap, a, smem_bytes, n_ctas, st);      \
+        case EPI_BWD_PN: return launch_fold<CI, CO, EPI_BWD_PN, K>(tmap, a, smem_bytes, n_ctas, st);      \
+        case EPI_DBL: return launch_fold<CI, CO, EPI_DBL, K>(tmap, a, smem_bytes, n_ctas, st);            \
+    }
+#define NGAN_FOLD_CASE(CI, CO)              \
+    if (cin == CI && cout == CO) {          \
+        if (nkx == 3) {                     \
+            NGAN_FOLD_CASE_K(CI, CO, 3)     \
+        } else {                            \
+            NGAN_FOLD_CASE_K(CI, CO, 1)     \
+        }                                   \
     }
 
 int conv3x3_fold_dispatch(int epi, const void* x, ConvArgs a, int B, int cin, int cout, int H, int W,
                           cudaStream_t st) {
-    const int NF = 3 * cout;
-    // M-tiles (4 tile rows each) per CTA tile: two accumulator buffers of nMT*NF columns must fit in 512 columns
+    // NKX: 3 = horizontal taps folded into N, 1 = one MMA per tap (see the kernel comment)
+    static const int nkx_env = getenv("NGAN_FOLD_NKX") ? atoi(getenv("NGAN_FOLD_NKX")) : 3;
+    const int nkx = nkx_env == 1 ? 1 : 3;
+    const int NF = nkx == 3 ? 3 * cout : cout;         // accumulator columns per M-tile
+    // M-tiles (4 tile rows each) per CTA tile: at least two accumulator buffers of nMT*NF columns in 512 columns
     int nMT = 256 / NF;
     if (nMT > 4) nMT = 4;
     if (nMT < 1) nMT = 1;
@@ -369,7 +417,13 @@ int conv3x3_fold_dispatch(int epi, const void* x, ConvArgs a, int B, int cin, in
     a.dbg_clock = dbg_buf;
     g_conv_trace = dbg_buf;
     a.TH = TH; a.TW = kFoldTW; a.Wh = kFoldWh; a.nMT = nMT;
-    a.tmem_cols = pow2_cols(2 * nMT * NF);
+    static const int acc_env = getenv("NGAN_FOLD_ACC") ? atoi(getenv("NGAN_FOLD_ACC")) : kFoldMaxAcc;
+    int n_acc = 512 / (nMT * NF);
+    if (n_acc > kFoldMaxAcc) n_acc = kFoldMaxAcc;
+    if (n_acc > acc_env) n_acc = acc_env;
+    if (n_acc < 2) n_acc = 2;
+    a.n_acc = n_acc;
+    a.tmem_cols = pow2_cols(n_acc * nMT * NF);
     if (a.tmem_cols > 512) {
         set_error("conv3x3_fold: TMEM budget exceeded (cout=%d)", cout);
         return NGAN_ERR_UNSUPPORTED;

@@ -14,6 +14,7 @@ struct ConvArgs {
     int nMT;
     int tmem_cols;
     int n_stage;
+    int n_acc;   // accumulator buffers in TMEM (persistent kernel)
     long long* dbg_clock;   // timing experiments only: per-tile clock64() trace of CTA 0, or null
     int debug;   // timing experiments only (NGAN_CONV_DEBUG): 1 = skip MMAs, 2 = skip epilogue, 4 = skip input loads
     int tiles_x, tiles_y, n_tiles;  // persistent kernel: tile grid over (B, rows, cols)

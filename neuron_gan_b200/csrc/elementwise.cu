@@ -795,6 +795,23 @@ int gloss_fwd(const float* s_fake, float* out1, float* g_fake, float gscale, int
     gloss_kernel<<<1, 256, 0, st>>>(s_fake, out1, g_fake, gscale, B);
     return check_launch("gloss_fwd");
 }
+// The iteration's statistics as one packed tensor (the six .item() reads of train.py:389-394 become one D2H):
+// stats = {D_loss + penalty (train.py:362), score_real, score_fake, G_loss, penalty}
+__global__ void pack_stats_kernel(const float* __restrict__ out3, const float* __restrict__ out1,
+                                  const float* __restrict__ pen, float* __restrict__ stats) {
+    if (threadIdx.x == 0) {
+        const float p = pen[0];
+        stats[0] = out3[0] + p;
+        stats[1] = out3[1];
+        stats[2] = out3[2];
+        stats[3] = out1[0];
+        stats[4] = p;
+    }
+}
+int pack_stats(const float* out3, const float* out1, const float* pen, float* stats, cudaStream_t st) {
+    pack_stats_kernel<<<1, 32, 0, st>>>(out3, out1, pen, stats);
+    return check_launch("pack_stats");
+}
 // Gradient penalty (loss_functions.py:176): norm_b = norm_scale * ||g_b||_2, pen = lambda*mean((norm_b-1)^2),
 // coeff_b = gscale * d pen / d norm_b / norm_b  (so that d pen/d g_x = coeff_b * g_x).
 __global__ void gp_sumsq_kernel(const float* __restrict__ g, float* __restrict__ sumsq, size_t per_sample) {

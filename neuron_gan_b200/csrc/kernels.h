@@ -56,6 +56,7 @@ int wloss_fwd(const float* s_real, const float* s_fake, float drift, float* out3
 int gloss_fwd(const float* s_fake, float* out1, float* g_fake, float gscale, int B, cudaStream_t st);
 int gp_loss(const float* g, float norm_scale, float lambda, float* pen_out, float* coeff_out, float gscale, int B,
             size_t per_sample, cudaStream_t st);
+int pack_stats(const float* out3, const float* out1, const float* pen, float* stats, cudaStream_t st);
 int scale_rows_f32(const float* x, const float* coeff, float scale, float* out, int B, size_t per_sample,
                    cudaStream_t st);
 

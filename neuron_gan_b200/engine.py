@@ -60,6 +60,15 @@ def conv_images(conv):
     return ent['fwd'], ent['dgrad']
 
 
+def prepare_weights(net):
+    """Refresh (on the current stream) the bf16 operand images of every 3x3 conv of `net` whose master weight
+    changed.  Called before work on `net` is forked to several streams, so that no stream depends on a
+    preparation kernel another stream launched."""
+    for m in net.modules():
+        if isinstance(m, torch.nn.Conv2d) and hasattr(m, 'scale_value') and tuple(m.kernel_size) == (3, 3):
+            conv_images(m)
+
+
 def linear_shadow(lin, allocate_only=False):
     """bf16 copy of the generator's Linear_normalized weight (same [out, in] layout)."""
     w = lin.weight
@@ -83,6 +92,44 @@ def mark_updated(param, shadow_is_fresh=False):
         ent = _cache_get(param)
         if ent is not None and 'shadow' in ent:
             ent['key'] = _wkey(param)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Side stream for the weight-gradient kernels.  A wgrad depends only on a saved activation and on the gradient
+# the data-gradient chain has just produced, and nothing downstream waits for it until the optimiser, so it
+# runs beside the chain instead of in it (the narrow layers' wgrads use a fraction of the SMs).  Works eagerly
+# (events) and under CUDA-graph capture (fork/join edges).
+# ---------------------------------------------------------------------------------------------------------
+class _Side:
+    stream = None      # torch.cuda.Stream, created on first use
+    enabled = True
+    keep = []          # tensors a pending side-stream kernel reads: kept alive until side_join()
+    pending = False
+
+
+def _wgrad(x, ga, scale, dw):
+    """conv3x3_wgrad on the side stream (dw accumulates with atomics, so concurrent wgrads into one tensor are fine)."""
+    if dw is None:
+        return
+    if not _Side.enabled:
+        ops.conv3x3_wgrad(x, ga, scale, dw)
+        return
+    if _Side.stream is None:
+        _Side.stream = torch.cuda.Stream()
+    cur = torch.cuda.current_stream()
+    _Side.stream.wait_stream(cur)
+    with torch.cuda.stream(_Side.stream):
+        ops.conv3x3_wgrad(x, ga, scale, dw)
+    _Side.keep.append((x, ga))
+    _Side.pending = True
+
+
+def side_join():
+    """Make the current stream wait for every side-stream wgrad issued so far (call before reading gradients)."""
+    if _Side.pending:
+        torch.cuda.current_stream().wait_stream(_Side.stream)
+        _Side.keep.clear()
+        _Side.pending = False
 
 
 def _sink_get(sink, p):
@@ -109,8 +156,9 @@ def _g_block_fwd(blk, y, leak, save):
     return SimpleNamespace(blk=blk, xu=xu if save else None, y1=y1 if save else None, r1=r1, y2=y2, r2=r2)
 
 
-def g_forward(net, z, save):
-    """Generator_PG.forward (reference models.py:344-353). z: [B, latent] fp32 -> (img [B, R, R] fp32, ctx)."""
+def g_forward(net, z, save, img_out=None):
+    """Generator_PG.forward (reference models.py:344-353). z: [B, latent] fp32 -> (img [B, R, R] fp32, ctx).
+    img_out: optional preallocated [B, R, R] fp32 tensor that receives the image."""
     leak = net.LeakyReLU_neg_slope
     alpha = net.alpha_value()
     lin, conv0 = net.layers[0], net.layers[4]
@@ -126,7 +174,7 @@ def g_forward(net, z, save):
     ctx = (SimpleNamespace(z=z, y0=y0, r0=r0, yc=yc, rc=rc, recs=recs, alpha=alpha, new=None, toim=net.ToIm,
                            toim_new=None) if save else None)
     if alpha >= 1:
-        img = ops.toim_fwd(y, _flat(net.ToIm.weight))
+        img = ops.toim_fwd(y, _flat(net.ToIm.weight), out=img_out)
         if save:
             ctx.img = img
         return img, ctx
@@ -134,7 +182,7 @@ def g_forward(net, z, save):
     img_old = ops.toim_fwd(y, _flat(net.ToIm.weight))
     new = _g_block_fwd(net.conv_block_list[0], y, leak, save)
     img_end = ops.toim_fwd(new.y2, _flat(net.ToIm_list[0].weight))
-    img = ops.lerp(ops.up2_image(img_old), img_end, alpha)
+    img = ops.lerp(ops.up2_image(img_old), img_end, alpha, out=img_out)
     if save:
         ctx.new, ctx.img_old, ctx.img_end, ctx.toim_new = new, img_old, img_end, net.ToIm_list[0]
     return img, ctx
@@ -144,9 +192,9 @@ def _g_block_bwd(rec, ga2, y_prev, r_prev, leak, sink, extra_pre=None, extra_w=N
     """Backward through one generator block given ga2 (gradient at conv2's pre-activation); returns the
     gradient at the pre-activation of the stage below (whose output y_prev was upsampled into this block)."""
     c1, c2 = rec.blk.conv1, rec.blk.conv2
-    ops.conv3x3_wgrad(rec.y1, ga2, c2.scale_value, _sink_get(sink, c2.weight))
+    _wgrad(rec.y1, ga2, c2.scale_value, _sink_get(sink, c2.weight))
     ga1, _ = ops.conv3x3_dgrad_pn(ga2, conv_images(c2)[1], c2.scale_value, leak, rec.y1, rec.r1)
-    ops.conv3x3_wgrad(rec.xu, ga1, c1.scale_value, _sink_get(sink, c1.weight))
+    _wgrad(rec.xu, ga1, c1.scale_value, _sink_get(sink, c1.weight))
     g_up = ops.conv3x3_dgrad(ga1, conv_images(c1)[1], c1.scale_value, c1.in_channels)
     return ops.up2_bwd_pn_bwd(g_up, y_prev, r_prev, extra_pre, extra_w, leak)
 
@@ -172,7 +220,7 @@ def g_backward(net, ctx, g_img, sink):
         y_prev, r_prev = (ctx.recs[i - 1].y2, ctx.recs[i - 1].r2) if i > 0 else (ctx.yc, ctx.rc)
         ga = _g_block_bwd(ctx.recs[i], ga, y_prev, r_prev, leak, sink)
     lin, conv0 = net.layers[0], net.layers[4]
-    ops.conv3x3_wgrad(ctx.y0, ga, conv0.scale_value, _sink_get(sink, conv0.weight))
+    _wgrad(ctx.y0, ga, conv0.scale_value, _sink_get(sink, conv0.weight))
     ga0, _ = ops.conv3x3_dgrad_pn(ga, conv_images(conv0)[1], conv0.scale_value, leak, ctx.y0, ctx.r0)
     ops.linear_wgrad(ga0, ctx.z, lin.scale_value, _sink_get(sink, lin.weight))
 
@@ -257,7 +305,7 @@ def d_backward(net, ctx, gout, sink, addins=None, want_gxp=False, record=None):
         record.gout = gout
         record.stages = {}
     if sink is not None:
-        ops.conv3x3_wgrad(ctx.last_x, ga_l, last.scale_value, _sink_get(sink, last.weight))
+        _wgrad(ctx.last_x, ga_l, last.scale_value, _sink_get(sink, last.weight))
         ops.bias_grad(ga_l, _sink_get(sink, last.bias))
 
     top = ctx.stages[-1]
@@ -286,11 +334,11 @@ def d_backward(net, ctx, gout, sink, addins=None, want_gxp=False, record=None):
                 ga2, gy2 = ops.pn_bwd(g, st.y2, st.r2, gscale=gs * (0.25 if recv_unpool else 1.0),
                                       unpool=recv_unpool, addin=a2, want_gy=rec, leak=leak)
             if sink is not None:
-                ops.conv3x3_wgrad(st.y1, ga2, c2.scale_value, _sink_get(sink, c2.weight))
+                _wgrad(st.y1, ga2, c2.scale_value, _sink_get(sink, c2.weight))
             ga1, gy1 = ops.conv3x3_dgrad_pn(ga2, conv_images(c2)[1], c2.scale_value, leak, st.y1, st.r1, addin=a1,
                                             want_gy=rec)
             if sink is not None:
-                ops.conv3x3_wgrad(st.xin, ga1, c1.scale_value, _sink_get(sink, c1.weight))
+                _wgrad(st.xin, ga1, c1.scale_value, _sink_get(sink, c1.weight))
             if rec:
                 record.stages[id(st)] = SimpleNamespace(gy1=gy1, ga1=ga1, gy2=gy2, ga2=ga2, recv_unpool=recv_unpool)
             incoming = ('g', ops.conv3x3_dgrad(ga1, conv_images(c1)[1], c1.scale_value, c1.in_channels), 1.0,
@@ -339,9 +387,9 @@ def d_double_backward_sweep1(net, ctx, record, ghat_xp, sink):
                 cur = ops.avgpool2(cur)
         elif st.kind == 'block':
             c1, c2 = st.blk.conv1, st.blk.conv2
-            ops.conv3x3_wgrad(cur, r.ga1, c1.scale_value, _sink_get(sink, c1.weight))
+            _wgrad(cur, r.ga1, c1.scale_value, _sink_get(sink, c1.weight))
             gh1, ah1 = ops.conv3x3_dbl(cur, conv_images(c1)[0], c1.scale_value, leak, st.y1, st.r1, r.gy1)
-            ops.conv3x3_wgrad(gh1, r.ga2, c2.scale_value, _sink_get(sink, c2.weight))
+            _wgrad(gh1, r.ga2, c2.scale_value, _sink_get(sink, c2.weight))
             gh2, ah2 = ops.conv3x3_dbl(gh1, conv_images(c2)[0], c2.scale_value, leak, st.y2, st.r2, r.gy2)
             addins[id(st)] = (ah1, ah2)
             cur = gh2          # cotangent on gy2; the fade stage (if next) applies alpha and the pooling itself
@@ -358,7 +406,7 @@ def d_double_backward_sweep1(net, ctx, record, ghat_xp, sink):
             if r.unpool:
                 cur = ops.avgpool2(cur)
     last, head = net.last_conv(), net.head_conv()
-    ops.conv3x3_wgrad(cur, record.last.ga, last.scale_value, _sink_get(sink, last.weight))
+    _wgrad(cur, record.last.ga, last.scale_value, _sink_get(sink, last.weight))
     gh_l, ah_l = ops.conv3x3_dbl(cur, conv_images(last)[0], last.scale_value, leak, ctx.yl, ctx.rl, record.last.gy)
     ops.head_wgrad(gh_l, record.gout, head.scale_value, _sink_get(sink, head.weight))
     addins['last'] = ah_l

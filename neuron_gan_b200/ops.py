@@ -177,8 +177,8 @@ def up2_image_bwd(g, scale=1.0):
     return out
 
 
-def lerp(a, b, alpha):
-    out = torch.empty_like(a)
+def lerp(a, b, alpha, out=None):
+    out = torch.empty_like(a) if out is None else out
     _lib.call('ngan_lerp', _p(a, F32), _p(b, F32), alpha, _p(out), a.numel(), _stream())
     return out
 
@@ -237,9 +237,10 @@ def fromim_dbl(ghat_xp, g, w, what, in_scale=1.0, gscale=1.0, unpool=False, want
     return out
 
 
-def toim_fwd(y, w):
+def toim_fwd(y, w, out=None):
     B, C, H, W = c8_dims(y)
-    img = torch.empty((B, H, W), dtype=F32, device=y.device)
+    img = torch.empty((B, H, W), dtype=F32, device=y.device) if out is None else out
+    assert img.shape == (B, H, W) and img.dtype == F32
     _lib.call('ngan_toim_fwd', _p(y, BF16), _p(w, F32), _p(img), B, C, H, W, _stream())
     return img
 
@@ -330,9 +331,14 @@ def gp_loss(g, norm_scale, lam, gscale=1.0):
     return pen, coeff
 
 
+def pack_stats(out3, out1, pen, stats):
+    _lib.call('ngan_pack_stats', _p(out3, F32), _p(out1, F32), _p(pen, F32), _p(stats, F32), _stream())
+    return stats
+
+
 # ------------------------------------------------------------------------------------------ Adam
 def adam_multi(entries, beta1, beta2, eps):
-    """entries: list of dicts(p, g, m, v, shadow|None, step_size, inv_bc2_sqrt)"""
+    """entries: list of dicts(p, g, m, v, shadow|None, step_size, inv_bc2_sqrt, dyn|None)"""
     n = len(entries)
     if n == 0:
         return
@@ -346,4 +352,5 @@ def adam_multi(entries, beta1, beta2, eps):
         arr[i].n = e['p'].numel()
         arr[i].step_size = e['step_size']
         arr[i].inv_bc2_sqrt = e['inv_bc2_sqrt']
+        arr[i].dyn = e['dyn'].data_ptr() if e.get('dyn') is not None else None
     _lib.call('ngan_adam_multi', ctypes.cast(arr, ctypes.c_void_p), n, beta1, beta2, eps, _stream())

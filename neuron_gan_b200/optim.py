@@ -1,47 +1,112 @@
 """FusedAdam: torch.optim.Adam semantics (reference train.py:220-225) with the whole step as one multi-tensor
 kernel launch per network.  Keeps torch's state layout (`step`, `exp_avg`, `exp_avg_sq` per parameter) and
-`param_groups[...]['lr']`, which the reference's update_lr (train.py:250-265) mutates."""
+`param_groups[...]['lr']`, which the reference's update_lr (train.py:250-265) mutates.
+
+`step()` = `advance()` + `launch()`.  With `capturable=True` the two per-parameter scalars that change every step
+(lr / (1 - beta1^t) and 1 / sqrt(1 - beta2^t)) live in a small device buffer that `advance()` refreshes from the
+host, so a `launch()` captured in a CUDA graph stays valid across steps and learning-rate changes."""
 import math
 
 import torch
 
 from . import engine, ops
 
+_CHUNK = 48          # tensors per launch (kAdamMaxTensors in csrc/adam.cu)
+
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.capturable = capturable
+        self._dyn = None            # device [n_params, 2] fp32, capturable mode
+        self._slot = {}
 
-    @torch.no_grad()
-    def step(self, closure=None):
-        loss = closure() if closure is not None else None
+    # -- helpers -----------------------------------------------------------------------------------------
+    def _active(self):
         for group in self.param_groups:
-            beta1, beta2 = group['betas']
-            lr = group['lr']
-            entries, touched = [], []
             for p in group['params']:
                 if p.grad is None:            # inactive blocks: skipped, step count does not advance
                     continue
                 if not p.is_cuda:
                     raise RuntimeError('FusedAdam runs on CUDA parameters only (no CPU fallback)')
-                st = self.state[p]
-                if not st:
-                    st['step'] = 0
-                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st['step'] += 1
-                t = st['step']
+                yield group, p
+
+    def _state(self, p):
+        st = self.state[p]
+        if not st:
+            st['step'] = 0
+            st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        return st
+
+    def _ensure_dyn(self, device):
+        if self._dyn is None:
+            n = 0
+            for group in self.param_groups:
+                for p in group['params']:
+                    self._slot[id(p)] = n
+                    n += 1
+            self._dyn = torch.zeros((n, 2), dtype=torch.float32, device=device)
+        return self._dyn
+
+    @staticmethod
+    def _scalars(group, t):
+        beta1, beta2 = group['betas']
+        return group['lr'] / (1 - beta1 ** t), 1 / math.sqrt(1 - beta2 ** t)
+
+    # -- the two halves of a step ----------------------------------------------------------------------------
+    @torch.no_grad()
+    def advance(self):
+        """Host half: bump every active parameter's step count; in capturable mode also ship this step's
+        bias-correction scalars to the device buffer (one small async copy from pinned memory)."""
+        host, dev = None, None
+        for group, p in self._active():
+            st = self._state(p)
+            st['step'] += 1
+            if self.capturable:
+                if host is None:
+                    dev = self._ensure_dyn(p.device)
+                    # fresh pinned block per step: the caching host allocator keeps it alive until the copy ran
+                    host = torch.zeros(dev.shape, dtype=torch.float32, pin_memory=True)
+                a, b = self._scalars(group, st['step'])
+                i = self._slot[id(p)]
+                host[i, 0] = a
+                host[i, 1] = b
+        if host is not None:
+            dev.copy_(host, non_blocking=True)
+
+    @torch.no_grad()
+    def launch(self):
+        """Device half: one multi-tensor kernel per <= 48 tensors, on the current stream (capturable)."""
+        for group in self.param_groups:
+            beta1, beta2 = group['betas']
+            entries, touched = [], []
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                st = self._state(p)
                 shadow = None
                 if p.dim() == 2:              # the generator's Linear weight keeps a same-layout bf16 shadow
                     ent = engine._cache_get(p)
                     if ent is not None and 'shadow' in ent:
                         shadow = ent['shadow']
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                entries.append(dict(p=p, g=g, m=st['exp_avg'], v=st['exp_avg_sq'], shadow=shadow,
-                                    step_size=lr / (1 - beta1 ** t), inv_bc2_sqrt=1 / math.sqrt(1 - beta2 ** t)))
+                if self.capturable:
+                    self._ensure_dyn(p.device)
+                    a, b, dyn = 0.0, 0.0, self._dyn[self._slot[id(p)]]
+                else:
+                    (a, b), dyn = self._scalars(group, max(st['step'], 1)), None
+                entries.append(dict(p=p, g=g, m=st['exp_avg'], v=st['exp_avg_sq'], shadow=shadow, step_size=a,
+                                    inv_bc2_sqrt=b, dyn=dyn))
                 touched.append((p, shadow is not None))
-            for i in range(0, len(entries), 64):
-                ops.adam_multi(entries[i:i + 64], beta1, beta2, group['eps'])
+            for i in range(0, len(entries), _CHUNK):
+                ops.adam_multi(entries[i:i + _CHUNK], beta1, beta2, group['eps'])
             for p, fresh in touched:
                 engine.mark_updated(p, shadow_is_fresh=fresh)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        self.advance()
+        self.launch()
         return loss

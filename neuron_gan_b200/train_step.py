@@ -14,11 +14,12 @@ shard of the batch and the flat gradient buffers are all-reduced (mean) over NCC
 is exact for this loss (batch means of per-sample terms, no cross-sample layers).
 """
 import math
+from types import SimpleNamespace
 
 import torch
 import torch.distributed as dist
 
-from . import engine, ops
+from . import _lib, engine, ops
 from .optim import FusedAdam
 from .utils import sample_latent_vec
 
@@ -26,18 +27,27 @@ F32 = torch.float32
 
 
 class TrainStep:
+    """use_graph: None = capture the iteration into a CUDA graph as soon as the same configuration (batch,
+    resolution, alpha, active parameters) has been seen twice in a row, and replay it from then on; False = always
+    launch kernel by kernel.  Captured or not, the kernels and their order are identical."""
+
     def __init__(self, generator_net, discriminator_net, learning_rate=1e-4, beta1=0.5, grad_pen_lambda=10.0,
-                 drift_epsilon=1e-3, data_parallel=None):
+                 drift_epsilon=1e-3, data_parallel=None, use_graph=None):
         self.G, self.D = generator_net, discriminator_net
         self.lam, self.drift = float(grad_pen_lambda), float(drift_epsilon)
-        self.opt_g = FusedAdam(self.G.parameters(), lr=learning_rate, betas=(beta1, 0.999))
-        self.opt_d = FusedAdam(self.D.parameters(), lr=learning_rate, betas=(beta1, 0.999))
+        self.opt_g = FusedAdam(self.G.parameters(), lr=learning_rate, betas=(beta1, 0.999), capturable=True)
+        self.opt_d = FusedAdam(self.D.parameters(), lr=learning_rate, betas=(beta1, 0.999), capturable=True)
         if data_parallel is None:
             data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.dp = data_parallel
+        self.use_graph = use_graph
+        self.fork_chains = True         # run the two independent halves of the critic step on two streams
+        self._chain_stream = None
         self._bound = {}
-        self.kernel_launches = 0
-        self._pending_stats = None
+        self._graphs = {}
+        self._last_key = None
+        self._versions_seen = None
+        self.launches_per_step = 0      # kernels of libngan_b200.so launched (or replayed) by the last iteration
 
     # -- flat gradient buffers ---------------------------------------------------------------------------
     def _bind(self, net):
@@ -70,51 +80,165 @@ class TrainStep:
         z2 = sample_latent_vec((batch, self.G.latent_dim))
         eps = torch.rand((batch, 1, 1, 1))          # CPU generator for reproducibility
         z3 = sample_latent_vec((batch, self.G.latent_dim))
-        return tuple(t.to(device, non_blocking=True) for t in (z1, z2, eps, z3))
+        pin = torch.cuda.is_available()
+        return tuple((t.pin_memory() if pin else t).to(device, non_blocking=True) for t in (z1, z2, eps, z3))
 
-    @torch.no_grad()
-    def __call__(self, images, draws=None):
-        """images: [B, 1, R, R] fp32 on the GPU (this rank's shard).  Returns a device tensor
-        [D_loss, score_real, score_fake, G_loss, D_grad_pen] (D_loss includes the penalty, train.py:362)."""
-        G, D = self.G, self.D
-        dev = images.device
-        B = images.shape[0]
-        x = images.reshape(B, images.shape[-2], images.shape[-1]).to(F32).contiguous()
-        z1, z2, eps, z3 = draws if draws is not None else self.draw(B, dev)
-        eps = eps.reshape(B).to(F32).contiguous()
+    # -- the iteration as three kernel sequences; gradients are complete at the end of seg_d and seg_g -----------
+    def _buffers(self, B, R, dev):
+        """Step inputs: imgs = [x | G(z1) | G(z2)] (the critic batch [real; fake] and x_tilde are views of it),
+        z12 = [z1; z2] (both detached generator passes of the critic step run as one batch)."""
+        L = self.G.latent_dim
+        return SimpleNamespace(imgs=torch.empty((3 * B, R, R), dtype=F32, device=dev),
+                               z12=torch.empty((2 * B, L), dtype=F32, device=dev),
+                               z3=torch.empty((B, L), dtype=F32, device=dev),
+                               eps=torch.empty((B,), dtype=F32, device=dev), B=B, out=SimpleNamespace())
 
-        # ---------------- critic step (train.py:356-366)
+    @staticmethod
+    def _load(buf, x, z1, z2, eps, z3):
+        B = buf.B
+        buf.imgs[:B].copy_(x.reshape(B, x.shape[-2], x.shape[-1]), non_blocking=True)
+        buf.z12[:B].copy_(z1, non_blocking=True)
+        buf.z12[B:].copy_(z2, non_blocking=True)
+        buf.eps.copy_(eps.reshape(B), non_blocking=True)
+        buf.z3.copy_(z3, non_blocking=True)
+
+    def _seg_d(self, buf):
+        """critic step up to complete gradients (train.py:356-365).  After the shared generator pass the
+        Wasserstein part ([real; fake] forward + backward) and the gradient-penalty part (x_hat forward,
+        first-order backward, double backward) are independent chains that only meet in the gradient buffer
+        (atomics): they run on two streams, so the narrow low-resolution kernels of one fill the SMs the other
+        leaves idle."""
+        G, D, B = self.G, self.D, buf.B
         flat_d, sink_d = self._bind(D)
         flat_d.zero_()
-        fake, _ = engine.g_forward(G, z1, save=False)
-        scores, ctx = engine.d_forward(D, torch.cat([x, fake]), save=True)
-        gout = torch.empty(2 * B, dtype=F32, device=dev)
-        out3, _, _ = ops.wloss_into(scores[:B], scores[B:], self.drift, gout[:B], gout[B:])
+        engine.g_forward(G, buf.z12, save=False, img_out=buf.imgs[B:])
+        main = torch.cuda.current_stream()
+        fork = self.fork_chains
+        if fork:
+            if self._chain_stream is None:
+                self._chain_stream = torch.cuda.Stream()
+            engine.prepare_weights(D)
+            self._chain_stream.wait_stream(main)
+        with torch.cuda.stream(self._chain_stream if fork else main):
+            x_hat = ops.interp_images(buf.imgs[:B], buf.imgs[2 * B:], buf.eps)
+            buf.out.pen, _, _ = engine.d_grad_penalty(D, x_hat, self.lam, sink_d)
+            del x_hat
+        scores, ctx = engine.d_forward(D, buf.imgs[:2 * B], save=True)
+        gout = torch.empty(2 * B, dtype=F32, device=scores.device)
+        buf.out.out3, _, _ = ops.wloss_into(scores[:B], scores[B:], self.drift, gout[:B], gout[B:])
         engine.d_backward(D, ctx, gout, sink_d)
         del ctx
-        x_tilde, _ = engine.g_forward(G, z2, save=False)
-        x_hat = ops.interp_images(x, x_tilde, eps)
-        pen, _, _ = engine.d_grad_penalty(D, x_hat, self.lam, sink_d)
-        self._allreduce(flat_d)
-        self.opt_d.step()
+        if fork:
+            main.wait_stream(self._chain_stream)
+        engine.side_join()
+        return flat_d
 
-        # ---------------- generator step (train.py:375-385)
+    def _seg_g(self, buf):
+        """Adam(D) (train.py:366), then the generator step up to complete gradients (train.py:375-384)"""
+        G, D = self.G, self.D
+        self.opt_d.launch()
         flat_g, sink_g = self._bind(G)
         flat_g.zero_()
-        fake, gctx = engine.g_forward(G, z3, save=True)
+        fake, gctx = engine.g_forward(G, buf.z3, save=True)
         s_fake, dctx = engine.d_forward(D, fake, save=True)
-        out1, g_fake = ops.gloss(s_fake)
+        buf.out.out1, g_fake = ops.gloss(s_fake)
         g_xp = engine.d_backward(D, dctx, g_fake, None, want_gxp=True)
         gx = ops.unpool_image(g_xp, 0.25) if dctx.pooled else g_xp
         del dctx
         engine.g_backward(G, gctx, gx, sink_g)
         del gctx
-        self._allreduce(flat_g)
-        self.opt_g.step()
+        engine.side_join()
+        return flat_g
 
-        stats = torch.cat([out3, out1, pen])
-        stats[0] += stats[4]
+    def _seg_end(self, buf):
+        """Adam(G) (train.py:385) and the packed statistics (train.py:362, 389-394)"""
+        self.opt_g.launch()
+        stats = torch.empty(5, dtype=F32, device=buf.z3.device)
+        ops.pack_stats(buf.out.out3, buf.out.out1, buf.out.pen, stats)
         return stats
+
+    def _run_eager(self, buf):
+        n0 = _lib.launch_count
+        stats = self._run_eager_body(buf)
+        self.launches_per_step = _lib.launch_count - n0
+        return stats
+
+    def _run_eager_body(self, buf):
+        self._bind(self.D)          # p.grad views must exist before advance(): it skips parameters without grad
+        self._bind(self.G)
+        self.opt_d.advance()
+        self.opt_g.advance()
+        self._allreduce(self._seg_d(buf))
+        self._allreduce(self._seg_g(buf))
+        return self._seg_end(buf)
+
+    # -- CUDA-graph capture ----------------------------------------------------------------------------------
+    def _versions(self):
+        return tuple(p._version for net in (self.G, self.D) for p in net.parameters())
+
+    def _config_key(self, B, R):
+        return (B, R, self.G.alpha_value(), self.D.alpha_value(), self.G.N_layers, self.D.N_layers, self.dp,
+                self.lam, self.drift,
+                tuple(id(p) for p in self.G.active_parameters()), tuple(id(p) for p in self.D.active_parameters()))
+
+    def _capture(self, key, B, R, dev):
+        buf = self._buffers(B, R, dev)
+        ent = SimpleNamespace(buf=buf, graphs=[], flats=[], stats=None, launches=0)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count
+        pool = None
+        segs = [self._seg_d, self._seg_g, self._seg_end]
+        if not self.dp:          # single GPU: the whole iteration is one graph
+            segs = [lambda b: (self._seg_d(b), self._seg_g(b), self._seg_end(b))[-1]]
+        for seg in segs:         # data parallel: the two gradient all-reduces sit between three graphs
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                res = seg(buf)
+            pool = g.pool()
+            ent.graphs.append(g)
+            ent.flats.append(res)
+        ent.stats = ent.flats[-1]
+        ent.launches = _lib.launch_count - n0
+        _lib.launch_count = n0          # captured, not launched
+        self._graphs[key] = ent
+        return ent
+
+    @torch.no_grad()
+    def __call__(self, images, draws=None):
+        """images: [B, 1, R, R] fp32 (this rank's shard; GPU tensor, or pinned host tensor).  Returns a device tensor
+        [D_loss, score_real, score_fake, G_loss, D_grad_pen] (D_loss includes the penalty, train.py:362)."""
+        dev = next(self.G.parameters()).device
+        B, R = images.shape[0], images.shape[-1]
+        z1, z2, eps, z3 = draws if draws is not None else self.draw(B, dev)
+        key = self._config_key(B, R)
+        ent = self._graphs.get(key)
+        versions = self._versions()
+        if self.use_graph is False or ent is None or versions != self._versions_seen:
+            # kernel-by-kernel iteration: first sight of a configuration, or parameters changed from outside
+            # (load_state_dict ...) so the bf16 weight images must be refreshed by the host-side cache logic
+            buf = self._buffers(B, R, dev) if ent is None else ent.buf
+            self._load(buf, images, z1, z2, eps, z3)
+            stats = self._run_eager(buf)
+            self._versions_seen = self._versions()
+            if self.use_graph is not False and ent is None and key == self._last_key:
+                self._capture(key, B, R, dev)
+            self._last_key = key
+            return stats.clone() if ent is not None else stats
+        self._load(ent.buf, images, z1, z2, eps, z3)
+        self.opt_d.advance()
+        self.opt_g.advance()
+        if len(ent.graphs) == 1:
+            ent.graphs[0].replay()
+        else:
+            ent.graphs[0].replay()
+            self._allreduce(ent.flats[0])
+            ent.graphs[1].replay()
+            self._allreduce(ent.flats[1])
+            ent.graphs[2].replay()
+        self._last_key = key
+        self.launches_per_step = ent.launches
+        _lib.launch_count += ent.launches
+        return ent.stats.clone()
 
     @staticmethod
     def stats_dict(stats_host):

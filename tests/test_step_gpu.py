@@ -242,3 +242,54 @@ def test_gradients_match_bf16_emulating_oracle(res, alpha, batch):
     med_tol, max_tol = {16: (0.02, 0.04), 32: (0.06, 0.10), 64: (0.08, 0.30), 128: (0.12, 0.35)}.get(res, (0.20, 0.90))
     assert vals[len(vals) // 2] < med_tol, report
     assert vals[-1] < max_tol, report
+
+
+def _snapshot(nets_, opts):
+    params = [[p.detach().clone() for p in n.parameters()] for n in nets_]
+    states = [{p: (st['step'], st['exp_avg'].clone(), st['exp_avg_sq'].clone()) for p, st in o.state.items()}
+              for o in opts]
+    return params, states
+
+
+def _restore(nets_, opts, snap):
+    params, states = snap
+    with torch.no_grad():
+        for n, saved in zip(nets_, params):
+            for p, v in zip(n.parameters(), saved):
+                p.copy_(v)                      # in place: the captured graph keeps pointing at these tensors
+        for o, saved in zip(opts, states):
+            for p, (t, m, v) in saved.items():
+                o.state[p]['step'] = t
+                o.state[p]['exp_avg'].copy_(m)
+                o.state[p]['exp_avg_sq'].copy_(v)
+
+
+@pytest.mark.parametrize('res,alpha,batch', [(16, 1.0, 8), (64, 0.5, 4), (128, 1.0, 2)])
+def test_graph_replay_equals_eager(res, alpha, batch):
+    """One iteration replayed from the captured CUDA graph (critic step forked over two streams, wgrad kernels on a
+    third, Adam scalars read from device memory) against the same iteration launched kernel by kernel from the
+    same weights, optimiser state, images and draws."""
+    from neuron_gan_b200.train_step import TrainStep
+    G, D = nets(res, alpha)
+    step = TrainStep(G, D)
+    xs = [O.synthetic_images(batch, res, seed=40 + i).to(DEV) for i in range(4)]
+    draws = [tuple(t.to(DEV) for t in draws_like_reference(batch)) for _ in range(4)]
+    step(xs[0], draws[0])
+    step(xs[1], draws[1])                                  # second sight of the configuration: captured afterwards
+    assert len(step._graphs) == 1
+    launches_eager = step.launches_per_step
+    snap = _snapshot((G, D), (step.opt_g, step.opt_d))
+    s_replay = step(xs[2], draws[2]).cpu()
+    assert step.launches_per_step == launches_eager
+    after_replay = [[p.detach().clone() for p in n.parameters()] for n in (G, D)]
+    _restore((G, D), (step.opt_g, step.opt_d), snap)       # bumps the parameter versions -> next call runs eagerly
+    s_eager = step(xs[2], draws[2]).cpu()
+    assert torch.allclose(s_replay, s_eager, rtol=1e-4, atol=2e-5), (s_replay, s_eager)
+    # fp32 atomics make the last bits of a gradient run-dependent; Adam turns a sign change of a ~0 gradient
+    # element into a 2*lr difference, so compare in the mean and bound the maximum
+    for n, saved in zip((G, D), after_replay):
+        for (k, p), v in zip(n.named_parameters(), saved):
+            d = (p.detach() - v).abs()
+            assert d.max().item() <= 2.1e-4 and d.mean().item() < 2e-6, (k, d.max().item(), d.mean().item())
+    s_next = step(xs[3], draws[3]).cpu()                   # and the graph is used again afterwards
+    assert torch.isfinite(s_next).all() and step.launches_per_step == launches_eager
