@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument('--batch', type=int, default=16, help='images per GPU')
     ap.add_argument('--cpu-batch', type=int, default=0, help='batch of the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch kernel by kernel instead of replaying a CUDA graph')
     ap.add_argument('--no-profile', action='store_true', help='skip the per-kernel timing pass (roofline)')
     ap.add_argument('--dump-kernels', default='', help='write the full per-kernel table of the timing pass here')
     return ap.parse_args()
@@ -193,7 +194,7 @@ def run_b200(args):
 
     B, res, alpha = args.batch, args.res, args.alpha
     G, D = build_networks(res, alpha, seed=1, device=dev)
-    step = TrainStep(G, D)
+    step = TrainStep(G, D, use_graph=False if args.no_graph else None)
     # a small pool of different synthetic batches, pinned on the host and mirrored on the device
     n_pool = 4
     host = [O.synthetic_images(B, res, seed=100 + rank * 17 + i).pin_memory() for i in range(n_pool)]

@@ -114,9 +114,13 @@ int ngan_head_bwd_pn(const float* gout, const float* w, float scale, const void*
 int ngan_head_wgrad(const void* t_c8, const float* coeff, float scale, float* gw, int B, int C, int S, void* stream);
 
 /* ---- generator stem: Linear_normalized + Unflatten + LeakyReLU + PixelNorm, models.py:299-311 ---- */
-int ngan_prep_linear_weight(const float* w, void* w_bf16, long long n, void* stream);
-int ngan_linear_fwd(const float* z, const void* w_bf16, float scale, float leak, void* y_c8, float* r, int B, int K,
-                    int C, int S, void* stream);
+/* fp32 master [C*S*S][K] -> bf16 operand image [S*S][K/8][C][8] (the C weight rows of one pixel form one
+ * contiguous no-swizzle K-major UMMA operand) */
+int ngan_prep_linear_weight(const float* w, void* w_img, int K, int C, int S, void* stream);
+/* bytes of scratch ngan_linear_fwd needs (the latent batch as a bf16 UMMA operand, padded to 128 rows) */
+long long ngan_linear_fwd_workspace_bytes(int B, int K);
+int ngan_linear_fwd(const float* z, const void* w_img, float scale, float leak, void* y_c8, float* r, void* workspace,
+                    int B, int K, int C, int S, void* stream);
 int ngan_linear_wgrad(const void* ga_c8, const float* z, float scale, float* dw, int B, int K, int C, int S,
                       void* stream);
 
@@ -143,6 +147,9 @@ typedef struct {
     long long n;
     float step_size;     /* lr / (1 - beta1^t), t = this parameter's step count after the update */
     float inv_bc2_sqrt;  /* 1 / sqrt(1 - beta2^t) */
+    int shadow_k, shadow_c, shadow_ss;   /* 0, or the dims of ngan_prep_linear_weight's image: the shadow of element
+                            (f, k) of a [C*SS][K] parameter is then written at its place in [SS][K/8][C][8] */
+    int reserved;
     const float* dyn;    /* optional DEVICE pointer to {step_size, inv_bc2_sqrt}; when non-NULL it overrides the two
                             fields above at run time (lets a launch captured in a CUDA graph follow the step count) */
 } ngan_adam_tensor;

@@ -15,7 +15,8 @@ class AdamTensor(ctypes.Structure):
     """Mirror of ngan_adam_tensor."""
     _fields_ = [('p', ctypes.c_void_p), ('g', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p),
                 ('shadow_bf16', ctypes.c_void_p), ('n', ctypes.c_longlong), ('step_size', ctypes.c_float),
-                ('inv_bc2_sqrt', ctypes.c_float), ('dyn', ctypes.c_void_p)]
+                ('inv_bc2_sqrt', ctypes.c_float), ('shadow_k', ctypes.c_int), ('shadow_c', ctypes.c_int),
+                ('shadow_ss', ctypes.c_int), ('reserved', ctypes.c_int), ('dyn', ctypes.c_void_p)]
 
 
 def parse_header(path=HEADER_PATH):
@@ -23,7 +24,7 @@ def parse_header(path=HEADER_PATH):
     src = open(path).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
     protos = {}
-    for m in re.finditer(r'\b(int|const char\*)\s+(ngan_\w+)\s*\(([^)]*)\)\s*;', src):
+    for m in re.finditer(r'\b(int|long long|const char\*)\s+(ngan_\w+)\s*\(([^)]*)\)\s*;', src):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         parsed = []
         if args and args != 'void':
@@ -34,7 +35,7 @@ def parse_header(path=HEADER_PATH):
                 else:
                     ty, nm = a.rsplit(' ', 1)
                     parsed.append((_CTYPES[ty], nm))
-        protos[name] = (ctypes.c_char_p if ret != 'int' else ctypes.c_int, parsed)
+        protos[name] = ({'int': ctypes.c_int, 'long long': ctypes.c_longlong}.get(ret, ctypes.c_char_p), parsed)
     return protos
 
 
@@ -93,6 +94,8 @@ def call(name, *args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     rc = getattr(lib, name)(*args)
+    if _protos[name][0] is not ctypes.c_int:
+        return rc
     if rc != 0:
         raise NganError(f'{name} failed ({rc}): {lib.ngan_last_error().decode()}')
     launch_count += _LAUNCHES.get(name, 1)

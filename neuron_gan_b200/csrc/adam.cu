@@ -11,7 +11,7 @@
 
 namespace ngan {
 
-constexpr int kAdamMaxTensors = 48;   // 48 x 64 B: the table travels in (4 KB) kernel-parameter space
+constexpr int kAdamMaxTensors = 48;   // 48 x 80 B: the table travels in (4 KB) kernel-parameter space
 struct AdamEntry {
     float* p;
     const float* g;
@@ -21,6 +21,8 @@ struct AdamEntry {
     long long n;
     float step_size;      // lr / (1 - beta1^t)
     float inv_bc2_sqrt;   // 1 / sqrt(1 - beta2^t)
+    int shadow_k, shadow_c, shadow_ss;   // != 0: shadow is the linear operand image [SS][K/8][C][8] (linear.cu)
+    int reserved;
     const float* dyn;     // optional device pointer to {step_size, inv_bc2_sqrt}: overrides the two fields above, so a
                           // launch captured in a CUDA graph picks up the values of the current step at replay
 };
@@ -52,7 +54,14 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
             uint2 o;
             o.x = pack_bf16(p.x, p.y);
             o.y = pack_bf16(p.z, p.w);
-            reinterpret_cast<uint2*>(t.shadow)[i] = o;
+            size_t dst = static_cast<size_t>(i) * 4;
+            if (t.shadow_k) {      // element (f, k) of [C*SS][K] -> [SS][K/8][C][8]; the 4 k's stay contiguous
+                const size_t f = dst / t.shadow_k;
+                const int k = static_cast<int>(dst - f * t.shadow_k);
+                const int c = static_cast<int>(f / t.shadow_ss), px = static_cast<int>(f - static_cast<size_t>(c) * t.shadow_ss);
+                dst = ((static_cast<size_t>(px) * (t.shadow_k / 8) + (k >> 3)) * t.shadow_c + c) * 8 + (k & 7);
+            }
+            *reinterpret_cast<uint2*>(t.shadow + dst) = o;
         }
     }
     // tail (n % 4 elements), handled by the first threads of block 0
@@ -65,7 +74,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
             v = beta2 * v + (1.f - beta2) * g * g;
             p = p - step_size * (m / (sqrtf(v) * inv_bc2_sqrt + eps));
             t.p[i] = p; t.m[i] = m; t.v[i] = v;
-            if (t.shadow) t.shadow[i] = __float2bfloat16(p);
+            if (t.shadow && !t.shadow_k) t.shadow[i] = __float2bfloat16(p);   // (image layouts have n % 4 == 0)
         }
     }
 #undef NGAN_ADAM1
@@ -89,7 +98,7 @@ int adam_multi_launch(const AdamEntry* entries, int n_tensors, float beta1, floa
             return NGAN_ERR_INVALID;
         }
     }
-    for (int i = n_tensors; i < kAdamMaxTensors; ++i) tab.e[i] = AdamEntry{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0.f, nullptr};
+    for (int i = n_tensors; i < kAdamMaxTensors; ++i) tab.e[i] = AdamEntry{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0.f, 0, 0, 0, 0, nullptr};
     long long bx = (max_n / 4 + 255) / 256;
     if (bx > 148 * 8) bx = 148 * 8;
     if (bx < 1) bx = 1;

@@ -197,14 +197,17 @@ int ngan_head_wgrad(const void* t, const float* coeff, float scale, float* gw, i
     NGAN_REQUIRE(t && coeff && gw && !bad_c(C) && B > 0, "head_wgrad: bad arguments");
     return head_wgrad(t, coeff, scale, gw, B, C, Sz, S(stream));
 }
-int ngan_prep_linear_weight(const float* w, void* wb, long long n, void* stream) {
-    NGAN_REQUIRE(w && wb && n > 0, "prep_linear_weight: bad arguments");
-    return prep_linear_weight(w, wb, static_cast<size_t>(n), S(stream));
+int ngan_prep_linear_weight(const float* w, void* wb, int K, int C, int Sz, void* stream) {
+    NGAN_REQUIRE(w && wb && K > 0 && C > 0 && Sz > 0, "prep_linear_weight: bad arguments");
+    return prep_linear_weight(w, wb, K, C, Sz, S(stream));
 }
-int ngan_linear_fwd(const float* z, const void* wb, float scale, float leak, void* y, float* r, int B, int K, int C,
-                    int Sz, void* stream) {
-    NGAN_REQUIRE(z && wb && y && B > 0, "linear_fwd: bad arguments");
-    return linear_fwd_pn(z, wb, scale, leak, y, r, B, K, C, Sz, S(stream));
+long long ngan_linear_fwd_workspace_bytes(int B, int K) {
+    return static_cast<long long>((B + 127) / 128 * 128) * K * 2;
+}
+int ngan_linear_fwd(const float* z, const void* wb, float scale, float leak, void* y, float* r, void* workspace, int B,
+                    int K, int C, int Sz, void* stream) {
+    NGAN_REQUIRE(z && wb && y && workspace && B > 0, "linear_fwd: bad arguments");
+    return linear_fwd_pn(z, wb, scale, leak, y, r, workspace, B, K, C, Sz, S(stream));
 }
 int ngan_linear_wgrad(const void* ga, const float* z, float scale, float* dw, int B, int K, int C, int Sz,
                       void* stream) {

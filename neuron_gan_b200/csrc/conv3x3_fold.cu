@@ -36,9 +36,25 @@ template <int COUT, int EPI> struct FoldCfg {
     static constexpr int kEpiGroups = (COUT >= 64 || (COUT >= 32 && EPI == EPI_DBL)) ? 2 : 4;
     static constexpr int kThreads = 96 + 128 * kEpiGroups;   // producer + 2 MMA warps + epilogue groups
 };
+// timing-experiment hooks (NGAN_CONV_DEBUG / NGAN_CONV_TRACE) are compiled in only with -DNGAN_CONV_DEBUG_BUILD:
+// their predicates cost ~10 % of the instructions of the issue-bound epilogue
+#ifdef NGAN_CONV_DEBUG_BUILD
+constexpr bool kDebug = true;
+#else
+constexpr bool kDebug = false;
+#endif
 constexpr int kFoldMaxStages = 12;
 constexpr int kFoldMaxAcc = 8;            // accumulator buffers in TMEM (ring between MMA issuers and epilogue)
 constexpr uint32_t kFoldBarBytes = (1 + 2 * kFoldMaxStages + 2 * kFoldMaxAcc) * 8 + 16;
+
+// tile -> (sample, tile row, tile column) without integer division: (n + 0.5) * (1/d) truncated is exact for
+// n*d < ~4e6, far above any tile count here (a 512x512 batch of 128 has 73728 tiles)
+__device__ __forceinline__ void tile_coords(const ConvArgs& a, int tile, int& b, int& tile_y, int& tile_x) {
+    b = __float2int_rz((static_cast<float>(tile) + 0.5f) * a.inv_tiles_per_img);
+    const int t2 = tile - b * (a.tiles_x * a.tiles_y);
+    tile_y = __float2int_rz((static_cast<float>(t2) + 0.5f) * a.inv_tiles_x);
+    tile_x = t2 - tile_y * a.tiles_x;
+}
 
 // Fused pointwise tail on one output pixel held in registers (o[c] = raw accumulator sums).
 template <int COUT, int EPI>
@@ -52,12 +68,18 @@ __device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool vali
         if (a.bias == nullptr) {
             // lrelu and PixelNorm commute with the positive scale: normalise lrelu(acc) directly
             // (mean(h^2) + eps = scale^2 * (mean(v^2) + eps/scale^2)); saves one multiply per channel.
+            // Packed f32x2 arithmetic (FMUL2 / FFMA2): this epilogue is instruction-issue bound.
+            float2* o2 = reinterpret_cast<float2*>(o);
+            const float2 leak2 = make_float2(a.leak, a.leak);
+            float2 ss2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int c = 0; c < COUT; ++c) {
-                const float v = fmaxf(o[c], a.leak * o[c]);
-                ss = fmaf(v, v, ss);
-                o[c] = v;
+            for (int c = 0; c < COUT / 2; ++c) {
+                const float2 l = __fmul2_rn(o2[c], leak2);
+                const float2 v = make_float2(fmaxf(o2[c].x, l.x), fmaxf(o2[c].y, l.y));
+                ss2 = __ffma2_rn(v, v, ss2);
+                o2[c] = v;
             }
+            ss = ss2.x + ss2.y;
             const float inv_s = 1.0f / a.scale;
             k = rsqrtf(ss * inv_c + 1e-8f * inv_s * inv_s);
             rinv = k * inv_s;
@@ -73,10 +95,12 @@ __device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool vali
         }
         if (valid) {
             uint4* out = reinterpret_cast<uint4*>(a.out0) + q0;
+            float2* o2 = reinterpret_cast<float2*>(o);
+            const float2 k2 = make_float2(k, k);
 #pragma unroll
             for (int j = 0; j < NCH; ++j) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[j * 8 + e] *= k;
+                for (int e = 0; e < 4; ++e) o2[j * 4 + e] = __fmul2_rn(o2[j * 4 + e], k2);
                 out[j * HW] = pack8(o + j * 8);
             }
             if (a.rout) a.rout[p0] = rinv;
@@ -86,8 +110,10 @@ __device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool vali
             uint4* out = reinterpret_cast<uint4*>(a.out0);
 #pragma unroll
             for (int j = 0; j < NCH; ++j) {
+                float2* o2 = reinterpret_cast<float2*>(o);
+                const float2 s2 = make_float2(a.scale, a.scale);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[j * 8 + e] *= a.scale;
+                for (int e = 0; e < 4; ++e) o2[j * 4 + e] = __fmul2_rn(o2[j * 4 + e], s2);
                 out[q0 + j * HW] = pack8(o + j * 8);
             }
         }
@@ -233,25 +259,30 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-    const int tiles_per_img = a.tiles_x * a.tiles_y;
 
     if (warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(bar_w, W_BYTES);
             bulk_load_1d(s_w, a.wprep, W_BYTES, bar_w);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-                const int stage = it % a.n_stage;
-                if (it >= a.n_stage) mbar_wait(bar_empty + stage, ((it / a.n_stage) - 1) & 1);
-                const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
-                const int tile_y = t2 / a.tiles_x, tile_x = t2 - tile_y * a.tiles_x;
-                if ((a.debug & 4) && it >= a.n_stage) {
+            int stage = 0;
+            uint32_t sph = 0;        // phase of the ring: flips every time `stage` wraps
+            bool wrapped = false;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                if (wrapped) mbar_wait(bar_empty + stage, sph ^ 1);
+                int b, tile_y, tile_x;
+                tile_coords(a, tile, b, tile_y, tile_x);
+                if (kDebug && (a.debug & 4) && wrapped) {
                     mbar_arrive(bar_full + stage);       // timing experiment: reuse whatever is in the stage
-                    continue;
+                } else {
+                    mbar_arrive_expect_tx(bar_full + stage, in_bytes);
+                    tma_load_4d(s_in + stage * in_bytes, &tmap, bar_full + stage, (tile_x * kFoldTW - 1) * 2,
+                                tile_y * a.TH - 1, 0, b);
                 }
-                mbar_arrive_expect_tx(bar_full + stage, in_bytes);
-                tma_load_4d(s_in + stage * in_bytes, &tmap, bar_full + stage, (tile_x * kFoldTW - 1) * 2,
-                            tile_y * a.TH - 1, 0, b);
+                if (++stage == a.n_stage) {
+                    stage = 0;
+                    sph ^= 1;
+                    wrapped = true;
+                }
             }
         }
     } else if (warp <= 2) {
@@ -259,22 +290,33 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
         // tile the other keeps the tensor core fed.  The loop is warp-uniform; one elected lane issues.
         mbar_wait_warp(bar_w, 0, lane);
         const uint32_t w_base = smem_u32(s_w);
+        // ring positions advance by two per iteration (the other MMA warp takes the tiles in between)
+        int stage = warp - 1, buf = warp - 1;            // n_stage >= 2, n_acc >= 2
+        uint32_t sph = 0, bph = 0;
+        bool reused = false;                             // this accumulator buffer has been used before
+        auto advance = [](int& idx, uint32_t& ph, int n) {
+            if (++idx == n) {
+                idx = 0;
+                ph ^= 1;
+                return true;
+            }
+            return false;
+        };
         for (int it = warp - 1;; it += 2) {
             const int tile = blockIdx.x + it * gridDim.x;
             if (tile >= a.n_tiles) break;
-            const int stage = it % a.n_stage, buf = it % a.n_acc, use = it / a.n_acc;
-            const bool trace = a.dbg_clock && blockIdx.x == 0 && it < 32 && lane == 0;
+            const bool trace = kDebug && a.dbg_clock && blockIdx.x == 0 && it < 32 && lane == 0;
             if (trace) a.dbg_clock[it * 8 + 0] = clock64();
-            if (use > 0) mbar_wait_warp(bar_acc_empty + buf, (use - 1) & 1, lane);
+            if (reused) mbar_wait_warp(bar_acc_empty + buf, bph ^ 1, lane);
             if (trace) a.dbg_clock[it * 8 + 1] = clock64();
-            mbar_wait_warp(bar_full + stage, (it / a.n_stage) & 1, lane);
+            mbar_wait_warp(bar_full + stage, sph, lane);
             tc_fence_after();
             if (trace) a.dbg_clock[it * 8 + 2] = clock64();
             if (elect_one()) {
                 const uint32_t in_base = smem_u32(s_in + stage * in_bytes);
                 const uint32_t acc = tmem_base + buf * buf_cols;
                 const uint32_t a_hi = umma_desc_hi(128), b_hi = umma_desc_hi(128);
-                if (!(a.debug & 1)) {
+                if (!(kDebug && (a.debug & 1))) {
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
@@ -300,32 +342,37 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
             }
             __syncwarp();
             if (trace) a.dbg_clock[it * 8 + 3] = clock64();
+            advance(stage, sph, a.n_stage);
+            advance(stage, sph, a.n_stage);
+            reused |= advance(buf, bph, a.n_acc);
+            reused |= advance(buf, bph, a.n_acc);
         }
     } else {
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
         const int group = (warp - 3) >> 2;         // epilogue group: M-tiles are interleaved between the groups
         const size_t HW = static_cast<size_t>(a.H) * a.W;
-        int it = 0;
+        int it = 0, buf = 0;
+        uint32_t bph = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-            const int buf = it % a.n_acc;
-            const int b = tile / tiles_per_img, t2 = tile - b * tiles_per_img;
-            const int tile_y = t2 / a.tiles_x, tile_x = t2 - tile_y * a.tiles_x;
-            const bool trace = a.dbg_clock && blockIdx.x == 0 && it < 32 && warp == 3 && lane == 0;
+            int b, tile_y, tile_x;
+            tile_coords(a, tile, b, tile_y, tile_x);
+            const bool trace = kDebug && a.dbg_clock && blockIdx.x == 0 && it < 32 && warp == 3 && lane == 0;
             if (trace) a.dbg_clock[it * 8 + 5] = clock64();
-            mbar_wait_warp(bar_acc_full + buf, (it / a.n_acc) & 1, lane);
+            mbar_wait_warp(bar_acc_full + buf, bph, lane);
             tc_fence_after();
             if (trace) a.dbg_clock[it * 8 + 6] = clock64();
             const int ox = tile_x * kFoldTW + lane;
             // M-tiles of consecutive tiles rotate over the groups (with one M-tile per tile, tiles alternate)
-            const int mt0 = (group + kFoldEpiGroups - (it * a.nMT) % kFoldEpiGroups) % kFoldEpiGroups;
-            for (int mt = mt0; mt < ((a.debug & 2) ? 0 : a.nMT); mt += kFoldEpiGroups) {
+            const int mt0 = static_cast<int>((static_cast<unsigned>(group) - static_cast<unsigned>(it * a.nMT)) &
+                                             (kFoldEpiGroups - 1));
+            for (int mt = mt0; mt < ((kDebug && (a.debug & 2)) ? 0 : a.nMT); mt += kFoldEpiGroups) {
                 const int rr = mt * 4 + quad;      // row of the tile (Wh = 32: one warp = one row)
                 const int oy = tile_y * a.TH + rr;
                 const bool valid = (lane < kFoldTW) && (rr < a.TH) && (oy < a.H) && (ox < a.W);
                 const uint32_t taddr = tmem_base + buf * buf_cols + (static_cast<uint32_t>(quad * 32) << 16) + mt * NMMA;
-                float o[COUT];
+                __align__(8) float o[COUT];
                 if constexpr (NKX == 3) {
-                    float v1[16], v2[16];
+                    __align__(8) float v1[16], v2[16];
 #pragma unroll
                     for (int c0 = 0; c0 < COUT; c0 += 16) {
                         tmem_ld16_nowait(taddr + c0, o + c0);
@@ -333,8 +380,14 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
                         tmem_ld16_nowait(taddr + 2 * COUT + c0, v2);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            o[c0 + i] += __shfl_down_sync(0xffffffffu, v1[i], 1) + __shfl_down_sync(0xffffffffu, v2[i], 2);
+                        for (int i = 0; i < 16; i += 2) {
+                            const float2 s1 = make_float2(__shfl_down_sync(0xffffffffu, v1[i], 1),
+                                                          __shfl_down_sync(0xffffffffu, v1[i + 1], 1));
+                            const float2 s2 = make_float2(__shfl_down_sync(0xffffffffu, v2[i], 2),
+                                                          __shfl_down_sync(0xffffffffu, v2[i + 1], 2));
+                            float2* op = reinterpret_cast<float2*>(o + c0 + i);
+                            *op = __fadd2_rn(*op, __fadd2_rn(s1, s2));
+                        }
                     }
                 } else {
 #pragma unroll
@@ -349,6 +402,10 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty + buf);
             if (trace) a.dbg_clock[it * 8 + 7] = clock64();
+            if (++buf == a.n_acc) {
+                buf = 0;
+                bph ^= 1;
+            }
         }
     }
 
@@ -432,6 +489,8 @@ int conv3x3_fold_dispatch(int epi, const void* x, ConvArgs a, int B, int cin, in
     a.tiles_x = tiles_x;
     a.tiles_y = (H + TH - 1) / TH;
     a.n_tiles = a.tiles_x * a.tiles_y * B;
+    a.inv_tiles_x = 1.0f / a.tiles_x;
+    a.inv_tiles_per_img = 1.0f / (a.tiles_x * a.tiles_y);
     const uint32_t in_bytes = (cin / 8) * a.plane_bytes;
     const uint32_t w_bytes = ((9u * cin * cout * 2) + 127) & ~127u;
     // Deep ring: HBM needs ~100 KB of loads in flight per SM to run at full rate (latency x bandwidth), so the

@@ -18,6 +18,7 @@ struct ConvArgs {
     long long* dbg_clock;   // timing experiments only: per-tile clock64() trace of CTA 0, or null
     int debug;   // timing experiments only (NGAN_CONV_DEBUG): 1 = skip MMAs, 2 = skip epilogue, 4 = skip input loads
     int tiles_x, tiles_y, n_tiles;  // persistent kernel: tile grid over (B, rows, cols)
+    float inv_tiles_x, inv_tiles_per_img;
     uint32_t plane_bytes;  // (TH+2)*Wh*16
     float scale, leak;
     const __nv_bfloat16* wprep;  // per-tap image [9][CIN/8][COUT][8] or folded image [3][CIN/8][3*COUT][8]

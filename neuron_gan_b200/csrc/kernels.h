@@ -61,9 +61,9 @@ int scale_rows_f32(const float* x, const float* coeff, float scale, float* out, 
                    cudaStream_t st);
 
 // linear.cu
-int prep_linear_weight(const float* w, void* wb, size_t n, cudaStream_t st);
-int linear_fwd_pn(const float* z, const void* wb, float scale, float leak, void* y, float* r, int B, int K, int C,
-                  int S, cudaStream_t st);
+int prep_linear_weight(const float* w, void* wb, int K, int C, int S, cudaStream_t st);
+int linear_fwd_pn(const float* z, const void* wb, float scale, float leak, void* y, float* r, void* workspace, int B,
+                  int K, int C, int S, cudaStream_t st);
 int linear_wgrad(const void* ga, const float* z, float scale, float* dw, int B, int K, int C, int S,
                  cudaStream_t st);
 

@@ -69,18 +69,25 @@ def prepare_weights(net):
             conv_images(m)
 
 
+def _linear_dims(lin):
+    """(K, C, S) of the generator's Linear_normalized: latent -> C*S*S features (models.py:299-302)."""
+    return lin._ngan_dims
+
+
 def linear_shadow(lin, allocate_only=False):
-    """bf16 copy of the generator's Linear_normalized weight (same [out, in] layout)."""
+    """bf16 operand image of the generator's Linear_normalized weight, [S*S][K/8][C][8] (csrc/linear.cu)."""
     w = lin.weight
     ent = _cache_get(w)
     key = _wkey(w)
+    K, C, S = _linear_dims(lin)
     if ent is None or ent['shadow'].device != w.device:
-        ent = {'key': None, 'shadow': torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)}
+        ent = {'key': None, 'shadow': torch.empty(w.numel(), dtype=torch.bfloat16, device=w.device),
+               'shadow_dims': (K, C, S * S)}
         _cache_set(w, ent)
     if allocate_only:
         return ent
     if ent['key'] != key:
-        ops.prep_linear_weight(w.detach(), ent['shadow'])
+        ops.prep_linear_weight(w.detach(), C, S, ent['shadow'])
         ent['key'] = key
     return ent['shadow']
 
@@ -163,6 +170,7 @@ def g_forward(net, z, save, img_out=None):
     alpha = net.alpha_value()
     lin, conv0 = net.layers[0], net.layers[4]
     S, C0 = net.image_size_init, net.N_features_per_layer[0]
+    lin._ngan_dims = (lin.in_features, C0, S)
     z = z.detach().to(F32).contiguous()
     y0, r0 = ops.linear_fwd(z, linear_shadow(lin), lin.scale_value, leak, C0, S, want_r=save)
     yc, rc = _clp(y0, conv0, leak, save)

@@ -277,17 +277,26 @@ def head_wgrad(t, coeff, scale, gw):
 
 
 # ------------------------------------------------------------------------------------------ generator stem
-def prep_linear_weight(w, out=None):
-    out = torch.empty(w.shape, dtype=BF16, device=w.device) if out is None else out
-    _lib.call('ngan_prep_linear_weight', _p(w, F32), _p(out, BF16), w.numel(), _stream())
+def prep_linear_weight(w, C, S, out=None):
+    """w: fp32 [C*S*S, K] -> bf16 operand image, flat [S*S][K/8][C][8] (see csrc/linear.cu)."""
+    K = w.shape[1]
+    assert w.shape[0] == C * S * S
+    out = torch.empty(w.numel(), dtype=BF16, device=w.device) if out is None else out
+    _lib.call('ngan_prep_linear_weight', _p(w, F32), _p(out, BF16), K, C, S, _stream())
     return out
 
 
-def linear_fwd(z, w_bf16, scale, leak, C, S, want_r=True):
+def linear_image_to_matrix(img, K, C, S):
+    """Inverse permutation of prep_linear_weight (tests / debugging): image -> [C*S*S, K] bf16."""
+    return img.view(S * S, K // 8, C, 8).permute(2, 0, 1, 3).reshape(C * S * S, K)
+
+
+def linear_fwd(z, w_img, scale, leak, C, S, want_r=True):
     B, K = z.shape
     y = c8_empty(B, C, S, S, z.device)
     r = torch.empty((B, S, S), dtype=F32, device=z.device) if want_r else None
-    _lib.call('ngan_linear_fwd', _p(z, F32), _p(w_bf16, BF16), scale, leak, _p(y), _p(r), B, K, C, S, _stream())
+    ws = torch.empty(_lib.call('ngan_linear_fwd_workspace_bytes', B, K), dtype=torch.uint8, device=z.device)
+    _lib.call('ngan_linear_fwd', _p(z, F32), _p(w_img, BF16), scale, leak, _p(y), _p(r), _p(ws), B, K, C, S, _stream())
     return y, r
 
 
@@ -353,4 +362,5 @@ def adam_multi(entries, beta1, beta2, eps):
         arr[i].step_size = e['step_size']
         arr[i].inv_bc2_sqrt = e['inv_bc2_sqrt']
         arr[i].dyn = e['dyn'].data_ptr() if e.get('dyn') is not None else None
+        arr[i].shadow_k, arr[i].shadow_c, arr[i].shadow_ss = e.get('shadow_dims') or (0, 0, 0)
     _lib.call('ngan_adam_multi', ctypes.cast(arr, ctypes.c_void_p), n, beta1, beta2, eps, _stream())

@@ -124,7 +124,9 @@ def eq_conv(x, w, b=None, pad=1, leak=0.2):
 def eq_linear(z, w, leak=0.2):
     """Linear_normalized.forward (models.py:240-241), no bias in G (models.py:299-300)."""
     s = torch.tensor(he_gain(leak) / math.sqrt(w.shape[1]), dtype=z.dtype)
-    return F.linear(s * z, _q(w))
+    if _EMULATE_BF16:                       # the CUDA GEMM takes both operands in bf16 and scales the fp32 sums
+        return s * F.linear(_q(z), _q(w))
+    return F.linear(s * z, w)
 
 
 def up2(x):

@@ -25,5 +25,5 @@ def test_argument_validation_without_gpu():
 
 
 def test_adam_struct_layout_matches_header():
-    assert ctypes.sizeof(_lib.AdamTensor) == 64
-    assert _lib.AdamTensor.n.offset == 40 and _lib.AdamTensor.step_size.offset == 48 and _lib.AdamTensor.dyn.offset == 56
+    assert ctypes.sizeof(_lib.AdamTensor) == 80
+    assert _lib.AdamTensor.n.offset == 40 and _lib.AdamTensor.step_size.offset == 48 and _lib.AdamTensor.dyn.offset == 72

@@ -263,8 +263,8 @@ def test_linear(B):
     s = GAIN / math.sqrt(K)
     h = F.leaky_relu(F.linear(s * z, w), LEAK).unflatten(1, (C, S, S))
     y_ref, r_ref = pn_ref(h)
-    wb = o.prep_linear_weight(w)
-    assert torch.equal(wb.float(), w)
+    wb = o.prep_linear_weight(w, C, S)
+    assert torch.equal(o.linear_image_to_matrix(wb, K, C, S).float(), w.to(torch.bfloat16).float())
     y, r = o.linear_fwd(z, wb, s, LEAK, C, S)
     assert rel(o.c8_to_nchw(y), y_ref) < 5e-3
     assert rel(r, r_ref[:, 0]) < 1e-3
@@ -313,3 +313,14 @@ def test_adam_multi():
     for p, q in zip(ps, ref):
         assert torch.allclose(p, q.data, rtol=1e-5, atol=1e-6)
     assert torch.equal(shadow, ps[0].to(torch.bfloat16))
+
+
+def test_adam_refreshes_the_linear_operand_image():
+    o = ops()
+    C, S, K = 64, 4, 512
+    p = torch.randn(C * S * S, K, device='cuda')
+    g, m, v = torch.randn_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    img = torch.zeros(p.numel(), dtype=torch.bfloat16, device='cuda')
+    o.adam_multi([dict(p=p, g=g, m=m, v=v, shadow=img, shadow_dims=(K, C, S * S), step_size=2e-4,
+                       inv_bc2_sqrt=31.6)], 0.5, 0.999, 1e-8)
+    assert torch.equal(img, o.prep_linear_weight(p, C, S))
