@@ -41,6 +41,8 @@ int ngan_c8_to_nchw(const void* src_c8, float* dst, int B, int C, int H, int W, 
 /* ---- equalised-LR 3x3 convolution: Conv2d_normalized.forward, models.py:172-204 ---- */
 /* fp32 weight [cout][cin][3][3] -> bf16 UMMA operand images for the forward conv and for the data-gradient conv */
 int ngan_prep_conv_weight(const float* w, void* w_fwd, void* w_dgrad, int cin, int cout, void* stream);
+/* 1 if the images of a cin -> cout layer use the kx-folded layout (the layer runs on the folded kernel) */
+int ngan_conv_weight_is_folded(int cin, int cout);
 /* y = PixelNorm(LeakyReLU(scale*conv(x,W) + bias)), r = PixelNorm scale.  models.py:203-204 + 263-268 (+110-126) */
 int ngan_conv3x3_fwd(const void* x_c8, const void* w_fwd, const float* bias, float scale, float leak, void* y_c8,
                      float* r, int B, int cin, int cout, int H, int W, void* stream);
@@ -147,9 +149,10 @@ typedef struct {
     long long n;
     float step_size;     /* lr / (1 - beta1^t), t = this parameter's step count after the update */
     float inv_bc2_sqrt;  /* 1 / sqrt(1 - beta2^t) */
-    int shadow_k, shadow_c, shadow_ss;   /* 0, or the dims of ngan_prep_linear_weight's image: the shadow of element
-                            (f, k) of a [C*SS][K] parameter is then written at its place in [SS][K/8][C][8] */
-    int reserved;
+    int shadow_k, shadow_c, shadow_ss;   /* shadow_kind 1: {K, C, S*S} of ngan_prep_linear_weight's image;
+                            shadow_kind 2: {cin, cout, ngan_conv_weight_is_folded(cin, cout)} of a 3x3 conv weight */
+    int shadow_kind;     /* 0: shadow has p's layout; 1: shadow is the linear operand image; 2: shadow is the forward
+                            image of ngan_prep_conv_weight immediately followed by the data-gradient image */
     const float* dyn;    /* optional DEVICE pointer to {step_size, inv_bc2_sqrt}; when non-NULL it overrides the two
                             fields above at run time (lets a launch captured in a CUDA graph follow the step count) */
 } ngan_adam_tensor;

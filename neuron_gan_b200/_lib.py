@@ -16,7 +16,7 @@ class AdamTensor(ctypes.Structure):
     _fields_ = [('p', ctypes.c_void_p), ('g', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p),
                 ('shadow_bf16', ctypes.c_void_p), ('n', ctypes.c_longlong), ('step_size', ctypes.c_float),
                 ('inv_bc2_sqrt', ctypes.c_float), ('shadow_k', ctypes.c_int), ('shadow_c', ctypes.c_int),
-                ('shadow_ss', ctypes.c_int), ('reserved', ctypes.c_int), ('dyn', ctypes.c_void_p)]
+                ('shadow_ss', ctypes.c_int), ('shadow_kind', ctypes.c_int), ('dyn', ctypes.c_void_p)]
 
 
 def parse_header(path=HEADER_PATH):
@@ -64,6 +64,7 @@ def load():
     return lib
 
 
+_QUERIES = {'ngan_linear_fwd_workspace_bytes', 'ngan_conv_weight_is_folded', 'ngan_version'}   # no launch, value returned
 # kernels launched per C-ABI call (everything not listed launches exactly one)
 _LAUNCHES = {'ngan_gp_loss': 2}
 launch_count = 0          # running count of kernels launched through this binding (bench.py reads it)
@@ -94,7 +95,7 @@ def call(name, *args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     rc = getattr(lib, name)(*args)
-    if _protos[name][0] is not ctypes.c_int:
+    if name in _QUERIES:
         return rc
     if rc != 0:
         raise NganError(f'{name} failed ({rc}): {lib.ngan_last_error().decode()}')

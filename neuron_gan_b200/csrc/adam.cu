@@ -7,6 +7,7 @@
 // passed by value in kernel-parameter space (no device-side table to maintain).
 // Optionally refreshes a bf16 shadow copy of the parameter in the same pass (the generator's linear weight).
 #include "common.cuh"
+#include "conv_args.cuh"
 #include "kernels.h"
 
 namespace ngan {
@@ -21,8 +22,9 @@ struct AdamEntry {
     long long n;
     float step_size;      // lr / (1 - beta1^t)
     float inv_bc2_sqrt;   // 1 / sqrt(1 - beta2^t)
-    int shadow_k, shadow_c, shadow_ss;   // != 0: shadow is the linear operand image [SS][K/8][C][8] (linear.cu)
-    int reserved;
+    int shadow_k, shadow_c, shadow_ss;   // kind 1: dims of the linear operand image [SS][K/8][C][8] (linear.cu)
+                                         // kind 2: {cin, cout, folded} of a 3x3 conv weight (conv_args.cuh)
+    int shadow_kind;                     // 0 = same layout as p, 1 = linear image, 2 = conv fwd + dgrad images
     const float* dyn;     // optional device pointer to {step_size, inv_bc2_sqrt}: overrides the two fields above, so a
                           // launch captured in a CUDA graph picks up the values of the current step at replay
 };
@@ -55,7 +57,18 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
             o.x = pack_bf16(p.x, p.y);
             o.y = pack_bf16(p.z, p.w);
             size_t dst = static_cast<size_t>(i) * 4;
-            if (t.shadow_k) {      // element (f, k) of [C*SS][K] -> [SS][K/8][C][8]; the 4 k's stay contiguous
+            if (t.shadow_kind == 2) {      // 3x3 conv weight: scatter into the forward and data-gradient images
+                const int cin = t.shadow_k, cout = t.shadow_c;
+                __nv_bfloat16* fwd = t.shadow;
+                __nv_bfloat16* dgr = t.shadow + static_cast<size_t>(cin) * cout * 9;
+                const int i0 = static_cast<int>(dst);
+                conv_image_store(__float2bfloat16(p.x), i0, cin, cout, t.shadow_ss, fwd, dgr);
+                conv_image_store(__float2bfloat16(p.y), i0 + 1, cin, cout, t.shadow_ss, fwd, dgr);
+                conv_image_store(__float2bfloat16(p.z), i0 + 2, cin, cout, t.shadow_ss, fwd, dgr);
+                conv_image_store(__float2bfloat16(p.w), i0 + 3, cin, cout, t.shadow_ss, fwd, dgr);
+                continue;
+            }
+            if (t.shadow_kind == 1) {      // element (f, k) of [C*SS][K] -> [SS][K/8][C][8]; the 4 k's stay contiguous
                 const size_t f = dst / t.shadow_k;
                 const int k = static_cast<int>(dst - f * t.shadow_k);
                 const int c = static_cast<int>(f / t.shadow_ss), px = static_cast<int>(f - static_cast<size_t>(c) * t.shadow_ss);
@@ -74,7 +87,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
             v = beta2 * v + (1.f - beta2) * g * g;
             p = p - step_size * (m / (sqrtf(v) * inv_bc2_sqrt + eps));
             t.p[i] = p; t.m[i] = m; t.v[i] = v;
-            if (t.shadow && !t.shadow_k) t.shadow[i] = __float2bfloat16(p);   // (image layouts have n % 4 == 0)
+            if (t.shadow && !t.shadow_kind) t.shadow[i] = __float2bfloat16(p);   // (image layouts have n % 4 == 0)
         }
     }
 #undef NGAN_ADAM1

@@ -5,6 +5,7 @@
 
 #include "../../include/ngan_b200.h"
 #include "common.cuh"
+#include "conv_args.cuh"
 #include "kernels.h"
 
 namespace ngan {
@@ -63,6 +64,7 @@ int ngan_prep_conv_weight(const float* w, void* w_fwd, void* w_dgrad, int cin, i
     NGAN_REQUIRE(w && (w_fwd || w_dgrad) && !bad_c(cin) && !bad_c(cout), "prep_conv_weight: bad arguments");
     return prep_conv_weight(w, w_fwd, w_dgrad, cin, cout, S(stream));
 }
+int ngan_conv_weight_is_folded(int cin, int cout) { return conv_uses_folded_kernel(cin, cout) ? 1 : 0; }
 int ngan_conv3x3_fwd(const void* x, const void* w_fwd, const float* bias, float scale, float leak, void* y, float* r,
                      int B, int cin, int cout, int H, int W, void* stream) {
     NGAN_REQUIRE(x && w_fwd && y && B > 0, "conv3x3_fwd: null pointer or empty batch");

@@ -458,23 +458,8 @@ int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, 
 __global__ void prep_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
                                         __nv_bfloat16* __restrict__ dgrad, int cin, int cout, int folded) {
     const int n = cin * cout * 9;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int tap = i % 9;
-        const int ci = (i / 9) % cin;
-        const int co = i / (9 * cin);
-        const __nv_bfloat16 v = __float2bfloat16(w[i]);
-        if (!folded) {
-            if (fwd) fwd[((static_cast<size_t>(tap) * (cin / 8) + ci / 8) * cout + co) * 8 + (ci % 8)] = v;
-            if (dgrad) dgrad[((static_cast<size_t>(8 - tap) * (cout / 8) + co / 8) * cin + ci) * 8 + (co % 8)] = v;
-        } else {
-            // folded image [ky][K/8][(kx, n)][8]: the three horizontal taps of a row share one MMA (N = 3*n)
-            const int ky = tap / 3, kx = tap % 3;
-            if (fwd) fwd[((static_cast<size_t>(ky) * (cin / 8) + ci / 8) * (3 * cout) + kx * cout + co) * 8 + (ci % 8)] = v;
-            if (dgrad)
-                dgrad[((static_cast<size_t>(2 - ky) * (cout / 8) + co / 8) * (3 * cin) + (2 - kx) * cin + ci) * 8 +
-                      (co % 8)] = v;
-        }
-    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        conv_image_store(__float2bfloat16(w[i]), i, cin, cout, folded, fwd, dgrad);
 }
 
 int prep_conv_weight(const float* w, void* fwd, void* dgrad, int cin, int cout, cudaStream_t st) {

@@ -36,6 +36,28 @@ struct ConvArgs {
 // channel pairs small enough for all nine weight slabs to stay in shared memory use the folded kernel
 inline bool conv_uses_folded_kernel(int cin, int cout) { return cin * cout <= 4096; }
 
+// Element i of the fp32 master weight [COUT][CIN][3][3] -> its place in the two bf16 UMMA operand images
+//   per-tap:  fwd [9][CIN/8][COUT][8],  dgrad [9][COUT/8][CIN][8] with the taps flipped (dx = convT(g, W))
+//   folded:   fwd [3 ky][CIN/8][3*COUT (kx, co)][8],  dgrad [3][COUT/8][3*CIN][8]   (conv3x3_fold.cu)
+// Used by the preparation kernel and by the Adam kernel, which refreshes the images in the pass that updates
+// the master.
+__device__ __forceinline__ void conv_image_store(__nv_bfloat16 v, int i, int cin, int cout, int folded,
+                                                 __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgrad) {
+    const int tap = i % 9;
+    const int ci = (i / 9) % cin;
+    const int co = i / (9 * cin);
+    if (!folded) {
+        if (fwd) fwd[((static_cast<size_t>(tap) * (cin / 8) + ci / 8) * cout + co) * 8 + (ci % 8)] = v;
+        if (dgrad) dgrad[((static_cast<size_t>(8 - tap) * (cout / 8) + co / 8) * cin + ci) * 8 + (co % 8)] = v;
+    } else {
+        const int ky = tap / 3, kx = tap % 3;
+        if (fwd) fwd[((static_cast<size_t>(ky) * (cin / 8) + ci / 8) * (3 * cout) + kx * cout + co) * 8 + (ci % 8)] = v;
+        if (dgrad)
+            dgrad[((static_cast<size_t>(2 - ky) * (cout / 8) + co / 8) * (3 * cin) + (2 - kx) * cin + ci) * 8 +
+                  (co % 8)] = v;
+    }
+}
+
 int make_c8_tensor_map(CUtensorMap* map, const void* base, int B, int C, int H, int W, int box_w, int box_h,
                        int box_planes);
 int conv3x3_fold_dispatch(int epi, const void* x, ConvArgs a, int B, int cin, int cout, int H, int W,

@@ -80,34 +80,75 @@ int c8_to_nchw(const void* src, float* dst, int B, int C, int H, int W, cudaStre
     return check_launch("c8_to_nchw");
 }
 
+// 32-bit index decomposition: every tensor handled here has < 2^32 granules (largest: a 512x512 batch), and
+// 64-bit div/mod costs ~100 instructions each on the GPU -- more than the rest of these kernels.
+__device__ __forceinline__ void split_xyb(size_t i, int W, int H, int& x, int& y, size_t& b) {
+    const unsigned iu = static_cast<unsigned>(i);
+    const unsigned row = iu / static_cast<unsigned>(W);
+    const unsigned bb = row / static_cast<unsigned>(H);
+    x = static_cast<int>(iu - row * W);
+    y = static_cast<int>(row - bb * H);
+    b = bb;
+}
+__device__ __forceinline__ void split_bpix(size_t i, size_t HW, size_t& b, size_t& pix) {
+    const unsigned iu = static_cast<unsigned>(i), hw = static_cast<unsigned>(HW);
+    const unsigned bb = iu / hw;
+    b = bb;
+    pix = iu - bb * hw;
+}
+
 // ------------------------------------------------------------------------------- resampling (forward)
-__global__ void upsample2x_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int H, int W,
-                                     size_t total) {
-    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int OW = 2 * W, OH = 2 * H;
-    const int ox = static_cast<int>(i % OW);
-    const int oy = static_cast<int>((i / OW) % OH);
-    const size_t plane = i / (static_cast<size_t>(OW) * OH);
-    int y0, y1, x0, x1;
-    float ly, lx;
-    up2_src(oy, H, y0, y1, ly);
-    up2_src(ox, W, x0, x1, lx);
+// One thread per INPUT granule (y, x): its 2x2 output quad needs the clamped 3x3 neighbourhood (align_corners =
+// False, scale 2: out[2i] = .25 x[i-1] + .75 x[i], out[2i+1] = .75 x[i] + .25 x[i+1], separable; the fixed tap
+// pattern of models.py:78-89).  9 loads (neighbours are L1 hits) and 4 stores per thread; a warp writes two
+// contiguous 1 KB row segments.
+__global__ void __launch_bounds__(128) upsample2x_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int H,
+                                                            int W) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ix >= W) return;
+    const int iy = blockIdx.y;
+    const size_t plane = blockIdx.z;
     const uint4* p = x + plane * H * W;
-    float a[8], b[8], c[8], d[8], o[8];
-    unpack8(__ldg(p + static_cast<size_t>(y0) * W + x0), a);
-    unpack8(__ldg(p + static_cast<size_t>(y0) * W + x1), b);
-    unpack8(__ldg(p + static_cast<size_t>(y1) * W + x0), c);
-    unpack8(__ldg(p + static_cast<size_t>(y1) * W + x1), d);
+    const int xm = max(ix - 1, 0), xp = min(ix + 1, W - 1);
+    const int ys[3] = {max(iy - 1, 0), iy, min(iy + 1, H - 1)};
+    float hl[3][8], hr[3][8];     // horizontally interpolated left / right output columns of the three rows
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-        o[e] = (1.f - ly) * ((1.f - lx) * a[e] + lx * b[e]) + ly * ((1.f - lx) * c[e] + lx * d[e]);
-    out[i] = pack8(o);
+    for (int r = 0; r < 3; ++r) {
+        const uint4* row = p + static_cast<size_t>(ys[r]) * W;
+        float a[8], b[8], c[8];
+        unpack8(__ldg(row + xm), a);
+        unpack8(__ldg(row + ix), b);
+        unpack8(__ldg(row + xp), c);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            hl[r][e] = 0.25f * a[e] + 0.75f * b[e];
+            hr[r][e] = 0.75f * b[e] + 0.25f * c[e];
+        }
+    }
+    float o[8];
+    uint4* q = out + plane * 4 * H * W + static_cast<size_t>(2 * iy) * (2 * W) + 2 * ix;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.25f * hl[0][e] + 0.75f * hl[1][e];
+    q[0] = pack8(o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.25f * hr[0][e] + 0.75f * hr[1][e];
+    q[1] = pack8(o);
+    q += 2 * W;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.75f * hl[1][e] + 0.25f * hl[2][e];
+    q[0] = pack8(o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.75f * hr[1][e] + 0.25f * hr[2][e];
+    q[1] = pack8(o);
 }
 int upsample2x_c8(const void* x, void* out, int B, int C, int H, int W, cudaStream_t st) {
-    const size_t total = static_cast<size_t>(B) * (C / 8) * H * W * 4;
-    upsample2x_c8_kernel<<<nblocks(total, 256), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out),
-                                                               H, W, total);
+    const int threads = W < 128 ? ((W + 31) / 32 * 32) : 128;
+    const dim3 grid((W + threads - 1) / threads, H, B * (C / 8));
+    if (grid.z > 65535) {
+        set_error("upsample2x: too many planes (%u)", grid.z);
+        return NGAN_ERR_UNSUPPORTED;
+    }
+    upsample2x_c8_kernel<<<grid, threads, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), H, W);
     return check_launch("upsample2x_c8");
 }
 
@@ -115,9 +156,9 @@ __global__ void avgpool2_c8_kernel(const uint4* __restrict__ x, uint4* __restric
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int OW = W / 2, OH = H / 2;
-    const int ox = static_cast<int>(i % OW);
-    const int oy = static_cast<int>((i / OW) % OH);
-    const size_t plane = i / (static_cast<size_t>(OW) * OH);
+    int ox, oy;
+    size_t plane;
+    split_xyb(i, OW, OH, ox, oy, plane);
     const uint4* p = x + plane * H * W + static_cast<size_t>(2 * oy) * W + 2 * ox;
     float a[8], b[8], c[8], d[8], o[8];
     unpack8(__ldg(p), a);
@@ -144,8 +185,9 @@ __global__ void pn_bwd_c8_kernel(const uint4* __restrict__ g, int unpool, float 
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const size_t HW = static_cast<size_t>(H) * W;
-    const int px = static_cast<int>(i % W), py = static_cast<int>((i / W) % H);
-    const size_t b = i / HW;
+    int px, py;
+    size_t b;
+    split_xyb(i, W, H, px, py, b);
     const int nch = C / 8;
     const size_t q0 = b * nch * HW + static_cast<size_t>(py) * W + px;
     const size_t gHW = unpool ? HW / 4 : HW;
@@ -194,8 +236,9 @@ __global__ void up2_bwd_pn_bwd_kernel(const uint4* __restrict__ g_up, const uint
     if (i >= total) return;
     constexpr int NCH = C / 8;
     const size_t HW = static_cast<size_t>(H) * W;
-    const int px = static_cast<int>(i % W), py = static_cast<int>((i / W) % H);
-    const size_t b = i / HW;
+    int px, py;
+    size_t b;
+    split_xyb(i, W, H, px, py, b);
     float wy[4], wx[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -273,8 +316,9 @@ __global__ void pool_image_kernel(const float* __restrict__ x, float* __restrict
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int OW = W / 2, OH = H / 2;
-    const int ox = static_cast<int>(i % OW), oy = static_cast<int>((i / OW) % OH);
-    const size_t b = i / (static_cast<size_t>(OW) * OH);
+    int ox, oy;
+    size_t b;
+    split_xyb(i, OW, OH, ox, oy, b);
     const float* p = x + b * H * W + static_cast<size_t>(2 * oy) * W + 2 * ox;
     out[i] = 0.25f * (p[0] + p[1] + p[W] + p[W + 1]);
 }
@@ -288,8 +332,9 @@ __global__ void unpool_image_kernel(const float* __restrict__ g, float* __restri
                                     size_t total) {
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int x = static_cast<int>(i % W), y = static_cast<int>((i / W) % H);
-    const size_t b = i / (static_cast<size_t>(W) * H);
+    int x, y;
+    size_t b;
+    split_xyb(i, W, H, x, y, b);
     out[i] = scale * g[b * (H / 2) * (W / 2) + static_cast<size_t>(y >> 1) * (W / 2) + (x >> 1)];
 }
 int unpool_image(const float* g, float* out, float scale, int B, int H, int W, cudaStream_t st) {
@@ -301,8 +346,9 @@ __global__ void up2_image_kernel(const float* __restrict__ x, float* __restrict_
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int OW = 2 * W, OH = 2 * H;
-    const int ox = static_cast<int>(i % OW), oy = static_cast<int>((i / OW) % OH);
-    const size_t b = i / (static_cast<size_t>(OW) * OH);
+    int ox, oy;
+    size_t b;
+    split_xyb(i, OW, OH, ox, oy, b);
     int y0, y1, x0, x1;
     float ly, lx;
     up2_src(oy, H, y0, y1, ly);
@@ -321,8 +367,9 @@ __global__ void up2_image_bwd_kernel(const float* __restrict__ g, float* __restr
                                      size_t total) {
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int px = static_cast<int>(i % W), py = static_cast<int>((i / W) % H);
-    const size_t b = i / (static_cast<size_t>(W) * H);
+    int px, py;
+    size_t b;
+    split_xyb(i, W, H, px, py, b);
     const float* p = g + b * 4 * H * W;
     float acc = 0.f;
 #pragma unroll
@@ -395,7 +442,8 @@ __global__ void fromim_fwd_kernel(const float* __restrict__ xp, const float* __r
                                   size_t total) {
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const size_t b = i / HW, pix = i % HW;
+    size_t b, pix;
+    split_bpix(i, HW, b, pix);
     const int nch = C / 8;
     const float xv = xp[i];
     for (int j = 0; j < nch; ++j) {
@@ -417,7 +465,8 @@ __global__ void d_fade_fwd_kernel(const uint4* __restrict__ y_end, const float* 
                                   uint4* __restrict__ out, int C, size_t HW, size_t total) {
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const size_t b = i / HW, pix = i % HW;
+    size_t b, pix;
+    split_bpix(i, HW, b, pix);
     const int nch = C / 8;
     const float xv = xp[i];
     for (int j = 0; j < nch; ++j) {
@@ -460,8 +509,9 @@ __global__ void fromim_bwd_kernel(const uint4* __restrict__ g, int unpool, float
         const size_t i = (static_cast<size_t>(blockIdx.x) * kFromPix + p) * blockDim.x + threadIdx.x;
         ok[p] = i < total;
         pix[p] = ok[p] ? i : 0;
-        const int px = static_cast<int>(pix[p] % W), py = static_cast<int>((pix[p] / W) % H);
-        const size_t b = pix[p] / HW;
+        int px, py;
+        size_t b;
+        split_xyb(pix[p], W, H, px, py, b);
         gq[p] = unpool ? b * nch * gHW + static_cast<size_t>(py >> 1) * (W >> 1) + (px >> 1)
                        : b * nch * HW + static_cast<size_t>(py) * W + px;
         xv[p] = ok[p] ? xp[pix[p]] : 0.f;
@@ -518,8 +568,9 @@ __global__ void fromim_dbl_kernel(const float* __restrict__ ghat_xp, float in_sc
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const bool ok = i < total;
     const size_t ii = ok ? i : 0;
-    const int px = static_cast<int>(ii % W), py = static_cast<int>((ii / W) % H);
-    const size_t b = ii / HW;
+    int px, py;
+    size_t b;
+    split_xyb(ii, W, H, px, py, b);
     const size_t q0 = b * nch * HW + static_cast<size_t>(py) * W + px;
     const size_t g0 = unpool ? b * nch * gHW + static_cast<size_t>(py >> 1) * (W >> 1) + (px >> 1) : q0;
     const float X = ok ? in_scale * ghat_xp[ii] : 0.f;
@@ -552,7 +603,8 @@ __global__ void toim_fwd_kernel(const uint4* __restrict__ y, const float* __rest
                                 int C, size_t HW, size_t total) {
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const size_t b = i / HW, pix = i % HW;
+    size_t b, pix;
+    split_bpix(i, HW, b, pix);
     const int nch = C / 8;
     float acc = 0.f;
     for (int j = 0; j < nch; ++j) {
@@ -581,7 +633,8 @@ __global__ void toim_bwd_kernel(const float* __restrict__ g_img, float gscale, c
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const bool ok = i < total;
     const size_t ii = ok ? i : 0;
-    const size_t b = ii / HW, pix = ii % HW;
+    size_t b, pix;
+    split_bpix(ii, HW, b, pix);
     const int nch = C / 8;
     const float im = img[ii];
     const float gpre = ok ? gscale * g_img[ii] * (1.f - im * im) : 0.f;
@@ -725,7 +778,8 @@ __global__ void bias_grad_c8_kernel(const uint4* __restrict__ ga, float* __restr
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const bool ok = i < total;
     const size_t ii = ok ? i : 0;
-    const size_t b = ii / HW, pix = ii % HW;
+    size_t b, pix;
+    split_bpix(ii, HW, b, pix);
     const int nch = C / 8;
     for (int j = 0; j < nch; ++j) {
         float v[8];

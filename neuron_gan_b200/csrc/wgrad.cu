@@ -25,12 +25,14 @@ struct WgradArgs {
     int tiles_x, tiles_y, n_tiles;
     int ci_g, co_g;       // channels of x / ga handled by one CTA
     int n_ci_groups;
+    int n_stage;          // depth of the TMA ring (2..kWgMaxStages)
     uint32_t x_stage_bytes, g_stage_bytes;
     float scale;
     float* dw;
 };
 
 constexpr int kWgTH = 8;
+constexpr int kWgMaxStages = 6;
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
                                                   uint32_t& r3) {
@@ -52,9 +54,9 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
                                                             const WgradArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    uint8_t* s_x[2] = {smem, smem + a.x_stage_bytes};
-    uint8_t* s_g[2] = {smem + 2 * a.x_stage_bytes, smem + 2 * a.x_stage_bytes + a.g_stage_bytes};
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * a.x_stage_bytes + 2 * a.g_stage_bytes);
+    // ring of n_stage {x tile, ga tile} slots followed by the mbarriers
+    const uint32_t slot_bytes = a.x_stage_bytes + a.g_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.n_stage * slot_bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = blockIdx.y;
@@ -72,8 +74,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmap_x);
         prefetch_tmap(&tmap_g);
-        mbar_init(bars + 0, 1);
-        mbar_init(bars + 1, 1);
+        for (int i = 0; i < a.n_stage; ++i) mbar_init(bars + i, 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -82,10 +83,11 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
         const int tx = tile % a.tiles_x;
         const int ty = (tile / a.tiles_x) % a.tiles_y;
         const int b = tile / (a.tiles_x * a.tiles_y);
+        uint8_t* slot = smem + stage * slot_bytes;
         mbar_arrive_expect_tx(bars + stage, stage_bytes);
-        tma_load_4d(s_x[stage], &tmap_x, bars + stage, (tx * a.TW - 1) * 2, ty * kWgTH - 1, ci_group * (a.ci_g / 8),
-                    b);
-        tma_load_4d(s_g[stage], &tmap_g, bars + stage, tx * a.TW * 2, ty * kWgTH, co_group * (a.co_g / 8), b);
+        tma_load_4d(slot, &tmap_x, bars + stage, (tx * a.TW - 1) * 2, ty * kWgTH - 1, ci_group * (a.ci_g / 8), b);
+        tma_load_4d(slot + a.x_stage_bytes, &tmap_g, bars + stage, tx * a.TW * 2, ty * kWgTH,
+                    co_group * (a.co_g / 8), b);
     };
 
     float acc[9][2][4];
@@ -96,15 +98,23 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[t][n][k] = 0.f;
 
+    // Prologue: n_stage - 1 tiles in flight.  Iteration `it` first refills the slot that iteration it-1 consumed
+    // (everyone left it at the __syncthreads that closed that iteration), then waits for its own slot: HBM needs
+    // tens of KB in flight per SM, which two slots do not provide.
     int it = 0;
-    if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < a.n_tiles) issue(blockIdx.x, 0);
+    if (threadIdx.x == 0)
+        for (int i = 0; i < a.n_stage - 1; ++i) {
+            const int t = blockIdx.x + i * gridDim.x;
+            if (t < a.n_tiles) issue(t, i);
+        }
+    int stage = 0;
+    uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-        const int stage = it & 1;
-        const int next = tile + gridDim.x;
-        if (threadIdx.x == 0 && next < a.n_tiles) issue(next, stage ^ 1);
-        mbar_wait(bars + stage, (it >> 1) & 1);
+        const int ahead = tile + (a.n_stage - 1) * gridDim.x;
+        if (threadIdx.x == 0 && ahead < a.n_tiles) issue(ahead, stage == 0 ? a.n_stage - 1 : stage - 1);
+        mbar_wait(bars + stage, phase);
 
-        const uint32_t xb = smem_u32(s_x[stage]), gb = smem_u32(s_g[stage]);
+        const uint32_t xb = smem_u32(smem + stage * slot_bytes), gb = xb + a.x_stage_bytes;
         // per-lane ldmatrix row addresses (matrix = lane/8, row = lane%8)
         const int mi = lane >> 3, rowi = lane & 7;
         // A (ga): matrix mi -> pixels +(mi/2)*8, co plane 2*cob + (mi%2)
@@ -126,7 +136,11 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
                 }
             }
         }
-        __syncthreads();  // everyone is done with this stage before it is refilled two iterations later
+        __syncthreads();  // everyone is done with this slot before the next iteration refills it
+        if (++stage == a.n_stage) {
+            stage = 0;
+            phase ^= 1;
+        }
     }
 
     // ---- flush: acc[tap][nb] = D[co = g (+8)][ci = nb*8 + 2t (+1)].  The row-split warps of a block first
@@ -189,7 +203,11 @@ int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int B, 
     a.g_stage_bytes = ((a.co_g / 8) * g_plane + 127) & ~127u;
     a.scale = scale;
     a.dw = dw;
-    const uint32_t stage_total = 2 * a.x_stage_bytes + 2 * a.g_stage_bytes + 16;
+    int n_stage = static_cast<int>((112u * 1024) / (a.x_stage_bytes + a.g_stage_bytes));   // two CTAs per SM stay resident
+    if (n_stage > kWgMaxStages) n_stage = kWgMaxStages;
+    if (n_stage < 2) n_stage = 2;
+    a.n_stage = n_stage;
+    const uint32_t stage_total = n_stage * (a.x_stage_bytes + a.g_stage_bytes) + kWgMaxStages * 8;
     const uint32_t red_bytes = static_cast<uint32_t>(n_blk) * 2304 * sizeof(float);   // flush buffer aliases the stages
     const uint32_t smem_bytes = (stage_total > red_bytes ? stage_total : red_bytes) + 128;
 

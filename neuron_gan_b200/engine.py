@@ -55,7 +55,10 @@ def conv_images(conv):
     if ent is None or ent['key'] != key:
         bufs = (ent['fwd'], ent['dgrad']) if ent is not None and ent['fwd'].device == w.device else (None, None)
         fwd, dgrad = ops.prep_conv_weight(w.detach(), *bufs)
-        ent = {'key': key, 'fwd': fwd, 'dgrad': dgrad}
+        cout, cin = w.shape[0], w.shape[1]
+        # fwd and dgrad are the two halves of one buffer: FusedAdam rewrites both while it updates the master
+        ent = {'key': key, 'fwd': fwd, 'dgrad': dgrad, 'shadow': fwd, 'shadow_kind': 2,
+               'shadow_dims': (cin, cout, int(ops.conv_weight_is_folded(cin, cout)))}
         _cache_set(w, ent)
     return ent['fwd'], ent['dgrad']
 
@@ -82,7 +85,7 @@ def linear_shadow(lin, allocate_only=False):
     K, C, S = _linear_dims(lin)
     if ent is None or ent['shadow'].device != w.device:
         ent = {'key': None, 'shadow': torch.empty(w.numel(), dtype=torch.bfloat16, device=w.device),
-               'shadow_dims': (K, C, S * S)}
+               'shadow_dims': (K, C, S * S), 'shadow_kind': 1}
         _cache_set(w, ent)
     if allocate_only:
         return ent
@@ -108,35 +111,41 @@ def mark_updated(param, shadow_is_fresh=False):
 # (events) and under CUDA-graph capture (fork/join edges).
 # ---------------------------------------------------------------------------------------------------------
 class _Side:
-    stream = None      # torch.cuda.Stream, created on first use
+    streams = []       # torch.cuda.Stream pool, created on first use
+    n_streams = 3      # the low-resolution wgrads are latency-bound on a few dozen CTAs: several run side by side
     enabled = True
     keep = []          # tensors a pending side-stream kernel reads: kept alive until side_join()
-    pending = False
+    used = set()       # indices of pool streams with work since the last join
+    rr = 0
 
 
 def _wgrad(x, ga, scale, dw):
-    """conv3x3_wgrad on the side stream (dw accumulates with atomics, so concurrent wgrads into one tensor are fine)."""
+    """conv3x3_wgrad on a side stream (dw accumulates with atomics, so concurrent wgrads into one tensor are fine)."""
     if dw is None:
         return
     if not _Side.enabled:
         ops.conv3x3_wgrad(x, ga, scale, dw)
         return
-    if _Side.stream is None:
-        _Side.stream = torch.cuda.Stream()
-    cur = torch.cuda.current_stream()
-    _Side.stream.wait_stream(cur)
-    with torch.cuda.stream(_Side.stream):
+    if not _Side.streams:
+        _Side.streams = [torch.cuda.Stream() for _ in range(_Side.n_streams)]
+    i = _Side.rr % len(_Side.streams)
+    _Side.rr += 1
+    side = _Side.streams[i]
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
         ops.conv3x3_wgrad(x, ga, scale, dw)
     _Side.keep.append((x, ga))
-    _Side.pending = True
+    _Side.used.add(i)
 
 
 def side_join():
     """Make the current stream wait for every side-stream wgrad issued so far (call before reading gradients)."""
-    if _Side.pending:
-        torch.cuda.current_stream().wait_stream(_Side.stream)
+    if _Side.used:
+        cur = torch.cuda.current_stream()
+        for i in sorted(_Side.used):
+            cur.wait_stream(_Side.streams[i])
         _Side.keep.clear()
-        _Side.pending = False
+        _Side.used.clear()
 
 
 def _sink_get(sink, p):

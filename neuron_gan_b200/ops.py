@@ -55,9 +55,17 @@ def c8_to_nchw(x):
 
 
 # ------------------------------------------------------------------------------------------ conv 3x3
+def conv_weight_is_folded(cin, cout):
+    return bool(_lib.call('ngan_conv_weight_is_folded', cin, cout))
+
+
 def prep_conv_weight(w, w_fwd=None, w_dgrad=None):
-    """w: fp32 [cout, cin, 3, 3] -> (fwd image, dgrad image), bf16 flat buffers of cout*cin*9 elements."""
+    """w: fp32 [cout, cin, 3, 3] -> (fwd image, dgrad image), bf16 flat buffers of cout*cin*9 elements (views of one
+    2*cout*cin*9 buffer when allocated here: the layout the Adam kernel refreshes in place)."""
     cout, cin = w.shape[0], w.shape[1]
+    if w_fwd is None and w_dgrad is None:
+        both = torch.empty(2 * cout * cin * 9, dtype=BF16, device=w.device)
+        w_fwd, w_dgrad = both[:cout * cin * 9], both[cout * cin * 9:]
     if w_fwd is None:
         w_fwd = torch.empty(cout * cin * 9, dtype=BF16, device=w.device)
     if w_dgrad is None:
@@ -363,4 +371,5 @@ def adam_multi(entries, beta1, beta2, eps):
         arr[i].inv_bc2_sqrt = e['inv_bc2_sqrt']
         arr[i].dyn = e['dyn'].data_ptr() if e.get('dyn') is not None else None
         arr[i].shadow_k, arr[i].shadow_c, arr[i].shadow_ss = e.get('shadow_dims') or (0, 0, 0)
+        arr[i].shadow_kind = e.get('shadow_kind', 1 if e.get('shadow_dims') else 0)
     _lib.call('ngan_adam_multi', ctypes.cast(arr, ctypes.c_void_p), n, beta1, beta2, eps, _stream())

@@ -85,18 +85,18 @@ class FusedAdam(torch.optim.Optimizer):
                 if p.grad is None:
                     continue
                 st = self._state(p)
-                shadow, shadow_dims = None, None
-                if p.dim() == 2:              # the generator's Linear weight: its bf16 operand image is refreshed here
-                    ent = engine._cache_get(p)
-                    if ent is not None and 'shadow' in ent:
-                        shadow, shadow_dims = ent['shadow'], ent['shadow_dims']
+                # bf16 operand images of the GEMM weights (linear stem, 3x3 convs) are rewritten in the same pass
+                shadow, shadow_dims, shadow_kind = None, None, 0
+                ent = engine._cache_get(p) if p.dim() in (2, 4) else None
+                if ent is not None and 'shadow' in ent and ent['shadow'].device == p.device:
+                    shadow, shadow_dims, shadow_kind = ent['shadow'], ent['shadow_dims'], ent['shadow_kind']
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 if self.capturable:
                     self._ensure_dyn(p.device)
                     a, b, dyn = 0.0, 0.0, self._dyn[self._slot[id(p)]]
                 else:
                     (a, b), dyn = self._scalars(group, max(st['step'], 1)), None
-                entries.append(dict(p=p, g=g, m=st['exp_avg'], v=st['exp_avg_sq'], shadow=shadow, shadow_dims=shadow_dims,
+                entries.append(dict(p=p, g=g, m=st['exp_avg'], v=st['exp_avg_sq'], shadow=shadow, shadow_dims=shadow_dims, shadow_kind=shadow_kind,
                                     step_size=a, inv_bc2_sqrt=b, dyn=dyn))
                 touched.append((p, shadow is not None))
             for i in range(0, len(entries), _CHUNK):

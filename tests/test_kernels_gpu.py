@@ -324,3 +324,17 @@ def test_adam_refreshes_the_linear_operand_image():
     o.adam_multi([dict(p=p, g=g, m=m, v=v, shadow=img, shadow_dims=(K, C, S * S), step_size=2e-4,
                        inv_bc2_sqrt=31.6)], 0.5, 0.999, 1e-8)
     assert torch.equal(img, o.prep_linear_weight(p, C, S))
+
+
+@pytest.mark.parametrize('cin,cout', [(16, 16), (32, 64), (128, 128), (64, 128)])
+def test_adam_refreshes_the_conv_operand_images(cin, cout):
+    o = ops()
+    p = torch.randn(cout, cin, 3, 3, device='cuda')
+    g, m, v = torch.randn_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    n = p.numel()
+    img = torch.zeros(2 * n, dtype=torch.bfloat16, device='cuda')
+    o.adam_multi([dict(p=p, g=g, m=m, v=v, shadow=img, shadow_kind=2,
+                       shadow_dims=(cin, cout, int(o.conv_weight_is_folded(cin, cout))), step_size=2e-4,
+                       inv_bc2_sqrt=31.6)], 0.5, 0.999, 1e-8)
+    fwd, dgrad = o.prep_conv_weight(p)
+    assert torch.equal(img[:n], fwd) and torch.equal(img[n:], dgrad)
