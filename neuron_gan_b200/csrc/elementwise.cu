@@ -622,6 +622,7 @@ int toim_fwd(const void* y, const float* w, float* img, int B, int C, int H, int
 }
 // Backward of tanh(conv1x1(y)): gpre = gscale*g_img*(1-img^2); gw[c] += sum gpre*y_c; gy_c = w_c*gpre, then
 // (if ga != null) the PixelNorm/LeakyReLU backward of the layer that produced y.
+constexpr int kToPix = 4;  // pixels per thread: the per-channel weight-gradient sums are warp-reduced once per 4 pixels
 __global__ void toim_bwd_kernel(const float* __restrict__ g_img, float gscale, const float* __restrict__ img,
                                 const uint4* __restrict__ y, const float* __restrict__ r, const float* __restrict__ w,
                                 uint4* __restrict__ ga, float* __restrict__ gpre_out, float* __restrict__ gw,
@@ -630,36 +631,51 @@ __global__ void toim_bwd_kernel(const float* __restrict__ g_img, float gscale, c
     for (int k = threadIdx.x; k < C; k += blockDim.x) sacc[k] = 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const bool ok = i < total;
-    const size_t ii = ok ? i : 0;
-    size_t b, pix;
-    split_bpix(ii, HW, b, pix);
     const int nch = C / 8;
-    const float im = img[ii];
-    const float gpre = ok ? gscale * g_img[ii] * (1.f - im * im) : 0.f;
-    if (ok && gpre_out) gpre_out[ii] = gpre;
-    float t = 0.f;
-    for (int j = 0; j < nch; ++j) {
-        float yv[8], sw[8];
-        unpack8(__ldg(y + (b * nch + j) * HW + pix), yv);
+    size_t ii[kToPix], q0[kToPix];
+    float gpre[kToPix], t[kToPix];
+    bool ok[kToPix];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            sw[e] = gpre * yv[e];
-            t += __ldg(w + j * 8 + e) * yv[e];
-        }
-        warp_accum8(sw, sacc + j * 8, lane);
+    for (int p = 0; p < kToPix; ++p) {
+        const size_t i = (static_cast<size_t>(blockIdx.x) * kToPix + p) * blockDim.x + threadIdx.x;
+        ok[p] = i < total;
+        ii[p] = ok[p] ? i : 0;
+        size_t b, pix;
+        split_bpix(ii[p], HW, b, pix);
+        q0[p] = b * nch * HW + pix;
+        const float im = img[ii[p]];
+        gpre[p] = ok[p] ? gscale * g_img[ii[p]] * (1.f - im * im) : 0.f;
+        if (ok[p] && gpre_out) gpre_out[ii[p]] = gpre[p];
+        t[p] = 0.f;
     }
-    if (ga && ok) {
-        t *= gpre / C;
-        const float rinv = r[ii];
-        for (int j = 0; j < nch; ++j) {
-            float yv[8], o[8];
-            unpack8(__ldg(y + (b * nch + j) * HW + pix), yv);
+    for (int j = 0; j < nch; ++j) {
+        float sw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-                o[e] = lrelu_mask(yv[e], leak) * rinv * (__ldg(w + j * 8 + e) * gpre - yv[e] * t);
-            ga[(b * nch + j) * HW + pix] = pack8(o);
+        for (int p = 0; p < kToPix; ++p) {
+            float yv[8];
+            unpack8(__ldg(y + q0[p] + j * HW), yv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                sw[e] += gpre[p] * yv[e];
+                t[p] += __ldg(w + j * 8 + e) * yv[e];
+            }
+        }
+        if (gw) warp_accum8(sw, sacc + j * 8, lane);
+    }
+    if (ga) {
+#pragma unroll
+        for (int p = 0; p < kToPix; ++p) {
+            if (!ok[p]) continue;
+            const float tp = t[p] * gpre[p] / C;
+            const float rinv = r[ii[p]];
+            for (int j = 0; j < nch; ++j) {
+                float yv[8], o[8];
+                unpack8(__ldg(y + q0[p] + j * HW), yv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    o[e] = lrelu_mask(yv[e], leak) * rinv * (__ldg(w + j * 8 + e) * gpre[p] - yv[e] * tp);
+                ga[q0[p] + j * HW] = pack8(o);
+            }
         }
     }
     __syncthreads();
@@ -669,7 +685,7 @@ __global__ void toim_bwd_kernel(const float* __restrict__ g_img, float gscale, c
 int toim_bwd(const float* g_img, float gscale, const float* img, const void* y, const float* r, const float* w,
              void* ga, float* gpre, float* gw, float leak, int B, int C, int H, int W, cudaStream_t st) {
     const size_t HW = static_cast<size_t>(H) * W, total = B * HW;
-    toim_bwd_kernel<<<nblocks(total, 128), 128, C * sizeof(float), st>>>(
+    toim_bwd_kernel<<<nblocks(total, 128 * kToPix), 128, C * sizeof(float), st>>>(
         g_img, gscale, img, static_cast<const uint4*>(y), r, w, static_cast<uint4*>(ga), gpre, gw, leak, C, HW, total);
     return check_launch("toim_bwd");
 }
