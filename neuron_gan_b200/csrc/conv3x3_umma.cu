@@ -216,7 +216,10 @@ __global__ void __launch_bounds__(128) conv3x3_umma_kernel(const __grid_constant
     uint64_t* bar_wempty = bars + 2 + kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * kMaxStages);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the descriptor arithmetic in
+    // uniform registers and issues UTCHMMA / UTMALDG back to back instead of through a per-lane loop
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y, b = blockIdx.z;
 
     if (threadIdx.x == 0) {
@@ -234,43 +237,65 @@ __global__ void __launch_bounds__(128) conv3x3_umma_kernel(const __grid_constant
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    if (warp == 0 && lane == 0) {
-        // ---- input tile: one TMA box {2*Wh x (TH+2) x CIN/8 x 1} of 8-byte elements
-        mbar_arrive_expect_tx(bar_in, in_bytes);
-        tma_load_4d(s_in, &tmap, bar_in, (tile_x * a.TW - 1) * 2, tile_y * a.TH - 1, 0, b);
-        mbar_wait(bar_in, 0);
+    if (warp == 0) {
+        // ---- input tile: one TMA box {2*Wh x (TH+2) x CIN/8 x 1} of 8-byte elements, then the MMA issue loop
+        if (elect_one()) {
+            mbar_arrive_expect_tx(bar_in, in_bytes);
+            tma_load_4d(s_in, &tmap, bar_in, (tile_x * a.TW - 1) * 2, tile_y * a.TH - 1, 0, b);
+        }
+        __syncwarp();
+        mbar_wait_warp(bar_in, 0, lane);
         tc_fence_after();
         const uint32_t in_base = smem_u32(s_in);
         const uint32_t w_base = smem_u32(s_w);
+        int stage = 0;
+        uint32_t ph = 0;
         for (int tap = 0; tap < 9; ++tap) {
-            const int stage = tap % a.n_stage;
-            mbar_wait(bar_wfull + stage, (tap / a.n_stage) & 1);
+            mbar_wait_warp(bar_wfull + stage, ph, lane);
             tc_fence_after();
-            const uint32_t tap_off = ((tap / 3) * a.Wh + (tap % 3)) * 16;
+            if (elect_one()) {
+                const uint32_t tap_off = ((tap / 3) * a.Wh + (tap % 3)) * 16;
+                const uint32_t hi = umma_desc_hi(128);
 #pragma unroll
-            for (int kc = 0; kc < CIN / 16; ++kc) {
-                const uint32_t a_addr = in_base + (2 * kc) * a.plane_bytes + tap_off;
-                const uint32_t b_addr = w_base + stage * W_TAP_BYTES + (2 * kc) * COUT * 16;
-                const uint64_t bdesc = umma_desc(b_addr, COUT * 16, 128);
-                for (int mt = 0; mt < a.nMT; ++mt) {
-                    const uint64_t adesc = umma_desc(a_addr + mt * 128 * 16, a.plane_bytes, 128);
-                    umma_bf16(tmem_base + mt * COUT, adesc, bdesc, IDESC, (tap | kc) != 0);
+                for (int kc = 0; kc < CIN / 16; ++kc) {
+                    const uint32_t a_addr = in_base + (2 * kc) * a.plane_bytes + tap_off;
+                    const uint32_t b_lo = umma_desc_lo(w_base + stage * W_TAP_BYTES + (2 * kc) * COUT * 16, COUT * 16);
+                    uint32_t a_lo = umma_desc_lo(a_addr, a.plane_bytes);
+                    for (int mt = 0; mt < a.nMT; ++mt) {
+                        umma_bf16_2x32(tmem_base + mt * COUT, a_lo, hi, b_lo, hi, IDESC, (tap | kc) != 0);
+                        a_lo += (128 * 16) >> 4;
+                    }
+                }
+                umma_commit(bar_wempty + stage);  // slab free once these MMAs retire
+                if (tap == 8) umma_commit(bar_mma);
+            }
+            __syncwarp();
+            if (++stage == a.n_stage) {
+                stage = 0;
+                ph ^= 1;
+            }
+        }
+    } else if (warp == 1) {
+        // ---- weight slabs, one per tap, through a ring of n_stage buffers
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t ph = 0;
+            bool wrapped = false;
+            for (int tap = 0; tap < 9; ++tap) {
+                if (wrapped) mbar_wait(bar_wempty + stage, ph ^ 1);
+                mbar_arrive_expect_tx(bar_wfull + stage, W_TAP_BYTES);
+                bulk_load_1d(s_w + stage * W_TAP_BYTES, reinterpret_cast<const uint8_t*>(a.wprep) + tap * W_TAP_BYTES,
+                             W_TAP_BYTES, bar_wfull + stage);
+                if (++stage == a.n_stage) {
+                    stage = 0;
+                    ph ^= 1;
+                    wrapped = true;
                 }
             }
-            umma_commit(bar_wempty + stage);  // slab free once these MMAs retire
         }
-        umma_commit(bar_mma);
-    } else if (warp == 1 && lane == 0) {
-        // ---- weight slabs, one per tap, through a ring of n_stage buffers
-        for (int tap = 0; tap < 9; ++tap) {
-            const int stage = tap % a.n_stage;
-            if (tap >= a.n_stage) mbar_wait(bar_wempty + stage, ((tap / a.n_stage) - 1) & 1);
-            mbar_arrive_expect_tx(bar_wfull + stage, W_TAP_BYTES);
-            bulk_load_1d(s_w + stage * W_TAP_BYTES, reinterpret_cast<const uint8_t*>(a.wprep) + tap * W_TAP_BYTES,
-                         W_TAP_BYTES, bar_wfull + stage);
-        }
+        __syncwarp();
     }
 
     // ---- epilogue: every thread owns one accumulator row (= one output pixel, all COUT channels)

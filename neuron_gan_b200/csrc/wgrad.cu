@@ -11,6 +11,8 @@
 // ldmatrix.trans delivers, and the 9 taps are 9 shifted ldmatrix addresses into the same haloed x tile.
 // CTAs are persistent over pixel tiles (grid.x) and split the (co, ci) block space (grid.y); partial sums
 // are combined with fp32 atomics into the (pre-zeroed or accumulating) gradient tensor.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -144,9 +146,10 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
     }
 
     // ---- flush: acc[tap][nb] = D[co = g (+8)][ci = nb*8 + 2t (+1)].  The row-split warps of a block first
-    // combine in shared memory (the operand stages are drained by now), then the CTA issues one global atomic
-    // per output element.
-    float* s_red = reinterpret_cast<float*>(smem);   // [n_blk][9][16][16]
+    // combine in shared memory (the operand slots are drained by now), laid out like the gradient tensor itself
+    // ([co][ci][tap], tap fastest), so that the CTA's global atomics run over contiguous addresses: 144 consecutive
+    // floats per (block, co) row instead of one 32-byte sector per lane.
+    float* s_red = reinterpret_cast<float*>(smem);   // [n_blk][16 co][16 ci][9 taps]
     const int g = lane >> 2, t = lane & 3;
     __syncthreads();
     for (int i = threadIdx.x; i < n_blk * 2304; i += blockDim.x) s_red[i] = 0.f;
@@ -160,16 +163,17 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
                 for (int k = 0; k < 4; ++k) {
                     const int co = g + (k >> 1) * 8;
                     const int ci = nb * 8 + 2 * t + (k & 1);
-                    atomicAdd(s_red + ((blk * 9 + tap) * 16 + co) * 16 + ci, acc[tap][nb][k]);
+                    atomicAdd(s_red + ((blk * 16 + co) * 16 + ci) * 9 + tap, acc[tap][nb][k]);
                 }
     }
     __syncthreads();
     if (it > 0) {
         for (int i = threadIdx.x; i < n_blk * 2304; i += blockDim.x) {
-            const int ci = i & 15, co = (i >> 4) & 15, tap = (i >> 8) % 9, b = i / 2304;
+            const int b = i / 2304, rem = i - b * 2304;
+            const int co = rem / 144, j = rem - co * 144;        // j = ci * 9 + tap
             const int co_abs = co_group * a.co_g + (b / n_ci_blk) * 16 + co;
-            const int ci_abs = ci_group * a.ci_g + (b % n_ci_blk) * 16 + ci;
-            atomicAdd(a.dw + (static_cast<size_t>(co_abs) * a.cin + ci_abs) * 9 + tap, a.scale * s_red[i]);
+            const int ci0 = ci_group * a.ci_g + (b % n_ci_blk) * 16;
+            atomicAdd(a.dw + (static_cast<size_t>(co_abs) * a.cin + ci0) * 9 + j, a.scale * s_red[i]);
         }
     }
 }
@@ -227,7 +231,8 @@ int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int B, 
     // CTAs per channel group: fill the machine, but keep >= 8 tiles per CTA when the problem is small so the
     // per-CTA flush (n_blk * 2304 atomics) does not dominate the few MMAs a tile needs.
     int per_group = (2 * 148 + n_groups - 1) / n_groups;
-    const int by_work = (a.n_tiles + 7) / 8;
+    static const int tiles_per_cta = getenv("NGAN_WGRAD_TPC") ? atoi(getenv("NGAN_WGRAD_TPC")) : 8;
+    const int by_work = (a.n_tiles + tiles_per_cta - 1) / tiles_per_cta;
     if (per_group > by_work) per_group = by_work;
     if (per_group < 1) per_group = 1;
     conv3x3_wgrad_kernel<<<dim3(per_group, n_groups), 256, smem_bytes, st>>>(tmx, tmg, a);

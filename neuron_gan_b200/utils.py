@@ -173,3 +173,45 @@ def plot_gen_samples(Generator: nn.Module, eval_noise=None, N_images=16, seed=No
     import torchvision
     torchvision.utils.save_image(images, filename, nrow=n_rows, normalize=True)
     return images
+
+
+class DevicePrefetcher:
+    """Iterate host batches (ideally pinned) as device tensors with the next batch's host-to-device copy running on
+    its own stream while the current one is consumed -- the role `pin_memory=True` + `non_blocking` copies play in
+    the reference's loop (train.py:150-154, 352-353).  The yielded tensor is only valid until the next iteration."""
+
+    def __init__(self, batches, device, depth=2):
+        self.batches, self.device, self.depth = batches, torch.device(device), max(2, int(depth))
+
+    def __iter__(self):
+        copy_stream = torch.cuda.Stream(self.device)
+        slots, ready, free = [None] * self.depth, [None] * self.depth, [None] * self.depth
+        it = iter(self.batches)
+
+        def launch(k, host):
+            with torch.cuda.stream(copy_stream):
+                if free[k] is not None:
+                    copy_stream.wait_event(free[k])          # the consumer has finished reading this slot
+                if slots[k] is None or slots[k].shape != host.shape or slots[k].dtype != host.dtype:
+                    slots[k] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+                slots[k].copy_(host, non_blocking=True)
+                ready[k] = torch.cuda.Event()
+                ready[k].record(copy_stream)
+
+        first = next(it, None)
+        if first is None:
+            return
+        launch(0, first)
+        i = 0
+        while True:
+            k = i % self.depth
+            nxt = next(it, None)
+            if nxt is not None:
+                launch((i + 1) % self.depth, nxt)
+            torch.cuda.current_stream(self.device).wait_event(ready[k])
+            yield slots[k]
+            free[k] = torch.cuda.Event()
+            free[k].record(torch.cuda.current_stream(self.device))
+            if nxt is None:
+                return
+            i += 1

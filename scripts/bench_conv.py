@@ -13,13 +13,20 @@ def run(B, C, R, n_buf=6, iters=30):
     y, r = o.conv3x3_fwd(xs[0], w_fwd, None, s, 0.2, C)
     res = {}
     def timeit(name, fn, nbytes):
+        # the calls are captured into one CUDA graph and replayed: small kernels would otherwise be timed at the
+        # host's launch rate (~20 us per Python call), not the GPU's
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(iters):
+                fn(i)
+        g.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(iters):
-            fn(i)
+        g.replay()
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / iters * 1e3
