@@ -46,6 +46,12 @@ int ngan_conv_weight_is_folded(int cin, int cout);
 /* y = PixelNorm(LeakyReLU(scale*conv(x,W) + bias)), r = PixelNorm scale.  models.py:203-204 + 263-268 (+110-126) */
 int ngan_conv3x3_fwd(const void* x_c8, const void* w_fwd, const float* bias, float scale, float leak, void* y_c8,
                      float* r, int B, int cin, int cout, int H, int W, void* stream);
+/* The generator's last conv with ToImage fused (models.py:141-149, 344-353): additionally img[b,y,x] =
+ * tanh(sum_c toim_w[c] * y[b,c,y,x]) (fp32 [B][H][W]).  y_c8 and r may be NULL when only the image is wanted (the
+ * detached generator passes of the critic step).  Folded layers only (ngan_conv_weight_is_folded). */
+int ngan_conv3x3_fwd_toim(const void* x_c8, const void* w_fwd, const float* bias, float scale, float leak, void* y_c8,
+                          float* r, const float* toim_w, float* img, int B, int cin, int cout, int H, int W,
+                          void* stream);
 /* gx = scale * convT(ga, W): autograd's convolution_backward (input gradient) of models.py:204.  cin/cout are the
  * LAYER's channel counts: ga has cout channels, gx has cin. */
 int ngan_conv3x3_dgrad(const void* ga_c8, const void* w_dgrad, float scale, void* gx_c8, int B, int cin, int cout,

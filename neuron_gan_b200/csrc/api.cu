@@ -71,6 +71,12 @@ int ngan_conv3x3_fwd(const void* x, const void* w_fwd, const float* bias, float 
     return conv3x3_dispatch(EPI_FWD_PN, x, w_fwd, B, cin, cout, H, W, scale, leak, bias, y, nullptr, r, nullptr,
                             nullptr, nullptr, nullptr, S(stream));
 }
+int ngan_conv3x3_fwd_toim(const void* x, const void* w_fwd, const float* bias, float scale, float leak, void* y, float* r,
+                          const float* toim_w, float* img, int B, int cin, int cout, int H, int W, void* stream) {
+    NGAN_REQUIRE(x && w_fwd && toim_w && img && B > 0, "conv3x3_fwd_toim: null pointer or empty batch");
+    return conv3x3_dispatch(EPI_FWD_PN, x, w_fwd, B, cin, cout, H, W, scale, leak, bias, y, nullptr, r, nullptr,
+                            nullptr, nullptr, nullptr, S(stream), toim_w, img);
+}
 int ngan_conv3x3_dgrad(const void* ga, const void* w_dgrad, float scale, void* gx, int B, int cin, int cout, int H,
                        int W, void* stream) {
     NGAN_REQUIRE(ga && w_dgrad && gx && B > 0, "conv3x3_dgrad: null pointer or empty batch");

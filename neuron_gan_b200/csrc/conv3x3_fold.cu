@@ -94,14 +94,23 @@ __device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool vali
             k = rinv = rsqrtf(ss * inv_c + 1e-8f);
         }
         if (valid) {
-            uint4* out = reinterpret_cast<uint4*>(a.out0) + q0;
-            float2* o2 = reinterpret_cast<float2*>(o);
-            const float2 k2 = make_float2(k, k);
+            if (a.img_out) {
+                // fused ToImage (models.py:141-149): plain 1x1 conv to one channel + tanh on the normalised activation
+                float dot = 0.f;
 #pragma unroll
-            for (int j = 0; j < NCH; ++j) {
+                for (int c = 0; c < COUT; ++c) dot = fmaf(__ldg(a.toim_w + c), o[c], dot);
+                a.img_out[p0] = tanhf(k * dot);
+            }
+            if (a.out0) {
+                uint4* out = reinterpret_cast<uint4*>(a.out0) + q0;
+                float2* o2 = reinterpret_cast<float2*>(o);
+                const float2 k2 = make_float2(k, k);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o2[j * 4 + e] = __fmul2_rn(o2[j * 4 + e], k2);
-                out[j * HW] = pack8(o + j * 8);
+                for (int j = 0; j < NCH; ++j) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o2[j * 4 + e] = __fmul2_rn(o2[j * 4 + e], k2);
+                    out[j * HW] = pack8(o + j * 8);
+                }
             }
             if (a.rout) a.rout[p0] = rinv;
         }

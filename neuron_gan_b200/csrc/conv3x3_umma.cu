@@ -437,7 +437,8 @@ static int launch_conv(const CUtensorMap& tmap, const ConvArgs& a, const TilePla
 
 int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, int cout, int H, int W, float scale,
                      float leak, const float* bias, void* out0, void* out1, float* rout, const void* y,
-                     const float* r, const void* gy, const void* addin, cudaStream_t st) {
+                     const float* r, const void* gy, const void* addin, cudaStream_t st, const float* toim_w,
+                     float* img_out) {
     ConvArgs a;
     a.B = B; a.H = H; a.W = W;
     a.scale = scale; a.leak = leak;
@@ -448,11 +449,18 @@ int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, 
     a.out0 = static_cast<__nv_bfloat16*>(out0);
     a.out1 = static_cast<__nv_bfloat16*>(out1);
     a.rout = rout;
+    a.toim_w = toim_w;
+    a.img_out = img_out;
     a.y = static_cast<const __nv_bfloat16*>(y);
     a.r = r;
     a.gy = static_cast<const __nv_bfloat16*>(gy);
     a.addin = static_cast<const __nv_bfloat16*>(addin);
     if (conv_uses_folded_kernel(cin, cout)) return conv3x3_fold_dispatch(epi, x, a, B, cin, cout, H, W, st);
+    if (img_out || !out0) {
+        set_error("conv3x3: the fused ToImage epilogue exists only for folded layers (cin*cout <= 4096), got %d -> %d",
+                  cin, cout);
+        return NGAN_ERR_UNSUPPORTED;
+    }
 
     TilePlan plan;
     if (!plan_tiles(B, H, W, cin, cout, &plan)) {

@@ -26,6 +26,8 @@ struct ConvArgs {
     __nv_bfloat16* out0;
     __nv_bfloat16* out1;
     float* rout;
+    const float* toim_w;         // FWD (folded kernel): fused ToImage, img = tanh(sum_c toim_w[c] * y[c]) ...
+    float* img_out;              // ... written here ([B][H][W] fp32); out0 may then be null (y not stored)
     const __nv_bfloat16* y;
     const float* r;
     const __nv_bfloat16* gy;

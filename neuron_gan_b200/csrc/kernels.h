@@ -10,7 +10,8 @@ enum ConvEpilogue { EPI_FWD_PN = 0, EPI_LINEAR = 1, EPI_BWD_PN = 2, EPI_DBL = 3 
 // conv3x3_umma.cu
 int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, int cout, int H, int W, float scale,
                      float leak, const float* bias, void* out0, void* out1, float* rout, const void* y,
-                     const float* r, const void* gy, const void* addin, cudaStream_t st);
+                     const float* r, const void* gy, const void* addin, cudaStream_t st, const float* toim_w = nullptr,
+                     float* img_out = nullptr);
 int prep_conv_weight(const float* w, void* fwd, void* dgrad, int cin, int cout, cudaStream_t st);
 
 // wgrad.cu

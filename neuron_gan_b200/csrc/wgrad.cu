@@ -145,16 +145,16 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
         }
     }
 
-    // ---- flush: acc[tap][nb] = D[co = g (+8)][ci = nb*8 + 2t (+1)].  The row-split warps of a block first
-    // combine in shared memory (the operand slots are drained by now), laid out like the gradient tensor itself
-    // ([co][ci][tap], tap fastest), so that the CTA's global atomics run over contiguous addresses: 144 consecutive
-    // floats per (block, co) row instead of one 32-byte sector per lane.
-    float* s_red = reinterpret_cast<float*>(smem);   // [n_blk][16 co][16 ci][9 taps]
+    // ---- flush: acc[tap][nb] = D[co = g (+8)][ci = nb*8 + 2t (+1)].  Every warp stores its accumulator block to its
+    // own slice of shared memory (the operand slots are drained by now; plain stores -- shared-memory float atomics
+    // are CAS loops), the CTA then sums the row-split slices of each output and issues one global atomic per
+    // output.  Slices are laid out like the gradient tensor itself ([co][ci][tap], tap fastest), so the atomics
+    // of a warp run over contiguous addresses: 144 consecutive floats per (block, co) row.
+    float* s_red = reinterpret_cast<float*>(smem);   // [8 warps = rsplit x n_blk][16 co][16 ci][9 taps]
     const int g = lane >> 2, t = lane & 3;
     __syncthreads();
-    for (int i = threadIdx.x; i < n_blk * 2304; i += blockDim.x) s_red[i] = 0.f;
-    __syncthreads();
     if (it > 0) {
+        float* mine = s_red + warp * 2304;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
@@ -163,17 +163,19 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
                 for (int k = 0; k < 4; ++k) {
                     const int co = g + (k >> 1) * 8;
                     const int ci = nb * 8 + 2 * t + (k & 1);
-                    atomicAdd(s_red + ((blk * 16 + co) * 16 + ci) * 9 + tap, acc[tap][nb][k]);
+                    mine[(co * 16 + ci) * 9 + tap] = acc[tap][nb][k];
                 }
     }
     __syncthreads();
     if (it > 0) {
         for (int i = threadIdx.x; i < n_blk * 2304; i += blockDim.x) {
             const int b = i / 2304, rem = i - b * 2304;
+            float v = 0.f;
+            for (int r = 0; r < rsplit; ++r) v += s_red[(r * n_blk + b) * 2304 + rem];     // warp = rs * n_blk + blk
             const int co = rem / 144, j = rem - co * 144;        // j = ci * 9 + tap
             const int co_abs = co_group * a.co_g + (b / n_ci_blk) * 16 + co;
             const int ci0 = ci_group * a.ci_g + (b % n_ci_blk) * 16;
-            atomicAdd(a.dw + (static_cast<size_t>(co_abs) * a.cin + ci0) * 9 + j, a.scale * s_red[i]);
+            atomicAdd(a.dw + (static_cast<size_t>(co_abs) * a.cin + ci0) * 9 + j, a.scale * v);
         }
     }
 }
@@ -212,7 +214,7 @@ int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int B, 
     if (n_stage < 2) n_stage = 2;
     a.n_stage = n_stage;
     const uint32_t stage_total = n_stage * (a.x_stage_bytes + a.g_stage_bytes) + kWgMaxStages * 8;
-    const uint32_t red_bytes = static_cast<uint32_t>(n_blk) * 2304 * sizeof(float);   // flush buffer aliases the stages
+    const uint32_t red_bytes = 8u * 2304 * sizeof(float);   // flush slices (one per warp) alias the operand slots
     const uint32_t smem_bytes = (stage_total > red_bytes ? stage_total : red_bytes) + 128;
 
     CUtensorMap tmx, tmg;
@@ -228,12 +230,14 @@ int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int B, 
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(wgrad)");
         configured = true;
     }
-    // CTAs per channel group: fill the machine, but keep >= 8 tiles per CTA when the problem is small so the
-    // per-CTA flush (n_blk * 2304 atomics) does not dominate the few MMAs a tile needs.
-    int per_group = (2 * 148 + n_groups - 1) / n_groups;
-    static const int tiles_per_cta = getenv("NGAN_WGRAD_TPC") ? atoi(getenv("NGAN_WGRAD_TPC")) : 8;
-    const int by_work = (a.n_tiles + tiles_per_cta - 1) / tiles_per_cta;
-    if (per_group > by_work) per_group = by_work;
+    // CTAs: every CTA ends with a flush of n_blk*2304 atomics, so the CTA count is what small problems pay for and
+    // the tiles per CTA what large ones pay for.  Measured (B200, graph-timed): one resident wave (148 CTAs over
+    // all channel groups) is best up to a few tiles per CTA, two CTAs per SM beyond that.
+    const long long work = static_cast<long long>(a.n_tiles) * n_groups;
+    static const int target_env = getenv("NGAN_WGRAD_CTAS") ? atoi(getenv("NGAN_WGRAD_CTAS")) : 0;
+    const int target = target_env ? target_env : (work >= 4LL * 148 ? 2 * 148 : 148);
+    int per_group = target / n_groups;
+    if (per_group > a.n_tiles) per_group = a.n_tiles;
     if (per_group < 1) per_group = 1;
     conv3x3_wgrad_kernel<<<dim3(per_group, n_groups), 256, smem_bytes, st>>>(tmx, tmg, a);
     return check_launch("conv3x3_wgrad");

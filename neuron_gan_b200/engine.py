@@ -16,6 +16,7 @@ Here each pass is an explicit kernel sequence over saved activations:
 
 Parameter gradients ACCUMULATE into the fp32 tensors of a `sink` (dict id(param) -> tensor).
 """
+import os
 import weakref
 from types import SimpleNamespace
 
@@ -159,17 +160,37 @@ def _flat(w):
 # ---------------------------------------------------------------------------------------------------------
 # Generator
 # ---------------------------------------------------------------------------------------------------------
+FUSE_TOIMAGE = os.environ.get('NGAN_NO_FUSED_TOIM', '') == ''     # A/B switch for the fused ToImage epilogue
+
+
 def _clp(x, conv, leak, save):
     y, r = ops.conv3x3_fwd(x, conv_images(conv)[0], conv.bias.detach() if conv.bias is not None else None,
                            conv.scale_value, leak, conv.out_channels, want_r=save)
     return y, r
 
 
-def _g_block_fwd(blk, y, leak, save):
+def _clp_toim(x, conv, leak, save, toim, need_y, img_out=None):
+    """conv + LeakyReLU + PixelNorm followed by ToImage (`toim`): one kernel when the layer runs on the folded conv
+    kernel (its epilogue has every channel of a pixel in registers), else two.  y is not even stored when neither
+    the backward pass (save) nor a following block (need_y) wants it.  Returns (y | None, r | None, img)."""
+    w_im = _flat(toim.weight)
+    if FUSE_TOIMAGE and ops.conv_weight_is_folded(conv.in_channels, conv.out_channels):
+        return ops.conv3x3_fwd_toim(x, conv_images(conv)[0], conv.bias.detach() if conv.bias is not None else None,
+                                    conv.scale_value, leak, conv.out_channels, w_im, want_y=save or need_y,
+                                    want_r=save, img_out=img_out)
+    y, r = _clp(x, conv, leak, save)
+    return y, r, ops.toim_fwd(y, w_im, out=img_out)
+
+
+def _g_block_fwd(blk, y, leak, save, toim=None, need_y=True, img_out=None):
     xu = ops.upsample2x(y)
     y1, r1 = _clp(xu, blk.conv1, leak, save)
-    y2, r2 = _clp(y1, blk.conv2, leak, save)
-    return SimpleNamespace(blk=blk, xu=xu if save else None, y1=y1 if save else None, r1=r1, y2=y2, r2=r2)
+    if toim is None:
+        y2, r2 = _clp(y1, blk.conv2, leak, save)
+        img = None
+    else:
+        y2, r2, img = _clp_toim(y1, blk.conv2, leak, save, toim, need_y, img_out)
+    return SimpleNamespace(blk=blk, xu=xu if save else None, y1=y1 if save else None, r1=r1, y2=y2, r2=r2, img=img)
 
 
 def g_forward(net, z, save, img_out=None):
@@ -182,26 +203,35 @@ def g_forward(net, z, save, img_out=None):
     lin._ngan_dims = (lin.in_features, C0, S)
     z = z.detach().to(F32).contiguous()
     y0, r0 = ops.linear_fwd(z, linear_shadow(lin), lin.scale_value, leak, C0, S, want_r=save)
-    yc, rc = _clp(y0, conv0, leak, save)
+    fade = alpha < 1
+    blocks = net.trunk_blocks()
+    # the trunk's ToImage rides on the trunk's last conv; during a fade-in its activation also feeds the new block
+    trunk_out = img_out if not fade else None
+    if blocks:
+        yc, rc = _clp(y0, conv0, leak, save)
+        img_trunk = None
+    else:
+        yc, rc, img_trunk = _clp_toim(y0, conv0, leak, save, net.ToIm, need_y=fade, img_out=trunk_out)
     recs, y, r = [], yc, rc
-    for blk in net.trunk_blocks():
-        rec = _g_block_fwd(blk, y, leak, save)
+    for i, blk in enumerate(blocks):
+        last = i == len(blocks) - 1
+        rec = _g_block_fwd(blk, y, leak, save, toim=net.ToIm if last else None, need_y=fade,
+                           img_out=trunk_out if last else None)
         recs.append(rec)
         y, r = rec.y2, rec.r2
+        if last:
+            img_trunk = rec.img
     ctx = (SimpleNamespace(z=z, y0=y0, r0=r0, yc=yc, rc=rc, recs=recs, alpha=alpha, new=None, toim=net.ToIm,
                            toim_new=None) if save else None)
-    if alpha >= 1:
-        img = ops.toim_fwd(y, _flat(net.ToIm.weight), out=img_out)
+    if not fade:
         if save:
-            ctx.img = img
-        return img, ctx
+            ctx.img = img_trunk
+        return img_trunk, ctx
     # fade-in: im_start = up(ToIm_old(x)), im_end = ToIm_new(block_new(x))      (models.py:347-350)
-    img_old = ops.toim_fwd(y, _flat(net.ToIm.weight))
-    new = _g_block_fwd(net.conv_block_list[0], y, leak, save)
-    img_end = ops.toim_fwd(new.y2, _flat(net.ToIm_list[0].weight))
-    img = ops.lerp(ops.up2_image(img_old), img_end, alpha, out=img_out)
+    new = _g_block_fwd(net.conv_block_list[0], y, leak, save, toim=net.ToIm_list[0], need_y=False)
+    img = ops.lerp(ops.up2_image(img_trunk), new.img, alpha, out=img_out)
     if save:
-        ctx.new, ctx.img_old, ctx.img_end, ctx.toim_new = new, img_old, img_end, net.ToIm_list[0]
+        ctx.new, ctx.img_old, ctx.img_end, ctx.toim_new = new, img_trunk, new.img, net.ToIm_list[0]
     return img, ctx
 
 

@@ -83,6 +83,18 @@ def conv3x3_fwd(x, w_fwd, bias, scale, leak, cout, want_r=True):
     return y, r
 
 
+def conv3x3_fwd_toim(x, w_fwd, bias, scale, leak, cout, toim_w, want_y=True, want_r=True, img_out=None):
+    """conv + LeakyReLU + PixelNorm with ToImage fused: returns (y or None, r or None, img [B, H, W] fp32)."""
+    B, cin, H, W = c8_dims(x)
+    y = c8_empty(B, cout, H, W, x.device) if want_y else None
+    r = torch.empty((B, H, W), dtype=F32, device=x.device) if want_r else None
+    img = torch.empty((B, H, W), dtype=F32, device=x.device) if img_out is None else img_out
+    assert img.shape == (B, H, W) and img.dtype == F32
+    _lib.call('ngan_conv3x3_fwd_toim', _p(x, BF16), _p(w_fwd, BF16), _p(bias, F32), scale, leak, _p(y), _p(r),
+              _p(toim_w, F32), _p(img), B, cin, cout, H, W, _stream())
+    return y, r, img
+
+
 def conv3x3_dgrad(ga, w_dgrad, scale, cin):
     B, cout, H, W = c8_dims(ga)
     gx = c8_empty(B, cin, H, W, ga.device)

@@ -19,6 +19,7 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self.capturable = capturable
         self._dyn = None            # device [n_params, 2] fp32, capturable mode
+        self._ring = None           # pinned staging for the per-step scalars
         self._slot = {}
 
     # -- helpers -----------------------------------------------------------------------------------------
@@ -59,21 +60,27 @@ class FusedAdam(torch.optim.Optimizer):
     def advance(self):
         """Host half: bump every active parameter's step count; in capturable mode also ship this step's
         bias-correction scalars to the device buffer (one small async copy from pinned memory)."""
-        host, dev = None, None
+        host, dev, k = None, None, None
         for group, p in self._active():
             st = self._state(p)
             st['step'] += 1
             if self.capturable:
                 if host is None:
                     dev = self._ensure_dyn(p.device)
-                    # fresh pinned block per step: the caching host allocator keeps it alive until the copy ran
-                    host = torch.zeros(dev.shape, dtype=torch.float32, pin_memory=True)
+                    if self._ring is None:
+                        from .utils import PinnedRing
+                        self._ring = PinnedRing([tuple(dev.shape)])
+                        for (buf,) in self._ring.sets:
+                            buf.zero_()
+                    k, (host,) = self._ring.acquire()
+                    rows = host.numpy()
                 a, b = self._scalars(group, st['step'])
                 i = self._slot[id(p)]
-                host[i, 0] = a
-                host[i, 1] = b
+                rows[i, 0] = a
+                rows[i, 1] = b
         if host is not None:
             dev.copy_(host, non_blocking=True)
+            self._ring.release(k)
 
     @torch.no_grad()
     def launch(self):

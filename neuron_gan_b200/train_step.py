@@ -21,7 +21,7 @@ import torch.distributed as dist
 
 from . import _lib, engine, ops
 from .optim import FusedAdam
-from .utils import sample_latent_vec
+from .utils import PinnedRing, sample_latent_vec
 
 F32 = torch.float32
 
@@ -45,6 +45,7 @@ class TrainStep:
         self._chain_stream = None
         self._bound = {}
         self._graphs = {}
+        self._rings = {}
         self._last_key = None
         self._versions_seen = None
         self.launches_per_step = 0      # kernels of libngan_b200.so launched (or replayed) by the last iteration
@@ -75,13 +76,16 @@ class TrainStep:
             dist.all_reduce(flat, op=dist.ReduceOp.AVG)
 
     # -- RNG draws in the reference's order: z (D_W_loss) -> z (grad pen) -> eps -> z (G_W_loss) --------------
-    def draw(self, batch, device):
+    def draw_host(self, batch):
         z1 = sample_latent_vec((batch, self.G.latent_dim))
         z2 = sample_latent_vec((batch, self.G.latent_dim))
         eps = torch.rand((batch, 1, 1, 1))          # CPU generator for reproducibility
         z3 = sample_latent_vec((batch, self.G.latent_dim))
-        pin = torch.cuda.is_available()
-        return tuple((t.pin_memory() if pin else t).to(device, non_blocking=True) for t in (z1, z2, eps, z3))
+        return z1, z2, eps, z3
+
+    def draw(self, batch, device):
+        """The four draws of one iteration as device tensors (for callers that keep draws resident)."""
+        return tuple(t.to(device) for t in self.draw_host(batch))
 
     # -- the iteration as three kernel sequences; gradients are complete at the end of seg_d and seg_g -----------
     def _buffers(self, B, R, dev):
@@ -93,14 +97,24 @@ class TrainStep:
                                z3=torch.empty((B, L), dtype=F32, device=dev),
                                eps=torch.empty((B,), dtype=F32, device=dev), B=B, out=SimpleNamespace())
 
-    @staticmethod
-    def _load(buf, x, z1, z2, eps, z3):
-        B = buf.B
+    def _load(self, buf, x, z1, z2, eps, z3):
+        """Copy the iteration's inputs into the step buffers.  Device and pinned-host sources are copied directly
+        (asynchronously); pageable host tensors -- the CPU draws -- go through a ring of pinned staging buffers."""
+        B, L = buf.B, self.G.latent_dim
         buf.imgs[:B].copy_(x.reshape(B, x.shape[-2], x.shape[-1]), non_blocking=True)
-        buf.z12[:B].copy_(z1, non_blocking=True)
-        buf.z12[B:].copy_(z2, non_blocking=True)
-        buf.eps.copy_(eps.reshape(B), non_blocking=True)
-        buf.z3.copy_(z3, non_blocking=True)
+        pairs = ((buf.z12[:B], z1), (buf.z12[B:], z2), (buf.eps, eps.reshape(B)), (buf.z3, z3))
+        if all(src.is_cuda or src.is_pinned() for _, src in pairs):
+            for dst, src in pairs:
+                dst.copy_(src, non_blocking=True)
+            return
+        ring = self._rings.get(B)
+        if ring is None:
+            ring = self._rings[B] = PinnedRing([(B, L), (B, L), (B,), (B, L)])
+        k, stage = ring.acquire()
+        for (dst, src), st in zip(pairs, stage):
+            st.copy_(src)
+            dst.copy_(st, non_blocking=True)
+        ring.release(k)
 
     def _seg_d(self, buf):
         """critic step up to complete gradients (train.py:356-365).  After the shared generator pass the
@@ -209,7 +223,7 @@ class TrainStep:
         [D_loss, score_real, score_fake, G_loss, D_grad_pen] (D_loss includes the penalty, train.py:362)."""
         dev = next(self.G.parameters()).device
         B, R = images.shape[0], images.shape[-1]
-        z1, z2, eps, z3 = draws if draws is not None else self.draw(B, dev)
+        z1, z2, eps, z3 = draws if draws is not None else self.draw_host(B)
         key = self._config_key(B, R)
         ent = self._graphs.get(key)
         versions = self._versions()

@@ -178,15 +178,20 @@ def plot_gen_samples(Generator: nn.Module, eval_noise=None, N_images=16, seed=No
 class DevicePrefetcher:
     """Iterate host batches (ideally pinned) as device tensors with the next batch's host-to-device copy running on
     its own stream while the current one is consumed -- the role `pin_memory=True` + `non_blocking` copies play in
-    the reference's loop (train.py:150-154, 352-353).  The yielded tensor is only valid until the next iteration."""
+    the reference's loop (train.py:150-154, 352-353).  The yielded tensor is only valid until the next iteration.
+    `batches` is an iterable, or a callable returning one (so the object can be iterated once per epoch)."""
 
     def __init__(self, batches, device, depth=2):
         self.batches, self.device, self.depth = batches, torch.device(device), max(2, int(depth))
+        self._stream = None
+        self._slots = [None] * self.depth          # device staging, kept across iterations of this object
 
     def __iter__(self):
-        copy_stream = torch.cuda.Stream(self.device)
-        slots, ready, free = [None] * self.depth, [None] * self.depth, [None] * self.depth
-        it = iter(self.batches)
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(self.device)
+        copy_stream = self._stream
+        slots, ready, free = self._slots, [None] * self.depth, [None] * self.depth
+        it = iter(self.batches() if callable(self.batches) else self.batches)
 
         def launch(k, host):
             with torch.cuda.stream(copy_stream):
@@ -215,3 +220,27 @@ class DevicePrefetcher:
             if nxt is None:
                 return
             i += 1
+
+
+class PinnedRing:
+    """A few sets of pinned host staging buffers reused round-robin.  Asynchronous host-to-device copies need pinned
+    sources that stay untouched until the copy has run; allocating fresh pinned memory every step costs a
+    cudaHostAlloc whenever the caching allocator has nothing free (milliseconds of jitter), so the buffers are
+    allocated once and each set is guarded by an event recorded after its last use."""
+
+    def __init__(self, shapes, dtype=torch.float32, depth=4):
+        self.sets = [[torch.empty(s, dtype=dtype).pin_memory() for s in shapes] for _ in range(depth)]
+        self.events = [None] * depth
+        self.i = 0
+
+    def acquire(self):
+        k = self.i % len(self.sets)
+        self.i += 1
+        if self.events[k] is not None:
+            self.events[k].synchronize()          # long complete unless the host runs > depth steps ahead
+        return k, self.sets[k]
+
+    def release(self, k):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k] = ev

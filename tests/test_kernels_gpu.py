@@ -338,3 +338,34 @@ def test_adam_refreshes_the_conv_operand_images(cin, cout):
                        inv_bc2_sqrt=31.6)], 0.5, 0.999, 1e-8)
     fwd, dgrad = o.prep_conv_weight(p)
     assert torch.equal(img[:n], fwd) and torch.equal(img[n:], dgrad)
+
+
+@pytest.mark.parametrize('B,cin,cout,H,W', [(2, 16, 16, 64, 64), (3, 32, 16, 40, 72), (2, 64, 64, 32, 32)])
+@pytest.mark.parametrize('want_y', [True, False])
+def test_conv3x3_fwd_with_fused_toimage(B, cin, cout, H, W, want_y):
+    """conv + LeakyReLU + PixelNorm + ToImage in one kernel == torch fp32 reference of the same chain
+    (models.py:203-204, 263-268, 141-149); y / r are optional outputs."""
+    o = ops()
+    x = rnd(B, cin, H, W, seed=31)
+    w = rnd(cout, cin, 3, 3, seed=32, scale=GAIN / math.sqrt(cin * 9))
+    tw = torch.randn(cout, device='cuda') * 0.3
+    s = GAIN / math.sqrt(cin * 9)
+    y_ref, r_ref = pn_ref(F.leaky_relu(F.conv2d(s * x, w, None, padding=1), LEAK))
+    img_ref = torch.tanh((y_ref * tw.view(1, -1, 1, 1)).sum(1))
+    w_fwd, _ = o.prep_conv_weight(w)
+    y, r, img = o.conv3x3_fwd_toim(o.nchw_to_c8(x), w_fwd, None, s, LEAK, cout, tw, want_y=want_y, want_r=want_y)
+    assert torch.allclose(img, img_ref, atol=1e-2) and rel(img, img_ref) < 1e-2
+    if want_y:
+        assert rel(o.c8_to_nchw(y), y_ref) < 1e-2 and rel(r, r_ref[:, 0]) < 1e-2
+    else:
+        assert y is None and r is None
+
+
+def test_fused_toimage_is_refused_for_wide_layers():
+    from neuron_gan_b200._lib import NganError
+    o = ops()
+    x = rnd(1, 128, 16, 16, seed=33)
+    w = rnd(128, 128, 3, 3, seed=34)
+    w_fwd, _ = o.prep_conv_weight(w)
+    with pytest.raises(NganError):
+        o.conv3x3_fwd_toim(o.nchw_to_c8(x), w_fwd, None, 1.0, LEAK, 128, torch.zeros(128, device='cuda'))

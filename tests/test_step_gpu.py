@@ -293,3 +293,43 @@ def test_graph_replay_equals_eager(res, alpha, batch):
             assert d.max().item() <= 2.1e-4 and d.mean().item() < 2e-6, (k, d.max().item(), d.mean().item())
     s_next = step(xs[3], draws[3]).cpu()                   # and the graph is used again afterwards
     assert torch.isfinite(s_next).all() and step.launches_per_step == launches_eager
+
+
+def test_progressive_schedule_through_a_transition():
+    """TrainStep across the structure mutations of a resolution transition (train.py:319-333): 16x16 stable ->
+    increase_resolution -> fade-in steps -> stable 32x32.  The active parameter set, the flat gradient buffers and
+    the captured graphs all change at these points; losses stay finite, newly active blocks start training
+    (their Adam step counts start at the transition), and after the transition the state dict carries the
+    reference's renumbered keys."""
+    from neuron_gan_b200.train_step import TrainStep
+    torch.manual_seed(11)
+    G, D = nets(16, 1.0)
+    step = TrainStep(G, D)
+    B = 4
+    seen_keys = set()
+
+    def run(n, res):
+        for i in range(n):
+            stats = step(O.synthetic_images(B, res, seed=70 + i).to(DEV)).cpu()
+            assert torch.isfinite(stats).all(), stats
+            seen_keys.add(step._last_key)
+
+    run(3, 16)                                            # third iteration is a graph replay
+    new_g = G.conv_block_list[0].conv1.weight
+    w_before = new_g.detach().clone()
+    assert new_g.grad is None and not step.opt_g.state.get(new_g)
+    G.increase_resolution()
+    D.increase_resolution()
+    assert G.image_size == D.image_size == 32 and G.alpha_value() == 0.0
+    for _ in range(3):                                    # alpha: 0.25, 0.5, 0.75 (one iteration each, like an epoch)
+        G.advance_transition(0.25)
+        D.advance_transition(0.25)
+        run(1, 32)
+    assert step.opt_g.state[new_g]['step'] == 3 and not torch.equal(new_g.detach(), w_before)
+    G.advance_transition(0.25)                            # alpha reaches 1: the block moves into `layers`
+    D.advance_transition(0.25)
+    assert G.alpha_value() >= 1.0 and 'layers.7.1.weight' in G.state_dict() and len(G.conv_block_list) == 4
+    run(3, 32)
+    assert step.opt_g.state[new_g]['step'] == 6
+    assert step.opt_d.state[D.head_conv().weight]['step'] == 9      # the trunk trained in every iteration
+    assert len(seen_keys) == 5 and len(step._graphs) == 2             # graphs only for the two repeated configurations
