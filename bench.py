@@ -330,7 +330,10 @@ def run_b200(args):
         for tot, cnt, name, a in top:
             fam_tot[fam_of(name)] = fam_tot.get(fam_of(name), 0.0) + tot
         dom = max(fam_tot, key=fam_tot.get)
-        cand = [e for e in top if fam_of(e[2]) == dom and algorithmic_bytes(e[2], e[3])]
+        # ... = the launch shape with the longest single launch: the event pair around a launch also times ~5-10 us of
+        # launch latency on an idle stream (this pass is host-paced), which distorts the short launches
+        cand = sorted((e for e in top if fam_of(e[2]) == dom and algorithmic_bytes(e[2], e[3])),
+                      key=lambda e: -e[0] / e[1])
         if cand:
             tot, cnt, name, a = cand[0]
             by, fl = algorithmic_bytes(name, a), conv_flops(name, a)

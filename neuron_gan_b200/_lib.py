@@ -5,7 +5,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libngan_b200.so')
+LIB_PATH = os.environ.get('NGAN_LIB') or os.path.join(_HERE, 'libngan_b200.so')   # NGAN_LIB: debug builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'ngan_b200.h')
 
 _CTYPES = {'int': ctypes.c_int, 'float': ctypes.c_float, 'long long': ctypes.c_longlong}

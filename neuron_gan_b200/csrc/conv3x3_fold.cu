@@ -128,88 +128,108 @@ __device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool vali
         }
     } else if constexpr (EPI == EPI_BWD_PN) {
         // ga = mask(y) * r * (g - y*mean_c(g*y)) (+ addin), g = scale*acc     [SURVEY.md 8a row 3]
+        // = mask(y) * (A*acc - Bt*y) with A = r*scale, Bt = r*t, t = scale*mean_c(acc*y): packed f32x2 arithmetic.
         // Wide layers (COUT > 16) re-load y in the second pass (an L1 hit) instead of holding it in registers.
         if (!valid) return;
         constexpr bool kKeep = COUT <= 16;
         const uint4* yq = reinterpret_cast<const uint4*>(a.y) + q0;
-        uint4 yp[kKeep ? NCH : 1];
+        __align__(8) float ykeep[kKeep ? COUT : 8];
         const float rinv = __ldg(a.r + p0);
-        float t = 0.f;
+        float2* o2 = reinterpret_cast<float2*>(o);
+        float2 dot2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
-            const uint4 yj = __ldg(yq + j * HW);
-            if constexpr (kKeep) yp[j] = yj;
-            float yv[8];
-            unpack8(yj, yv);
+            __align__(8) float ytmp[8];
+            float* yv = kKeep ? ykeep + j * 8 : ytmp;
+            unpack8(__ldg(yq + j * HW), yv);
+            const float2* y2 = reinterpret_cast<const float2*>(yv);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                o[j * 8 + e] *= a.scale;
-                t += o[j * 8 + e] * yv[e];
-            }
+            for (int e = 0; e < 4; ++e) dot2 = __ffma2_rn(o2[j * 4 + e], y2[e], dot2);
         }
-        t *= inv_c;
+        const float t = (dot2.x + dot2.y) * a.scale * inv_c;
+        const float A = rinv * a.scale, nBt = -rinv * t;
+        const float2 A2 = make_float2(A, A), nBt2 = make_float2(nBt, nBt), s2 = make_float2(a.scale, a.scale);
         uint4* out = reinterpret_cast<uint4*>(a.out0);
         uint4* out1 = reinterpret_cast<uint4*>(a.out1);
         const uint4* aq = reinterpret_cast<const uint4*>(a.addin);
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
-            float yv[8], ad[8], ga[8];
-            if constexpr (kKeep) unpack8(yp[j], yv); else unpack8(__ldg(yq + j * HW), yv);
+            __align__(8) float ytmp[8], ad[8], ga[8];
+            float* yv = kKeep ? ykeep + j * 8 : ytmp;
+            if constexpr (!kKeep) unpack8(__ldg(yq + j * HW), yv);
             if (aq) unpack8(__ldg(aq + q0 + j * HW), ad);
+            const float2* y2 = reinterpret_cast<const float2*>(yv);
+            float2* ga2 = reinterpret_cast<float2*>(ga);
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-                ga[e] = lrelu_mask(yv[e], a.leak) * rinv * (o[j * 8 + e] - yv[e] * t) + (aq ? ad[e] : 0.f);
+            for (int e = 0; e < 4; ++e) {
+                float2 v = __ffma2_rn(y2[e], nBt2, __fmul2_rn(o2[j * 4 + e], A2));
+                v = __fmul2_rn(v, make_float2(lrelu_mask(y2[e].x, a.leak), lrelu_mask(y2[e].y, a.leak)));
+                if (aq) v = __fadd2_rn(v, reinterpret_cast<const float2*>(ad)[e]);
+                ga2[e] = v;
+            }
             out[q0 + j * HW] = pack8(ga);
-            if (out1) out1[q0 + j * HW] = pack8(o + j * 8);
+            if (out1) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ga2[e] = __fmul2_rn(o2[j * 4 + e], s2);
+                out1[q0 + j * HW] = pack8(ga);
+            }
         }
-    } else {  // EPI_DBL, formulas in conv3x3_umma.cu / SURVEY.md 8a row 3
+    } else {  // EPI_DBL, formulas in conv3x3_umma.cu / SURVEY.md 8a row 3 (packed f32x2 arithmetic)
+        //   gh = mask*scale*acc;  t = mean(gy*y), u = mean(gh*y), w = mean(gh*gy)
+        //   out0 (ghat_y) = r*(gh - u*y);  out1 (ahat) = -mask*r^2*(t*gh + u*gy + (w - 3ut)*y)
         if (!valid) return;
         constexpr bool kKeep = COUT <= 16;
         const uint4* yq = reinterpret_cast<const uint4*>(a.y) + q0;
         const uint4* gq = reinterpret_cast<const uint4*>(a.gy) + q0;
-        uint4 yp[kKeep ? NCH : 1], gp[kKeep ? NCH : 1];
+        __align__(8) float ykeep[kKeep ? COUT : 8], gkeep[kKeep ? COUT : 8];
         const float rinv = __ldg(a.r + p0);
-        float t = 0.f, u = 0.f, w = 0.f;
+        float2* o2 = reinterpret_cast<float2*>(o);
+        const float2 s2 = make_float2(a.scale, a.scale);
+        float2 t2 = make_float2(0.f, 0.f), u2 = t2, w2 = t2;
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
-            const uint4 yj = __ldg(yq + j * HW), gj = __ldg(gq + j * HW);
-            if constexpr (kKeep) {
-                yp[j] = yj;
-                gp[j] = gj;
-            }
-            float yv[8], gv[8];
-            unpack8(yj, yv);
-            unpack8(gj, gv);
+            __align__(8) float ytmp[8], gtmp[8];
+            float* yv = kKeep ? ykeep + j * 8 : ytmp;
+            float* gv = kKeep ? gkeep + j * 8 : gtmp;
+            unpack8(__ldg(yq + j * HW), yv);
+            unpack8(__ldg(gq + j * HW), gv);
+            const float2* y2 = reinterpret_cast<const float2*>(yv);
+            const float2* g2 = reinterpret_cast<const float2*>(gv);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float gh = lrelu_mask(yv[e], a.leak) * a.scale * o[j * 8 + e];
-                o[j * 8 + e] = gh;
-                t += gv[e] * yv[e];
-                u += gh * yv[e];
-                w += gh * gv[e];
+            for (int e = 0; e < 4; ++e) {
+                const float2 m = make_float2(lrelu_mask(y2[e].x, a.leak), lrelu_mask(y2[e].y, a.leak));
+                const float2 gh = __fmul2_rn(__fmul2_rn(o2[j * 4 + e], s2), m);
+                o2[j * 4 + e] = gh;
+                t2 = __ffma2_rn(g2[e], y2[e], t2);
+                u2 = __ffma2_rn(gh, y2[e], u2);
+                w2 = __ffma2_rn(gh, g2[e], w2);
             }
         }
-        t *= inv_c;
-        u *= inv_c;
-        w *= inv_c;
+        const float t = (t2.x + t2.y) * inv_c, u = (u2.x + u2.y) * inv_c, w = (w2.x + w2.y) * inv_c;
         const float k3 = w - 3.f * u * t;
+        const float nr2 = -rinv * rinv;
+        const float2 r2 = make_float2(rinv, rinv), nru2 = make_float2(-rinv * u, -rinv * u);
+        const float2 ct = make_float2(nr2 * t, nr2 * t), cu = make_float2(nr2 * u, nr2 * u), ck = make_float2(nr2 * k3, nr2 * k3);
         uint4* out0 = reinterpret_cast<uint4*>(a.out0);
         uint4* out1 = reinterpret_cast<uint4*>(a.out1);
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
-            float yv[8], gv[8], o0[8], o1[8];
-            if constexpr (kKeep) {
-                unpack8(yp[j], yv);
-                unpack8(gp[j], gv);
-            } else {
+            __align__(8) float ytmp[8], gtmp[8], o0[8], o1[8];
+            float* yv = kKeep ? ykeep + j * 8 : ytmp;
+            float* gv = kKeep ? gkeep + j * 8 : gtmp;
+            if constexpr (!kKeep) {
                 unpack8(__ldg(yq + j * HW), yv);
                 unpack8(__ldg(gq + j * HW), gv);
             }
+            const float2* y2 = reinterpret_cast<const float2*>(yv);
+            const float2* g2 = reinterpret_cast<const float2*>(gv);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float gh = o[j * 8 + e];
-                o0[e] = rinv * (gh - yv[e] * u);
-                o1[e] = -lrelu_mask(yv[e], a.leak) * rinv * rinv * (t * gh + u * gv[e] + k3 * yv[e]);
+            for (int e = 0; e < 4; ++e) {
+                const float2 gh = o2[j * 4 + e];
+                reinterpret_cast<float2*>(o0)[e] = __ffma2_rn(y2[e], nru2, __fmul2_rn(gh, r2));
+                const float2 m = make_float2(lrelu_mask(y2[e].x, a.leak), lrelu_mask(y2[e].y, a.leak));
+                float2 v = __ffma2_rn(y2[e], ck, __ffma2_rn(g2[e], cu, __fmul2_rn(gh, ct)));
+                reinterpret_cast<float2*>(o1)[e] = __fmul2_rn(v, m);
             }
             out0[q0 + j * HW] = pack8(o0);
             out1[q0 + j * HW] = pack8(o1);
@@ -411,6 +431,8 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty + buf);
             if (trace) a.dbg_clock[it * 8 + 7] = clock64();
+            if (kDebug && a.dbg_clock && blockIdx.x == 0 && it < 32 && warp == 2 + 4 * kFoldEpiGroups && lane == 0)
+                a.dbg_clock[it * 8 + 4] = clock64();      // the last epilogue warp of the CTA
             if (++buf == a.n_acc) {
                 buf = 0;
                 bph ^= 1;
@@ -467,8 +489,10 @@ int conv3x3_fold_dispatch(int epi, const void* x, ConvArgs a, int B, int cin, in
     const int nkx = nkx_env == 1 ? 1 : 3;
     const int NF = nkx == 3 ? 3 * cout : cout;         // accumulator columns per M-tile
     // M-tiles (4 tile rows each) per CTA tile: at least two accumulator buffers of nMT*NF columns in 512 columns
+    static const int nmt_env = getenv("NGAN_FOLD_NMT") ? atoi(getenv("NGAN_FOLD_NMT")) : 0;   // tuning experiments
     int nMT = 256 / NF;
-    if (nMT > 4) nMT = 4;
+    const int nmt_cap = nmt_env > 0 ? nmt_env : 4;
+    if (nMT > nmt_cap) nMT = nmt_cap;
     if (nMT < 1) nMT = 1;
     const int tiles_x = (W + kFoldTW - 1) / kFoldTW;
     // shrink tiles while the grid cannot give every SM a couple of tiles

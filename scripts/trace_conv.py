@@ -14,6 +14,6 @@ lib = ctypes.CDLL(_lib.LIB_PATH)
 assert lib.ngan_debug_conv_trace(buf) == 0
 t = [[buf[i * 8 + k] for k in range(8)] for i in range(32)]
 t0 = t[0][0]
-print('tile: mma[start waitEmpty waitFull issued committed]  epi[start gotFull done]   (cycles since first)')
+print('tile: mma[start waitEmpty waitFull issued lastEpiWarpDone]  epi(warp 3)[start gotFull done]   (cycles since first)')
 for i in range(24):
     print(i, [v - t0 for v in t[i][:5]], [v - t0 for v in t[i][5:]])
