@@ -2,6 +2,7 @@
 // reporting, and forwarding to the launchers.  No torch types cross this boundary.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/ngan_b200.h"
 #include "common.cuh"
@@ -24,6 +25,10 @@ int check_cuda(cudaError_t e, const char* what) {
     return NGAN_ERR_CUDA;
 }
 int check_launch(const char* what) { return check_cuda(cudaGetLastError(), what); }
+bool pdl_enabled() {
+    static const bool on = getenv("NGAN_NO_PDL") == nullptr;
+    return on;
+}
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 static inline bool bad_c(int C) { return C <= 0 || (C % 8) != 0; }

@@ -22,6 +22,7 @@ namespace ngan {
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int check_launch(const char* what);
+bool pdl_enabled();   // programmatic dependent launch of the conv kernels (NGAN_NO_PDL=1 disables)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -114,6 +115,32 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor in the
+// stream is still draining: its CTAs run their prologue (barrier init, TMEM allocation, descriptor prefetch) and
+// then block in pdl_wait() until the predecessor grid has completed and its writes are visible.  pdl_trigger()
+// lets the NEXT kernel's CTAs be scheduled as soon as this grid's CTAs free their resources.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Host side: launch `kern` with the programmatic-stream-serialization attribute.  ONLY for kernels whose first
+// statements are pdl_trigger(); pdl_wait(); (or that wait before their first global-memory access).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM

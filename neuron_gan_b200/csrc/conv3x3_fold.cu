@@ -245,6 +245,7 @@ template <int CIN, int COUT, int EPI, int NKX>
 __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                     const ConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_trigger();
     constexpr int NF = 3 * COUT;                       // rows of the weight image per (ky, k-group): (kx, co)
     constexpr int NMMA = NKX == 3 ? NF : COUT;         // MMA N
     constexpr uint32_t W_BYTES = 9 * CIN * COUT * 2;   // [3 ky][CIN/8][NF][8] bf16
@@ -288,6 +289,7 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_wait();        // everything above overlapped the previous kernel's tail; its results are needed from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -462,7 +464,18 @@ static int launch_fold(const CUtensorMap& tmap, const ConvArgs& a, uint32_t smem
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv3x3_fold)");
         configured = true;
     }
-    kern<<<n_ctas, FoldCfg<COUT, EPI>::kThreads, smem_bytes, st>>>(tmap, a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_ctas);
+    cfg.blockDim = dim3(FoldCfg<COUT, EPI>::kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmap, a);
+    if (le != cudaSuccess) return check_cuda(le, "cudaLaunchKernelEx(conv3x3_fold)");
     return check_launch("conv3x3_fold");
 }
 

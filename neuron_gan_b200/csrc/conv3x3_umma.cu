@@ -202,6 +202,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint32_t tmem_a
 template <int CIN, int COUT, int EPI>
 __global__ void __launch_bounds__(128) conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_trigger();
     constexpr uint32_t W_TAP_BYTES = CIN * COUT * 2;
     constexpr uint32_t IDESC = umma_idesc_bf16(128, COUT);
 
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(128) conv3x3_umma_kernel(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_wait();        // everything above overlapped the previous kernel's tail; its results are needed from here on
 
     if (warp == 0) {
         // ---- input tile: one TMA box {2*Wh x (TH+2) x CIN/8 x 1} of 8-byte elements, then the MMA issue loop
@@ -421,7 +423,18 @@ static int launch_conv(const CUtensorMap& tmap, const ConvArgs& a, const TilePla
         configured = 227 * 1024;
     }
     dim3 grid((a.W + p.TW - 1) / p.TW, (a.H + p.TH - 1) / p.TH, a.B);
-    kern<<<grid, 128, p.smem_bytes, st>>>(tmap, a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = p.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmap, a);
+    if (le != cudaSuccess) return check_cuda(le, "cudaLaunchKernelEx(conv3x3_umma)");
     return check_launch("conv3x3_umma");
 }
 

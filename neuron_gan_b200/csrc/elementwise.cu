@@ -104,6 +104,7 @@ __device__ __forceinline__ void split_bpix(size_t i, size_t HW, size_t& b, size_
 // contiguous 1 KB row segments.
 __global__ void __launch_bounds__(128) upsample2x_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int H,
                                                             int W) {
+    pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     const int ix = blockIdx.x * blockDim.x + threadIdx.x;
     if (ix >= W) return;
     const int iy = blockIdx.y;
@@ -153,6 +154,7 @@ int upsample2x_c8(const void* x, void* out, int B, int C, int H, int W, cudaStre
 }
 
 __global__ void avgpool2_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int H, int W, size_t total) {
+    pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int OW = W / 2, OH = H / 2;
@@ -182,6 +184,7 @@ int avgpool2_c8(const void* x, void* out, int B, int C, int H, int W, cudaStream
 __global__ void pn_bwd_c8_kernel(const uint4* __restrict__ g, int unpool, float gscale, const uint4* __restrict__ y,
                                  const float* __restrict__ r, const uint4* __restrict__ addin, uint4* __restrict__ ga,
                                  uint4* __restrict__ gy_out, float leak, int C, int H, int W, size_t total) {
+    pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const size_t HW = static_cast<size_t>(H) * W;
@@ -232,6 +235,7 @@ __global__ void up2_bwd_pn_bwd_kernel(const uint4* __restrict__ g_up, const uint
                                       const float* __restrict__ r, const float* __restrict__ extra_pre,
                                       const float* __restrict__ extra_w, uint4* __restrict__ ga, float leak, int H,
                                       int W, size_t total) {
+    pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     constexpr int NCH = C / 8;
@@ -440,6 +444,7 @@ int scale_rows_f32(const float* x, const float* coeff, float scale, float* out, 
 __global__ void fromim_fwd_kernel(const float* __restrict__ xp, const float* __restrict__ w,
                                   const float* __restrict__ bias, uint4* __restrict__ out, int C, size_t HW,
                                   size_t total) {
+    pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     size_t b, pix;
@@ -463,6 +468,7 @@ int fromim_fwd(const float* xp, const float* w, const float* b, void* out, int B
 __global__ void d_fade_fwd_kernel(const uint4* __restrict__ y_end, const float* __restrict__ xp,
                                   const float* __restrict__ w, const float* __restrict__ bias, float alpha,
                                   uint4* __restrict__ out, int C, size_t HW, size_t total) {
+    pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     size_t b, pix;
@@ -558,6 +564,7 @@ int fromim_bwd(const void* g, int unpool, float gscale, const float* xp, const f
 __global__ void fromim_dbl_kernel(const float* __restrict__ ghat_xp, float in_scale, const uint4* __restrict__ g,
                                   int unpool, float gscale, const float* __restrict__ w, uint4* __restrict__ ghat_out,
                                   float* __restrict__ what, int C, int H, int W, size_t total) {
+    pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     extern __shared__ float sacc[];  // [C]
     for (int k = threadIdx.x; k < C; k += blockDim.x) sacc[k] = 0.f;
     __syncthreads();
@@ -627,6 +634,7 @@ __global__ void toim_bwd_kernel(const float* __restrict__ g_img, float gscale, c
                                 const uint4* __restrict__ y, const float* __restrict__ r, const float* __restrict__ w,
                                 uint4* __restrict__ ga, float* __restrict__ gpre_out, float* __restrict__ gw,
                                 float leak, int C, size_t HW, size_t total) {
+    pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     extern __shared__ float sacc[];  // [C]
     for (int k = threadIdx.x; k < C; k += blockDim.x) sacc[k] = 0.f;
     __syncthreads();
@@ -724,6 +732,7 @@ int head_fwd(const void* y, const float* w, const float* bias, float scale, floa
 __global__ void head_bwd_pn_kernel(const float* __restrict__ gout, const float* __restrict__ w, float scale,
                                    const uint4* __restrict__ y, const float* __restrict__ r, uint4* __restrict__ ga,
                                    uint4* __restrict__ gy_out, float leak, int C, int HW, size_t total) {
+    pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const size_t b = i / HW;

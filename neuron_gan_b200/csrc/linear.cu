@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(192) linear_fwd_umma_kernel(const uint4* __res
                                                               const __nv_bfloat16* __restrict__ wb, float scale,
                                                               float leak, uint4* __restrict__ y, float* __restrict__ r,
                                                               int B, int Bpad, int SS) {
+    pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     extern __shared__ uint8_t smem_raw[];
     constexpr int KG = K / 8;                          // k-groups (16-byte columns of the operands)
     constexpr int CHUNK_KG = kLinStageBytes / (C * 16);   // k-groups per weight chunk
