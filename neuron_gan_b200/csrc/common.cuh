@@ -91,11 +91,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// Warp-level wait: one lane polls, the others park at the warp barrier.  Hundreds of threads polling one
-// mbarrier serialise in the barrier unit and starve the single MMA-issuing thread (measured: ~3x slower loop).
+// Warp-level wait.  Default: every lane executes the same try_wait (one warp-wide instruction per poll, no
+// divergence: the lane-0-only variant pays a BSSY/BSYNC/WARPSYNC reconvergence and its branch-resolve stalls on
+// every wait, and the issue-bound epilogues wait twice per tile).  NGAN_LANE0_WAIT selects the old variant.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+#ifdef NGAN_LANE0_WAIT
     if (lane == 0) mbar_wait(bar, parity);
     __syncwarp();
+#else
+    (void)lane;
+    mbar_wait(bar, parity);
+#endif
 }
 
 // ---------------------------------------------------------------- TMA / bulk copies
