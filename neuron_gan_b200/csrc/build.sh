@@ -13,6 +13,11 @@ if [ -n "$NGAN_DEBUG_BUILD" ]; then
   OUT=../libngan_b200_dbg.so
   BUILD=build_dbg
 fi
+if [ -n "$NGAN_VARIANT" ]; then      # tuning variants: NGAN_VARIANT=name NGAN_EXTRA_FLAGS="-D..." bash build.sh
+  FLAGS="$FLAGS $NGAN_EXTRA_FLAGS"
+  OUT=../libngan_b200_$NGAN_VARIANT.so
+  BUILD=build_$NGAN_VARIANT
+fi
 mkdir -p $BUILD
 pids=()
 for f in api conv3x3_umma conv3x3_fold wgrad elementwise linear adam; do

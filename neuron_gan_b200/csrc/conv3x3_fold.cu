@@ -38,6 +38,23 @@ template <int COUT, int EPI> struct FoldCfg {
 };
 // timing-experiment hooks (NGAN_CONV_DEBUG / NGAN_CONV_TRACE) are compiled in only with -DNGAN_CONV_DEBUG_BUILD:
 // their predicates cost ~10 % of the instructions of the issue-bound epilogue
+// tuning switches of the epilogue <-> MMA hand-over (defaults = best measured, see profiles/README.md)
+#ifndef NGAN_EPI_EARLY
+#define NGAN_EPI_EARLY -1       // give the accumulator buffer back right after the TMEM loads (1), after the stores (0),
+#endif                          // or per kernel as measured (-1): early for the light linear epilogue and for the
+                                // 32/64-channel layers, late for the heavy 16-channel epilogues (early cost them 15 %)
+#ifndef NGAN_EPI_ALLARRIVE
+#define NGAN_EPI_ALLARRIVE 1    // every epilogue thread arrives on the buffer's barrier (1) or one elected lane per warp (0)
+#endif
+__device__ __forceinline__ void acc_release(uint64_t* bar) {
+    tc_fence_before();
+#if NGAN_EPI_ALLARRIVE
+    mbar_arrive(bar);
+#else
+    __syncwarp();
+    if (elect_one()) mbar_arrive(bar);
+#endif
+}
 #ifdef NGAN_CONV_DEBUG_BUILD
 constexpr bool kDebug = true;
 #else
@@ -251,6 +268,7 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
     constexpr uint32_t W_BYTES = 9 * CIN * COUT * 2;   // [3 ky][CIN/8][NF][8] bf16
     constexpr uint32_t IDESC = umma_idesc_bf16(128, NMMA);
     constexpr int kFoldEpiGroups = FoldCfg<COUT, EPI>::kEpiGroups;
+    constexpr bool kEarlyRelease = NGAN_EPI_EARLY < 0 ? (EPI == EPI_LINEAR || COUT >= 32) : (NGAN_EPI_EARLY != 0);
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const uint32_t in_bytes = (CIN / 8) * a.plane_bytes;   // plane = (TH+2)*32*16, a multiple of 128
@@ -279,7 +297,7 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
         }
         for (int s = 0; s < a.n_acc; ++s) {
             mbar_init(bar_acc_full + s, 1);
-            mbar_init(bar_acc_empty + s, 4 * kFoldEpiGroups);   // one arrival per epilogue warp
+            mbar_init(bar_acc_empty + s, (NGAN_EPI_ALLARRIVE ? 128 : 4) * kFoldEpiGroups);
         }
         mbar_fence_init();
     }
@@ -396,7 +414,11 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
             // M-tiles of consecutive tiles rotate over the groups (with one M-tile per tile, tiles alternate)
             const int mt0 = static_cast<int>((static_cast<unsigned>(group) - static_cast<unsigned>(it * a.nMT)) &
                                              (kFoldEpiGroups - 1));
+            // The accumulator buffer goes back to the MMA warps as soon as this thread's TMEM loads have landed in
+            // registers -- before the arithmetic and the stores -- so the next tile's MMAs overlap this epilogue.
+            bool released = false;
             for (int mt = mt0; mt < ((kDebug && (a.debug & 2)) ? 0 : a.nMT); mt += kFoldEpiGroups) {
+                const bool last_mt = mt + kFoldEpiGroups >= a.nMT;
                 const int rr = mt * 4 + quad;      // row of the tile (Wh = 32: one warp = one row)
                 const int oy = tile_y * a.TH + rr;
                 const bool valid = (lane < kFoldTW) && (rr < a.TH) && (oy < a.H) && (ox < a.W);
@@ -410,6 +432,10 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
                         tmem_ld16_nowait(taddr + COUT + c0, v1);
                         tmem_ld16_nowait(taddr + 2 * COUT + c0, v2);
                         tmem_ld_wait();
+                        if (kEarlyRelease && last_mt && c0 + 16 >= COUT) {
+                            acc_release(bar_acc_empty + buf);
+                            released = true;
+                        }
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
                             const float2 s1 = make_float2(__shfl_down_sync(0xffffffffu, v1[i], 1),
@@ -424,14 +450,16 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
 #pragma unroll
                     for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16_nowait(taddr + c0, o + c0);
                     tmem_ld_wait();
+                    if (kEarlyRelease && last_mt) {
+                        acc_release(bar_acc_empty + buf);
+                        released = true;
+                    }
                 }
                 const size_t q0 = static_cast<size_t>(b) * (COUT / 8) * HW + static_cast<size_t>(oy) * a.W + ox;
                 const size_t p0 = static_cast<size_t>(b) * HW + static_cast<size_t>(oy) * a.W + ox;
                 conv_tail<COUT, EPI>(a, o, valid, q0, p0, HW);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc_empty + buf);
+            if (!released) acc_release(bar_acc_empty + buf);     // (or no M-tile of this tile fell to this group)
             if (trace) a.dbg_clock[it * 8 + 7] = clock64();
             if (kDebug && a.dbg_clock && blockIdx.x == 0 && it < 32 && warp == 2 + 4 * kFoldEpiGroups && lane == 0)
                 a.dbg_clock[it * 8 + 4] = clock64();      // the last epilogue warp of the CTA
