@@ -119,7 +119,9 @@ int ngan_head_fwd(const void* y_c8, const float* w, const float* bias, float sca
                   int S, void* stream);
 int ngan_head_bwd_pn(const float* gout, const float* w, float scale, const void* y_c8, const float* r, void* ga_c8,
                      void* gy_out_c8, float leak, int B, int C, int S, void* stream);
-int ngan_head_wgrad(const void* t_c8, const float* coeff, float scale, float* gw, int B, int C, int S, void* stream);
+/* gw[c,p] += scale * sum_b coeff[b] * t[b,c,p] (atomics); gb (optional): gb[0] += sum_b coeff[b], the bias gradient */
+int ngan_head_wgrad(const void* t_c8, const float* coeff, float scale, float* gw, float* gb, int B, int C, int S,
+                    void* stream);
 
 /* ---- generator stem: Linear_normalized + Unflatten + LeakyReLU + PixelNorm, models.py:299-311 ---- */
 /* fp32 master [C*S*S][K] -> bf16 operand image [S*S][K/8][C][8] (the C weight rows of one pixel form one

@@ -206,9 +206,10 @@ int ngan_head_bwd_pn(const float* gout, const float* w, float scale, const void*
     NGAN_REQUIRE(gout && w && y && r && ga && !bad_c(C) && B > 0, "head_bwd_pn: bad arguments");
     return head_bwd_pn(gout, w, scale, y, r, ga, gy_out, leak, B, C, Sz, S(stream));
 }
-int ngan_head_wgrad(const void* t, const float* coeff, float scale, float* gw, int B, int C, int Sz, void* stream) {
+int ngan_head_wgrad(const void* t, const float* coeff, float scale, float* gw, float* gb, int B, int C, int Sz,
+                    void* stream) {
     NGAN_REQUIRE(t && coeff && gw && !bad_c(C) && B > 0, "head_wgrad: bad arguments");
-    return head_wgrad(t, coeff, scale, gw, B, C, Sz, S(stream));
+    return head_wgrad(t, coeff, scale, gw, gb, B, C, Sz, S(stream));
 }
 int ngan_prep_linear_weight(const float* w, void* wb, int K, int C, int Sz, void* stream) {
     NGAN_REQUIRE(w && wb && K > 0 && C > 0 && Sz > 0, "prep_linear_weight: bad arguments");

@@ -285,15 +285,22 @@ int pn_bwd_c8(const void* g, int unpool, float gscale, const void* y, const floa
 // Adjoint of the bilinear x2 upsample fused with the PixelNorm/LeakyReLU backward of the layer that fed it.
 // g_up: [B][C/8][2H][2W][8]; y, r, ga at H x W.  extra_pre/extra_w: the faded-out ToImage branch adds
 // extra_w[c] * extra_pre[pixel] to the gradient wrt y (generator transition, models.py:348).
-template <int C>
-__global__ void up2_bwd_pn_bwd_kernel(const uint4* __restrict__ g_up, const uint4* __restrict__ y,
-                                      const float* __restrict__ r, const float* __restrict__ extra_pre,
-                                      const float* __restrict__ extra_w, uint4* __restrict__ ga, float leak, int H,
-                                      int W, size_t total) {
+// One thread per (pixel, 8-channel group); the NCH threads of a pixel are adjacent lanes and combine their partial
+// sums of mean_c(g*y) with xor-shuffles.  (One thread per pixel looping over the groups left the 128-channel,
+// 16x16 launches of the generator's backward with 32 CTAs of serial 256-load threads: 49 us for 1 MB.)
+template <int NCH>
+__global__ void __launch_bounds__(128) up2_bwd_pn_bwd_kernel(const uint4* __restrict__ g_up, const uint4* __restrict__ y,
+                                                             const float* __restrict__ r,
+                                                             const float* __restrict__ extra_pre,
+                                                             const float* __restrict__ extra_w, uint4* __restrict__ ga,
+                                                             float leak, int H, int W, size_t total) {
     pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
-    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    constexpr int NCH = C / 8;
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t pix_id = tid / NCH;
+    const int j = static_cast<int>(tid % NCH);
+    const bool ok = pix_id < total;
+    const size_t i = ok ? pix_id : 0;          // out-of-range lanes still take part in the shuffles
+    constexpr int C = NCH * 8;
     const size_t HW = static_cast<size_t>(H) * W;
     int px, py;
     size_t b;
@@ -304,58 +311,53 @@ __global__ void up2_bwd_pn_bwd_kernel(const uint4* __restrict__ g_up, const uint
         wy[k] = up2_adj_w(2 * py - 1 + k, py, H);
         wx[k] = up2_adj_w(2 * px - 1 + k, px, W);
     }
-    float g[C];
     const size_t UW = 2 * static_cast<size_t>(W), UHW = 4 * HW;
-    const float ep = extra_pre ? extra_pre[i] : 0.f;
+    const uint4* p = g_up + (b * NCH + j) * UHW;
+    const size_t q = (b * NCH + j) * HW + static_cast<size_t>(py) * W + px;
+    const uint4 yq = __ldg(y + q);
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const uint4* p = g_up + (b * NCH + j) * UHW;
+    for (int a = 0; a < 4; ++a) {
+        if (wy[a] == 0.f) continue;
+        const size_t row = static_cast<size_t>(2 * py - 1 + a) * UW;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            if (wy[a] == 0.f) continue;
-            const size_t row = static_cast<size_t>(2 * py - 1 + a) * UW;
+        for (int c = 0; c < 4; ++c) {
+            if (wx[c] == 0.f) continue;
+            float v[8];
+            unpack8(__ldg(p + row + (2 * px - 1 + c)), v);
+            const float w = wy[a] * wx[c];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (wx[c] == 0.f) continue;
-                float v[8];
-                unpack8(__ldg(p + row + (2 * px - 1 + c)), v);
-                const float w = wy[a] * wx[c];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] += w * v[e];
-            }
+            for (int e = 0; e < 8; ++e) g[e] += w * v[e];
         }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) g[j * 8 + e] = acc[e] + (extra_pre ? extra_w[j * 8 + e] * ep : 0.f);
     }
-    const size_t q0 = b * NCH * HW + static_cast<size_t>(py) * W + px;
-    float t = 0.f, yv[8];
+    if (extra_pre) {
+        const float ep = extra_pre[i];
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-        unpack8(__ldg(y + q0 + j * HW), yv);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t += g[j * 8 + e] * yv[e];
+        for (int e = 0; e < 8; ++e) g[e] += __ldg(extra_w + j * 8 + e) * ep;
     }
+    float yv[8], t = 0.f;
+    unpack8(yq, yv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) t += g[e] * yv[e];
+#pragma unroll
+    for (int o = 1; o < NCH; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     t *= 1.0f / C;
     const float rinv = r[i];
+    float o8[8];
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-        unpack8(__ldg(y + q0 + j * HW), yv);
-        float o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = lrelu_mask(yv[e], leak) * rinv * (g[j * 8 + e] - yv[e] * t);
-        ga[q0 + j * HW] = pack8(o);
-    }
+    for (int e = 0; e < 8; ++e) o8[e] = lrelu_mask(yv[e], leak) * rinv * (g[e] - yv[e] * t);
+    if (ok) ga[q] = pack8(o8);
 }
 int up2_bwd_pn_bwd_c8(const void* g_up, const void* y, const float* r, const float* extra_pre, const float* extra_w,
                       void* ga, float leak, int B, int C, int H, int W, cudaStream_t st) {
     const size_t total = static_cast<size_t>(B) * H * W;
-    const int blocks = nblocks(total, 128);
+    const int blocks = nblocks(total * (C / 8), 128);
 #define NGAN_UP2B(CC)                                                                                           \
     case CC:                                                                                                    \
-        up2_bwd_pn_bwd_kernel<CC><<<blocks, 128, 0, st>>>(static_cast<const uint4*>(g_up),                       \
-                                                          static_cast<const uint4*>(y), r, extra_pre, extra_w,  \
-                                                          static_cast<uint4*>(ga), leak, H, W, total);          \
+        up2_bwd_pn_bwd_kernel<CC / 8><<<blocks, 128, 0, st>>>(static_cast<const uint4*>(g_up),                   \
+                                                              static_cast<const uint4*>(y), r, extra_pre,       \
+                                                              extra_w, static_cast<uint4*>(ga), leak, H, W,     \
+                                                              total);                                           \
         break;
     switch (C) {
         NGAN_UP2B(16)
@@ -363,11 +365,11 @@ int up2_bwd_pn_bwd_c8(const void* g_up, const void* y, const float* r, const flo
         NGAN_UP2B(64)
         NGAN_UP2B(128)
         default:
-            set_error("up2_bwd_pn_bwd: unsupported channel count %d", C);
+            set_error("up2_bwd_pn_bwd: unsupported channel count %d (16, 32, 64, 128 are built)", C);
             return NGAN_ERR_UNSUPPORTED;
     }
 #undef NGAN_UP2B
-    return check_launch("up2_bwd_pn_bwd");
+    return check_launch("up2_bwd_pn_bwd_c8");
 }
 
 // ------------------------------------------------------------------------------- 1-channel fp32 image ops
@@ -780,55 +782,82 @@ __global__ void head_fwd_kernel(const uint4* __restrict__ y, const float* __rest
 }
 int head_fwd(const void* y, const float* w, const float* bias, float scale, float* score, int B, int C, int S,
              cudaStream_t st) {
-    head_fwd_kernel<<<B, 256, 0, st>>>(static_cast<const uint4*>(y), w, bias, scale, score, C, S * S);
+    head_fwd_kernel<<<B, 1024, 0, st>>>(static_cast<const uint4*>(y), w, bias, scale, score, C, S * S);
     return check_launch("head_fwd");
 }
 // gy[b,c,p] = scale * w[c,p] * gout[b]; then PixelNorm/LeakyReLU backward of the layer that produced y.
-__global__ void head_bwd_pn_kernel(const float* __restrict__ gout, const float* __restrict__ w, float scale,
-                                   const uint4* __restrict__ y, const float* __restrict__ r, uint4* __restrict__ ga,
-                                   uint4* __restrict__ gy_out, float leak, int C, int HW, size_t total) {
+// One thread per (pixel, 8-channel group), xor-shuffle reduction over the NCH lanes of a pixel (the tensor is only
+// [B][128][16][16]: one thread per pixel meant 32 CTAs of threads that walk 16 groups twice).
+template <int NCH>
+__global__ void __launch_bounds__(128) head_bwd_pn_kernel(const float* __restrict__ gout, const float* __restrict__ w,
+                                                          float scale, const uint4* __restrict__ y,
+                                                          const float* __restrict__ r, uint4* __restrict__ ga,
+                                                          uint4* __restrict__ gy_out, float leak, int HW, size_t total) {
     pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
-    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= total) return;
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t pix_id = tid / NCH;
+    const int j = static_cast<int>(tid % NCH);
+    const bool ok = pix_id < total;
+    const size_t i = ok ? pix_id : 0;
+    constexpr int C = NCH * 8;
     const size_t b = i / HW;
-    const int pix = static_cast<int>(i % HW);
-    const int nch = C / 8;
+    const int pix = static_cast<int>(i - b * HW);
     const float go = scale * gout[b];
-    float t = 0.f;
-    for (int j = 0; j < nch; ++j) {
-        float yv[8];
-        unpack8(__ldg(y + (b * nch + j) * HW + pix), yv);
+    const size_t q = (b * NCH + j) * HW + pix;
+    float yv[8], gv[8], t = 0.f;
+    unpack8(__ldg(y + q), yv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) t += __ldg(w + static_cast<size_t>(j * 8 + e) * HW + pix) * yv[e];
+    for (int e = 0; e < 8; ++e) {
+        gv[e] = go * __ldg(w + static_cast<size_t>(j * 8 + e) * HW + pix);
+        t += gv[e] * yv[e];
     }
-    t *= go / C;
-    const float rinv = r[i];
-    for (int j = 0; j < nch; ++j) {
-        float yv[8], o[8], gv[8];
-        unpack8(__ldg(y + (b * nch + j) * HW + pix), yv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            gv[e] = go * __ldg(w + static_cast<size_t>(j * 8 + e) * HW + pix);
-            o[e] = lrelu_mask(yv[e], leak) * rinv * (gv[e] - yv[e] * t);
-        }
-        ga[(b * nch + j) * HW + pix] = pack8(o);
-        if (gy_out) gy_out[(b * nch + j) * HW + pix] = pack8(gv);
+    for (int o = 1; o < NCH; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    t *= 1.0f / C;
+    const float rinv = r[i];
+    float o8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o8[e] = lrelu_mask(yv[e], leak) * rinv * (gv[e] - yv[e] * t);
+    if (ok) {
+        ga[q] = pack8(o8);
+        if (gy_out) gy_out[q] = pack8(gv);
     }
 }
 int head_bwd_pn(const float* gout, const float* w, float scale, const void* y, const float* r, void* ga,
                 void* gy_out, float leak, int B, int C, int S, cudaStream_t st) {
     const size_t total = static_cast<size_t>(B) * S * S;
-    head_bwd_pn_kernel<<<nblocks(total, 128), 128, 0, st>>>(gout, w, scale, static_cast<const uint4*>(y), r,
-                                                             static_cast<uint4*>(ga), static_cast<uint4*>(gy_out),
-                                                             leak, C, S * S, total);
+    const int blocks = nblocks(total * (C / 8), 128);
+#define NGAN_HBP(N)                                                                                                  \
+    case N:                                                                                                          \
+        head_bwd_pn_kernel<N><<<blocks, 128, 0, st>>>(gout, w, scale, static_cast<const uint4*>(y), r,               \
+                                                      static_cast<uint4*>(ga), static_cast<uint4*>(gy_out), leak,    \
+                                                      S * S, total);                                                 \
+        break;
+    switch (C / 8) {
+        NGAN_HBP(2)
+        NGAN_HBP(4)
+        NGAN_HBP(8)
+        NGAN_HBP(16)
+        default:
+            set_error("head_bwd_pn: unsupported channel count %d (16, 32, 64, 128 are built)", C);
+            return NGAN_ERR_UNSUPPORTED;
+    }
+#undef NGAN_HBP
     return check_launch("head_bwd_pn");
 }
 // gw[c,p] += scale * sum_b coeff[b] * t[b,c,p]: head weight gradient (t = y, coeff = gout) and its double-backward
 // twin (t = cotangent on gy, coeff = gout).
+// Accumulates with atomics: the two halves of the critic step run on concurrent streams and both add to gw.
+// gb (optional): the head bias gradient, gb[0] += sum_b coeff[b].
 __global__ void head_wgrad_kernel(const uint4* __restrict__ t, const float* __restrict__ coeff, float scale,
-                                  float* __restrict__ gw, int B, int C, int HW) {
+                                  float* __restrict__ gw, float* __restrict__ gb, int B, int C, int HW) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int nch = C / 8;
+    if (gb && k == 0) {
+        float sum = 0.f;
+        for (int b = 0; b < B; ++b) sum += coeff[b];
+        atomicAdd(gb, sum);
+    }
     if (k >= nch * HW) return;
     const int j = k / HW, pix = k % HW;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -840,11 +869,12 @@ __global__ void head_wgrad_kernel(const uint4* __restrict__ t, const float* __re
         for (int e = 0; e < 8; ++e) acc[e] += c * tv[e];
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) gw[static_cast<size_t>(j * 8 + e) * HW + pix] += scale * acc[e];
+    for (int e = 0; e < 8; ++e) atomicAdd(gw + static_cast<size_t>(j * 8 + e) * HW + pix, scale * acc[e]);
 }
-int head_wgrad(const void* t, const float* coeff, float scale, float* gw, int B, int C, int S, cudaStream_t st) {
+int head_wgrad(const void* t, const float* coeff, float scale, float* gw, float* gb, int B, int C, int S,
+               cudaStream_t st) {
     const int n = (C / 8) * S * S;
-    head_wgrad_kernel<<<nblocks(n, 128), 128, 0, st>>>(static_cast<const uint4*>(t), coeff, scale, gw, B, C, S * S);
+    head_wgrad_kernel<<<nblocks(n, 128), 128, 0, st>>>(static_cast<const uint4*>(t), coeff, scale, gw, gb, B, C, S * S);
     return check_launch("head_wgrad");
 }
 

@@ -50,7 +50,8 @@ int head_fwd(const void* y, const float* w, const float* bias, float scale, floa
              cudaStream_t st);
 int head_bwd_pn(const float* gout, const float* w, float scale, const void* y, const float* r, void* ga,
                 void* gy_out, float leak, int B, int C, int S, cudaStream_t st);
-int head_wgrad(const void* t, const float* coeff, float scale, float* gw, int B, int C, int S, cudaStream_t st);
+int head_wgrad(const void* t, const float* coeff, float scale, float* gw, float* gb, int B, int C, int S,
+               cudaStream_t st);
 int bias_grad_c8(const void* ga, float* gb, int B, int C, int H, int W, cudaStream_t st);
 int wloss_fwd(const float* s_real, const float* s_fake, float drift, float* out3, float* g_real, float* g_fake,
               float gscale, int B, cudaStream_t st);

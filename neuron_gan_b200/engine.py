@@ -120,12 +120,11 @@ class _Side:
     rr = 0
 
 
-def _wgrad(x, ga, scale, dw):
-    """conv3x3_wgrad on a side stream (dw accumulates with atomics, so concurrent wgrads into one tensor are fine)."""
-    if dw is None:
-        return
+def _on_side(fn, *tensors):
+    """Run fn() -- a parameter-gradient kernel that only accumulates (atomics) into a gradient tensor -- on a side
+    stream, after everything already queued on the current stream; `tensors` are its inputs (kept alive)."""
     if not _Side.enabled:
-        ops.conv3x3_wgrad(x, ga, scale, dw)
+        fn()
         return
     if not _Side.streams:
         _Side.streams = [torch.cuda.Stream() for _ in range(_Side.n_streams)]
@@ -134,9 +133,15 @@ def _wgrad(x, ga, scale, dw):
     side = _Side.streams[i]
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        ops.conv3x3_wgrad(x, ga, scale, dw)
-    _Side.keep.append((x, ga))
+        fn()
+    _Side.keep.append(tensors)
     _Side.used.add(i)
+
+
+def _wgrad(x, ga, scale, dw):
+    """conv3x3_wgrad on a side stream (dw accumulates with atomics, so concurrent wgrads into one tensor are fine)."""
+    if dw is not None:
+        _on_side(lambda: ops.conv3x3_wgrad(x, ga, scale, dw), x, ga)
 
 
 def side_join():
@@ -343,8 +348,8 @@ def d_backward(net, ctx, gout, sink, addins=None, want_gxp=False, record=None):
         ga_l, gy_l = ops.head_bwd_pn(gout, head.weight.detach(), head.scale_value, ctx.yl, ctx.rl, want_gy=rec,
                                      leak=leak)
         if sink is not None:
-            ops.head_wgrad(ctx.yl, gout, head.scale_value, _sink_get(sink, head.weight))
-            _sink_get(sink, head.bias).add_(gout.sum())
+            hw, hb, yl = _sink_get(sink, head.weight), _sink_get(sink, head.bias), ctx.yl
+            _on_side(lambda: ops.head_wgrad(yl, gout, head.scale_value, hw, hb), yl, gout)
     else:
         ga_l, gy_l = ad['last'], None
     if rec:
@@ -353,7 +358,8 @@ def d_backward(net, ctx, gout, sink, addins=None, want_gxp=False, record=None):
         record.stages = {}
     if sink is not None:
         _wgrad(ctx.last_x, ga_l, last.scale_value, _sink_get(sink, last.weight))
-        ops.bias_grad(ga_l, _sink_get(sink, last.bias))
+        lb = _sink_get(sink, last.bias)
+        _on_side(lambda: ops.bias_grad(ga_l, lb), ga_l)
 
     top = ctx.stages[-1]
     if top.kind == 'block':
@@ -455,7 +461,8 @@ def d_double_backward_sweep1(net, ctx, record, ghat_xp, sink):
     last, head = net.last_conv(), net.head_conv()
     _wgrad(cur, record.last.ga, last.scale_value, _sink_get(sink, last.weight))
     gh_l, ah_l = ops.conv3x3_dbl(cur, conv_images(last)[0], last.scale_value, leak, ctx.yl, ctx.rl, record.last.gy)
-    ops.head_wgrad(gh_l, record.gout, head.scale_value, _sink_get(sink, head.weight))
+    hw, rgout = _sink_get(sink, head.weight), record.gout
+    _on_side(lambda: ops.head_wgrad(gh_l, rgout, head.scale_value, hw), gh_l, rgout)
     addins['last'] = ah_l
     return addins
 

@@ -291,9 +291,10 @@ def head_bwd_pn(gout, w, scale, y, r, want_gy=False, leak=0.2):
     return ga, gy
 
 
-def head_wgrad(t, coeff, scale, gw):
+def head_wgrad(t, coeff, scale, gw, gb=None):
+    """gw += scale * sum_b coeff[b] * t[b]; gb (the head's bias gradient, optional) += sum_b coeff[b]."""
     B, C, H, W = c8_dims(t)
-    _lib.call('ngan_head_wgrad', _p(t, BF16), _p(coeff, F32), scale, _p(gw, F32), B, C, H, _stream())
+    _lib.call('ngan_head_wgrad', _p(t, BF16), _p(coeff, F32), scale, _p(gw, F32), _p(gb, F32), B, C, H, _stream())
 
 
 # ------------------------------------------------------------------------------------------ generator stem

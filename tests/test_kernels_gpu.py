@@ -245,9 +245,11 @@ def test_head(B):
     ga, gy = o.head_bwd_pn(gout, w, s, o.nchw_to_c8(y), r[:, 0].contiguous(), want_gy=True)
     assert rel(o.c8_to_nchw(ga), ga_ref) < 8e-3
     assert rel(o.c8_to_nchw(gy), gy_ref) < 4e-3
-    gw = torch.zeros_like(w)
+    gw, ghb = torch.zeros_like(w), torch.full((1,), 0.5, device='cuda')
+    o.head_wgrad(o.nchw_to_c8(y), gout, s, gw, ghb)          # accumulates: gw += ..., bias gradient += sum(gout)
     o.head_wgrad(o.nchw_to_c8(y), gout, s, gw)
-    assert rel(gw, s * (y * gout.view(B, 1, 1, 1)).sum(0, keepdim=True)) < 1e-4
+    assert rel(gw, 2 * s * (y * gout.view(B, 1, 1, 1)).sum(0, keepdim=True)) < 1e-4
+    assert torch.allclose(ghb, 0.5 + gout.sum(), atol=1e-5)
     gb = torch.zeros(C, device='cuda')
     o.bias_grad(o.nchw_to_c8(y), gb)
     assert rel(gb, y.sum((0, 2, 3))) < 1e-4
