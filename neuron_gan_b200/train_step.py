@@ -41,6 +41,8 @@ class TrainStep:
             data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.dp = data_parallel
         self.use_graph = use_graph
+        self.segment_graphs = False     # capture three graphs even on one GPU (lets a caller time the three parts)
+        self.segment_events = None      # when a list: 4 CUDA events per replayed iteration are appended (start, D, G, end)
         self.fork_chains = True         # run the two independent halves of the critic step on two streams
         self._chain_stream = None
         self._bound = {}
@@ -202,7 +204,7 @@ class TrainStep:
         n0 = _lib.launch_count
         pool = None
         segs = [self._seg_d, self._seg_g, self._seg_end]
-        if not self.dp:          # single GPU: the whole iteration is one graph
+        if not self.dp and not self.segment_graphs:          # single GPU: the whole iteration is one graph
             segs = [lambda b: (self._seg_d(b), self._seg_g(b), self._seg_end(b))[-1]]
         for seg in segs:         # data parallel: the two gradient all-reduces sit between three graphs
             g = torch.cuda.CUDAGraph()
@@ -244,11 +246,22 @@ class TrainStep:
         if len(ent.graphs) == 1:
             ent.graphs[0].replay()
         else:
+            ev = None
+            if self.segment_events is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                self.segment_events.append(ev)
+                ev[0].record()
             ent.graphs[0].replay()
             self._allreduce(ent.flats[0])
+            if ev:
+                ev[1].record()
             ent.graphs[1].replay()
             self._allreduce(ent.flats[1])
+            if ev:
+                ev[2].record()
             ent.graphs[2].replay()
+            if ev:
+                ev[3].record()
         self._last_key = key
         self.launches_per_step = ent.launches
         _lib.launch_count += ent.launches
