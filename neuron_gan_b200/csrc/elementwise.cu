@@ -553,67 +553,96 @@ int d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const flo
 
 // Backward of FromImage: with G = gscale * g[(y,x) or (y/2,x/2)]:
 //   gw[c] += sum G_c * xp,  gb[c] += sum G_c,  g_img[b,p] (+)= sum_c w_c * G_c
-constexpr int kFromPix = 4;  // pixels per thread
-__global__ void fromim_bwd_kernel(const uint4* __restrict__ g, int unpool, float gscale, const float* __restrict__ xp,
-                                  const float* __restrict__ w, float* __restrict__ gw, float* __restrict__ gb,
-                                  float* __restrict__ g_img, int accumulate, int C, int H, int W, size_t total) {
-    extern __shared__ float sacc[];  // [2*C]: gw then gb
-    for (int k = threadIdx.x; k < 2 * C; k += blockDim.x) sacc[k] = 0.f;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
+// Thread layout of the two 1x1-conv backward kernels below: a block of 128 threads = (128 / NCH) pixel lanes x NCH
+// channel groups, the NCH threads of a pixel being adjacent lanes.  Each thread walks many pixels (grid-stride) and
+// keeps the per-channel sums of its group (weight / bias gradient) in registers; per pixel, sums over all channels
+// go through xor-shuffles over the NCH lanes; the per-channel sums meet once per block in shared memory, then one
+// global atomic per channel per block.  (Warp-reducing 8 values per group per pixel, as before, made these
+// kernels shuffle-bound at 512x512 and left the 128-channel 16x16 launches at 36-49 us for 1 MB.)
+constexpr int kPixPerThread = 8;
+template <int NCH>
+__global__ void __launch_bounds__(128) fromim_bwd_kernel(const uint4* __restrict__ g, int unpool, float gscale,
+                                                         const float* __restrict__ xp, const float* __restrict__ w,
+                                                         float* __restrict__ gw, float* __restrict__ gb,
+                                                         float* __restrict__ g_img, int accumulate, int H, int W,
+                                                         size_t total) {
+    constexpr int PL = 128 / NCH, C = NCH * 8;
+    __shared__ float red[2][PL][C];
+    const int pl = threadIdx.x / NCH, j = threadIdx.x % NCH;
     const size_t HW = static_cast<size_t>(H) * W;
     const size_t gHW = unpool ? HW / 4 : HW;
-    const int nch = C / 8;
-    size_t pix[kFromPix], gq[kFromPix];
-    float xv[kFromPix], img[kFromPix];
-    bool ok[kFromPix];
+    float wj[8], sw[8], sb[8];
 #pragma unroll
-    for (int p = 0; p < kFromPix; ++p) {
-        const size_t i = (static_cast<size_t>(blockIdx.x) * kFromPix + p) * blockDim.x + threadIdx.x;
-        ok[p] = i < total;
-        pix[p] = ok[p] ? i : 0;
+    for (int e = 0; e < 8; ++e) {
+        wj[e] = __ldg(w + j * 8 + e);
+        sw[e] = sb[e] = 0.f;
+    }
+    const size_t stride = static_cast<size_t>(gridDim.x) * PL;
+    const size_t n_iter = (total + stride - 1) / stride;        // the same trip count for every thread (shuffles inside)
+    for (size_t k = 0; k < n_iter; ++k) {
+        const size_t i = k * stride + static_cast<size_t>(blockIdx.x) * PL + pl;
+        const bool ok = i < total;
+        const size_t ii = ok ? i : 0;
         int px, py;
         size_t b;
-        split_xyb(pix[p], W, H, px, py, b);
-        gq[p] = unpool ? b * nch * gHW + static_cast<size_t>(py >> 1) * (W >> 1) + (px >> 1)
-                       : b * nch * HW + static_cast<size_t>(py) * W + px;
-        xv[p] = ok[p] ? xp[pix[p]] : 0.f;
-        img[p] = 0.f;
-    }
-    for (int j = 0; j < nch; ++j) {
-        float sw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        split_xyb(ii, W, H, px, py, b);
+        const size_t gq = unpool ? (b * NCH + j) * gHW + static_cast<size_t>(py >> 1) * (W >> 1) + (px >> 1)
+                                 : (b * NCH + j) * HW + static_cast<size_t>(py) * W + px;
+        float gv[8];
+        unpack8(ok ? __ldg(g + gq) : make_uint4(0, 0, 0, 0), gv);
+        const float xv = ok ? __ldg(xp + ii) : 0.f;
+        float im = 0.f;
 #pragma unroll
-        for (int p = 0; p < kFromPix; ++p) {
-            if (!ok[p]) continue;
-            float gv[8];
-            unpack8(__ldg(g + gq[p] + j * gHW), gv);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float G = gscale * gv[e];
-                sw[e] += G * xv[p];
-                sb[e] += G;
-                img[p] += __ldg(w + j * 8 + e) * G;
-            }
+        for (int e = 0; e < 8; ++e) {
+            const float G = gscale * gv[e];
+            sw[e] = fmaf(G, xv, sw[e]);
+            sb[e] += G;
+            im = fmaf(wj[e], G, im);
         }
-        warp_accum8(sw, sacc + j * 8, lane);
-        warp_accum8(sb, sacc + C + j * 8, lane);
-    }
-    if (g_img) {
 #pragma unroll
-        for (int p = 0; p < kFromPix; ++p)
-            if (ok[p]) g_img[pix[p]] = (accumulate ? g_img[pix[p]] : 0.f) + img[p];
+        for (int o = 1; o < NCH; o <<= 1) im += __shfl_xor_sync(0xffffffffu, im, o);
+        if (g_img && ok && j == 0) g_img[ii] = (accumulate ? g_img[ii] : 0.f) + im;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        red[0][pl][j * 8 + e] = sw[e];
+        red[1][pl][j * 8 + e] = sb[e];
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < C; k += blockDim.x) {
-        if (gw) atomicAdd(gw + k, sacc[k]);
-        if (gb) atomicAdd(gb + k, sacc[C + k]);
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+        const int which = c / C, cc = c - which * C;
+        float* dst = which ? gb : gw;
+        if (!dst) continue;
+        float v = 0.f;
+#pragma unroll 4
+        for (int q = 0; q < PL; ++q) v += red[which][q][cc];
+        atomicAdd(dst + cc, v);
     }
+}
+static int pointwise_blocks(size_t total, int pixel_lanes) {
+    size_t blocks = (total + static_cast<size_t>(pixel_lanes) * kPixPerThread - 1) / (static_cast<size_t>(pixel_lanes) * kPixPerThread);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    return static_cast<int>(blocks);
 }
 int fromim_bwd(const void* g, int unpool, float gscale, const float* xp, const float* w, float* gw, float* gb,
                float* g_img, int g_img_accumulate, int B, int C, int H, int W, cudaStream_t st) {
     const size_t total = static_cast<size_t>(B) * H * W;
-    fromim_bwd_kernel<<<nblocks(total, 128 * kFromPix), 128, 2 * C * sizeof(float), st>>>(
-        static_cast<const uint4*>(g), unpool, gscale, xp, w, gw, gb, g_img, g_img_accumulate, C, H, W, total);
+#define NGAN_FIB(N)                                                                                                  \
+    case N:                                                                                                          \
+        fromim_bwd_kernel<N><<<pointwise_blocks(total, 128 / N), 128, 0, st>>>(                                      \
+            static_cast<const uint4*>(g), unpool, gscale, xp, w, gw, gb, g_img, g_img_accumulate, H, W, total);     \
+        break;
+    switch (C / 8) {
+        NGAN_FIB(2)
+        NGAN_FIB(4)
+        NGAN_FIB(8)
+        NGAN_FIB(16)
+        default:
+            set_error("fromim_bwd: unsupported channel count %d (16, 32, 64, 128 are built)", C);
+            return NGAN_ERR_UNSUPPORTED;
+    }
+#undef NGAN_FIB
     return check_launch("fromim_bwd");
 }
 // Double backward of FromImage's input-gradient: first order was g_xp = sum_c w_c * G_c.  With cotangent
@@ -686,72 +715,84 @@ int toim_fwd(const void* y, const float* w, float* img, int B, int C, int H, int
 }
 // Backward of tanh(conv1x1(y)): gpre = gscale*g_img*(1-img^2); gw[c] += sum gpre*y_c; gy_c = w_c*gpre, then
 // (if ga != null) the PixelNorm/LeakyReLU backward of the layer that produced y.
-constexpr int kToPix = 4;  // pixels per thread: the per-channel weight-gradient sums are warp-reduced once per 4 pixels
-__global__ void toim_bwd_kernel(const float* __restrict__ g_img, float gscale, const float* __restrict__ img,
-                                const uint4* __restrict__ y, const float* __restrict__ r, const float* __restrict__ w,
-                                uint4* __restrict__ ga, float* __restrict__ gpre_out, float* __restrict__ gw,
-                                float leak, int C, size_t HW, size_t total) {
+// (thread layout: see fromim_bwd_kernel)
+template <int NCH>
+__global__ void __launch_bounds__(128) toim_bwd_kernel(const float* __restrict__ g_img, float gscale,
+                                                       const float* __restrict__ img, const uint4* __restrict__ y,
+                                                       const float* __restrict__ r, const float* __restrict__ w,
+                                                       uint4* __restrict__ ga, float* __restrict__ gpre_out,
+                                                       float* __restrict__ gw, float leak, size_t HW, size_t total) {
     pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
-    extern __shared__ float sacc[];  // [C]
-    for (int k = threadIdx.x; k < C; k += blockDim.x) sacc[k] = 0.f;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int nch = C / 8;
-    size_t ii[kToPix], q0[kToPix];
-    float gpre[kToPix], t[kToPix];
-    bool ok[kToPix];
+    constexpr int PL = 128 / NCH, C = NCH * 8;
+    __shared__ float red[PL][C];
+    const int pl = threadIdx.x / NCH, j = threadIdx.x % NCH;
+    float wj[8], sw[8];
 #pragma unroll
-    for (int p = 0; p < kToPix; ++p) {
-        const size_t i = (static_cast<size_t>(blockIdx.x) * kToPix + p) * blockDim.x + threadIdx.x;
-        ok[p] = i < total;
-        ii[p] = ok[p] ? i : 0;
+    for (int e = 0; e < 8; ++e) {
+        wj[e] = __ldg(w + j * 8 + e);
+        sw[e] = 0.f;
+    }
+    const size_t stride = static_cast<size_t>(gridDim.x) * PL;
+    const size_t n_iter = (total + stride - 1) / stride;
+    for (size_t k = 0; k < n_iter; ++k) {
+        const size_t i = k * stride + static_cast<size_t>(blockIdx.x) * PL + pl;
+        const bool ok = i < total;
+        const size_t ii = ok ? i : 0;
         size_t b, pix;
-        split_bpix(ii[p], HW, b, pix);
-        q0[p] = b * nch * HW + pix;
-        const float im = img[ii[p]];
-        gpre[p] = ok[p] ? gscale * g_img[ii[p]] * (1.f - im * im) : 0.f;
-        if (ok[p] && gpre_out) gpre_out[ii[p]] = gpre[p];
-        t[p] = 0.f;
-    }
-    for (int j = 0; j < nch; ++j) {
-        float sw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        split_bpix(ii, HW, b, pix);
+        const size_t q = (b * NCH + j) * HW + pix;
+        const float im = __ldg(img + ii);
+        const float gpre = ok ? gscale * __ldg(g_img + ii) * (1.f - im * im) : 0.f;
+        if (gpre_out && ok && j == 0) gpre_out[ii] = gpre;
+        float yv[8], t = 0.f;
+        unpack8(__ldg(y + q), yv);
 #pragma unroll
-        for (int p = 0; p < kToPix; ++p) {
-            float yv[8];
-            unpack8(__ldg(y + q0[p] + j * HW), yv);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                sw[e] += gpre[p] * yv[e];
-                t[p] += __ldg(w + j * 8 + e) * yv[e];
-            }
+        for (int e = 0; e < 8; ++e) {
+            sw[e] = fmaf(gpre, yv[e], sw[e]);
+            t = fmaf(wj[e], yv[e], t);
         }
-        if (gw) warp_accum8(sw, sacc + j * 8, lane);
-    }
-    if (ga) {
+        if (ga) {
 #pragma unroll
-        for (int p = 0; p < kToPix; ++p) {
-            if (!ok[p]) continue;
-            const float tp = t[p] * gpre[p] / C;
-            const float rinv = r[ii[p]];
-            for (int j = 0; j < nch; ++j) {
-                float yv[8], o[8];
-                unpack8(__ldg(y + q0[p] + j * HW), yv);
+            for (int o = 1; o < NCH; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            const float tp = t * gpre * (1.0f / C);
+            const float rinv = __ldg(r + ii);
+            float o8[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    o[e] = lrelu_mask(yv[e], leak) * rinv * (__ldg(w + j * 8 + e) * gpre[p] - yv[e] * tp);
-                ga[q0[p] + j * HW] = pack8(o);
-            }
+            for (int e = 0; e < 8; ++e) o8[e] = lrelu_mask(yv[e], leak) * rinv * (wj[e] * gpre - yv[e] * tp);
+            if (ok) ga[q] = pack8(o8);
         }
     }
-    __syncthreads();
-    if (gw)
-        for (int k = threadIdx.x; k < C; k += blockDim.x) atomicAdd(gw + k, sacc[k]);
+    if (gw) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) red[pl][j * 8 + e] = sw[e];
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float v = 0.f;
+#pragma unroll 4
+            for (int q = 0; q < PL; ++q) v += red[q][c];
+            atomicAdd(gw + c, v);
+        }
+    }
 }
 int toim_bwd(const float* g_img, float gscale, const float* img, const void* y, const float* r, const float* w,
              void* ga, float* gpre, float* gw, float leak, int B, int C, int H, int W, cudaStream_t st) {
     const size_t HW = static_cast<size_t>(H) * W, total = B * HW;
-    toim_bwd_kernel<<<nblocks(total, 128 * kToPix), 128, C * sizeof(float), st>>>(
-        g_img, gscale, img, static_cast<const uint4*>(y), r, w, static_cast<uint4*>(ga), gpre, gw, leak, C, HW, total);
+#define NGAN_TIB(N)                                                                                                 \
+    case N:                                                                                                         \
+        toim_bwd_kernel<N><<<pointwise_blocks(total, 128 / N), 128, 0, st>>>(                                       \
+            g_img, gscale, img, static_cast<const uint4*>(y), r, w, static_cast<uint4*>(ga), gpre, gw, leak, HW,    \
+            total);                                                                                                 \
+        break;
+    switch (C / 8) {
+        NGAN_TIB(2)
+        NGAN_TIB(4)
+        NGAN_TIB(8)
+        NGAN_TIB(16)
+        default:
+            set_error("toim_bwd: unsupported channel count %d (16, 32, 64, 128 are built)", C);
+            return NGAN_ERR_UNSUPPORTED;
+    }
+#undef NGAN_TIB
     return check_launch("toim_bwd");
 }
 
