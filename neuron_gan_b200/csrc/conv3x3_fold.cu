@@ -514,6 +514,9 @@ static int launch_fold(const CUtensorMap& tmap, const ConvArgs& a, uint32_t smem
         case EPI_BWD_PN: return launch_fold<CI, CO, EPI_BWD_PN, K>(tmap, a, smem_bytes, n_ctas, st);      \
         case EPI_DBL: return launch_fold<CI, CO, EPI_DBL, K>(tmap, a, smem_bytes, n_ctas, st);            \
     }
+// The one-MMA-per-tap variant (NKX = 1) was measured and rejected (profiles/README.md); it is only built with
+// -DNGAN_BUILD_NKX1 (then NGAN_FOLD_NKX=1 selects it at run time).
+#ifdef NGAN_BUILD_NKX1
 #define NGAN_FOLD_CASE(CI, CO)              \
     if (cin == CI && cout == CO) {          \
         if (nkx == 3) {                     \
@@ -522,12 +525,22 @@ static int launch_fold(const CUtensorMap& tmap, const ConvArgs& a, uint32_t smem
             NGAN_FOLD_CASE_K(CI, CO, 1)     \
         }                                   \
     }
+#else
+#define NGAN_FOLD_CASE(CI, CO)              \
+    if (cin == CI && cout == CO) {          \
+        NGAN_FOLD_CASE_K(CI, CO, 3)         \
+    }
+#endif
 
 int conv3x3_fold_dispatch(int epi, const void* x, ConvArgs a, int B, int cin, int cout, int H, int W,
                           cudaStream_t st) {
     // NKX: 3 = horizontal taps folded into N, 1 = one MMA per tap (see the kernel comment)
+#ifdef NGAN_BUILD_NKX1
     static const int nkx_env = getenv("NGAN_FOLD_NKX") ? atoi(getenv("NGAN_FOLD_NKX")) : 3;
     const int nkx = nkx_env == 1 ? 1 : 3;
+#else
+    const int nkx = 3;
+#endif
     const int NF = nkx == 3 ? 3 * cout : cout;         // accumulator columns per M-tile
     // M-tiles (4 tile rows each) per CTA tile: at least two accumulator buffers of nMT*NF columns in 512 columns
     static const int nmt_env = getenv("NGAN_FOLD_NMT") ? atoi(getenv("NGAN_FOLD_NMT")) : 0;   // tuning experiments
