@@ -49,3 +49,42 @@ def test_small_architecture_iteration():
     for name, key in dkm.items():
         if d_grads[key] is not None:
             assert torch.allclose(d_grads[key], tr.last_d_grads[name], rtol=1e-3, atol=1e-7), name
+
+
+def test_pth_interchange_with_the_reference_classes(tmp_path):
+    """Checkpoint layout (reference utils.py:142-223): a .pth written by this package's Checkpointer loads through
+    the UNMODIFIED reference's from_state_dict / Checkpointer, and one written by the reference loads here -- same
+    keys (also mid-transition, where the reference renumbers them), same tensors, same attrs."""
+    import os
+    from neuron_gan_b200 import models as my_models, utils as my_utils
+    ref_models, _, ref_utils = rh.load()
+    f = [128, 64, 32, 32, 16, 16]
+    for res, alpha in ((64, 0.5), (128, 1.0)):
+        # ours -> reference
+        torch.manual_seed(3)
+        G = my_models.Generator_PG(list(f), image_size_init=16)
+        D = my_models.Discriminator_PG(list(reversed(f)), image_size_init=16)
+        G.set_resolution(res, alpha)
+        D.set_resolution(res, alpha)
+        path = os.path.join(tmp_path, f'mine_{res}.pth')
+        my_utils.Checkpointer(G, D, 1e-4, path, N_epochs=4, verbose=False).save_state(2)
+        Gr = ref_models.Generator_PG.from_state_dict(path, verbose=False)
+        Dr = ref_models.Discriminator_PG.from_state_dict(path, verbose=False)
+        assert Gr.image_size == res and abs(float(Gr.alpha) - alpha) < 1e-7
+        for net, ref in ((G, Gr), (D, Dr)):
+            mine, theirs = net.state_dict(), ref.state_dict()
+            assert list(mine.keys()) == list(theirs.keys())
+            for k in mine:
+                assert torch.equal(mine[k].cpu(), theirs[k].cpu()), k
+        # reference -> ours
+        Gr2, Dr2 = rh.build_nets(res, alpha, seed=4)
+        path2 = os.path.join(tmp_path, f'ref_{res}.pth')
+        ref_utils.Checkpointer(Gr2, Dr2, 1e-4, path2, N_epochs=4, verbose=False).save_state(1)
+        G2 = my_models.Generator_PG.from_state_dict(path2, verbose=False)
+        D2 = my_models.Discriminator_PG.from_state_dict(path2, verbose=False)
+        for net, ref in ((G2, Gr2), (D2, Dr2)):
+            mine, theirs = net.state_dict(), ref.state_dict()
+            assert list(mine.keys()) == list(theirs.keys())
+            for k in mine:
+                assert torch.equal(mine[k].cpu(), theirs[k].cpu()), k
+        assert G2.saved_attrs == Gr2.saved_attrs and D2.saved_attrs == Dr2.saved_attrs
