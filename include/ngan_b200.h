@@ -131,8 +131,9 @@ int ngan_prep_linear_weight(const float* w, void* w_img, int K, int C, int S, vo
 long long ngan_linear_fwd_workspace_bytes(int B, int K);
 int ngan_linear_fwd(const float* z, const void* w_img, float scale, float leak, void* y_c8, float* r, void* workspace,
                     int B, int K, int C, int S, void* stream);
-int ngan_linear_wgrad(const void* ga_c8, const float* z, float scale, float* dw, int B, int K, int C, int S,
-                      void* stream);
+/* dW[f][k] (+)= scale * sum_b ga[b][f] * z[b][k]; accumulate == 0 overwrites dW (no read, no prior zeroing needed) */
+int ngan_linear_wgrad(const void* ga_c8, const float* z, float scale, float* dw, int accumulate, int B, int K, int C,
+                      int S, void* stream);
 
 /* ---- WGAN-GP loss reductions, loss_functions.py:14-47, 59-74, 157-180 ---- */
 /* out3 = {D_loss, score_real, score_fake}; g_real/g_fake = d(gscale*D_loss)/d(score) per sample */

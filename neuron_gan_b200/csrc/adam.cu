@@ -39,15 +39,52 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
     const float inv_bc2_sqrt = t.dyn ? __ldg(t.dyn + 1) : t.inv_bc2_sqrt;
     const long long n4 = t.n >> 2;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+#define NGAN_ADAM1(c)                                                      \
+    m.c = m.c + (1.f - beta1) * (g.c - m.c);                               \
+    v.c = beta2 * v.c + (1.f - beta2) * g.c * g.c;                         \
+    p.c = p.c - step_size * (m.c / (sqrtf(v.c) * inv_bc2_sqrt + eps));
+    if (t.shadow && t.shadow_kind == 1 && (t.shadow_c & 1) == 0) {
+        // The linear weight [C*SS][K] with its operand image [SS][K/8][C][8]: one thread updates the 8 k's of two
+        // channels c, c+1 of one pixel -- rows f and f + SS of the master, 32 contiguous bytes each -- and writes
+        // their two adjacent 16-byte granules of the image as one full 32-byte sector (4-element threads wrote
+        // quarter sectors: +27 % traffic on the 16.8 M-parameter tensor).
+        const int K = t.shadow_k, C = t.shadow_c, SS = t.shadow_ss, KG = K >> 3;
+        const long long items = static_cast<long long>(C / 2) * SS * KG;
+        for (long long it = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; it < items; it += stride) {
+            const int kg = static_cast<int>(it % KG);
+            const long long rest = it / KG;
+            const int px = static_cast<int>(rest % SS), cp = static_cast<int>(rest / SS);
+            uint4 img[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const long long i = ((static_cast<long long>(2 * cp + h) * SS + px) * K + kg * 8) >> 2;   // float4 index
+                uint32_t packed[4];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float4 p = reinterpret_cast<float4*>(t.p)[i + q];
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(t.g) + i + q);
+                    float4 m = reinterpret_cast<float4*>(t.m)[i + q];
+                    float4 v = reinterpret_cast<float4*>(t.v)[i + q];
+                    NGAN_ADAM1(x) NGAN_ADAM1(y) NGAN_ADAM1(z) NGAN_ADAM1(w)
+                    reinterpret_cast<float4*>(t.p)[i + q] = p;
+                    reinterpret_cast<float4*>(t.m)[i + q] = m;
+                    reinterpret_cast<float4*>(t.v)[i + q] = v;
+                    packed[2 * q] = pack_bf16(p.x, p.y);
+                    packed[2 * q + 1] = pack_bf16(p.z, p.w);
+                }
+                img[h] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(t.shadow) + (static_cast<long long>(px) * KG + kg) * C + 2 * cp;
+            dst[0] = img[0];
+            dst[1] = img[1];
+        }
+        return;
+    }
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 p = reinterpret_cast<float4*>(t.p)[i];
         const float4 g = __ldg(reinterpret_cast<const float4*>(t.g) + i);
         float4 m = reinterpret_cast<float4*>(t.m)[i];
         float4 v = reinterpret_cast<float4*>(t.v)[i];
-#define NGAN_ADAM1(c)                                                      \
-    m.c = m.c + (1.f - beta1) * (g.c - m.c);                               \
-    v.c = beta2 * v.c + (1.f - beta2) * g.c * g.c;                         \
-    p.c = p.c - step_size * (m.c / (sqrtf(v.c) * inv_bc2_sqrt + eps));
         NGAN_ADAM1(x) NGAN_ADAM1(y) NGAN_ADAM1(z) NGAN_ADAM1(w)
         reinterpret_cast<float4*>(t.p)[i] = p;
         reinterpret_cast<float4*>(t.m)[i] = m;

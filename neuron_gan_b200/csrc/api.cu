@@ -223,10 +223,10 @@ int ngan_linear_fwd(const float* z, const void* wb, float scale, float leak, voi
     NGAN_REQUIRE(z && wb && y && workspace && B > 0, "linear_fwd: bad arguments");
     return linear_fwd_pn(z, wb, scale, leak, y, r, workspace, B, K, C, Sz, S(stream));
 }
-int ngan_linear_wgrad(const void* ga, const float* z, float scale, float* dw, int B, int K, int C, int Sz,
-                      void* stream) {
+int ngan_linear_wgrad(const void* ga, const float* z, float scale, float* dw, int accumulate, int B, int K, int C,
+                      int Sz, void* stream) {
     NGAN_REQUIRE(ga && z && dw && B > 0, "linear_wgrad: bad arguments");
-    return linear_wgrad(ga, z, scale, dw, B, K, C, Sz, S(stream));
+    return linear_wgrad(ga, z, scale, dw, accumulate, B, K, C, Sz, S(stream));
 }
 int ngan_wloss(const float* s_real, const float* s_fake, float drift, float* out3, float* g_real, float* g_fake,
                float gscale, int B, void* stream) {

@@ -66,7 +66,7 @@ int scale_rows_f32(const float* x, const float* coeff, float scale, float* out, 
 int prep_linear_weight(const float* w, void* wb, int K, int C, int S, cudaStream_t st);
 int linear_fwd_pn(const float* z, const void* wb, float scale, float leak, void* y, float* r, void* workspace, int B,
                   int K, int C, int S, cudaStream_t st);
-int linear_wgrad(const void* ga, const float* z, float scale, float* dw, int B, int K, int C, int S,
+int linear_wgrad(const void* ga, const float* z, float scale, float* dw, int accumulate, int B, int K, int C, int S,
                  cudaStream_t st);
 
 // adam.cu (AdamEntry has the layout of ngan_adam_tensor in include/ngan_b200.h)

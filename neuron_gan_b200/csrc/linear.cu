@@ -220,12 +220,13 @@ int linear_fwd_pn(const float* z, const void* wb, float scale, float leak, void*
     return launch_linear<512, 256>(zp, wb, scale, leak, y, r, B, Bpad, S * S, st);
 }
 
-// dW[f][k] += scale * sum_b ga[b][f] * z[b][k], f = c*S*S + p; ga is C8 [B][C/8][S*S][8].
+// dW[f][k] (+)= scale * sum_b ga[b][f] * z[b][k], f = c*S*S + p; ga is C8 [B][C/8][S*S][8].  With accumulate == 0
+// the 67 MB gradient is written without being read (and the caller need not zero it first).
 // One block per C8 granule (8 rows of dW that share p), 128 threads x 4 consecutive k.
 template <int K>
 __global__ void __launch_bounds__(K / 4) linear_wgrad_kernel(const uint4* __restrict__ ga, const float* __restrict__ z,
-                                                             float scale, float* __restrict__ dw, int B, int C,
-                                                             int SS) {
+                                                             float scale, float* __restrict__ dw, int accumulate,
+                                                             int B, int C, int SS) {
     __shared__ float sg[64][8];
     const int p = blockIdx.x, j = blockIdx.y;
     const int nch = C / 8;
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(K / 4) linear_wgrad_kernel(const uint4* __rest
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         float4* d = reinterpret_cast<float4*>(dw + (static_cast<size_t>(j * 8 + e) * SS + p) * K) + threadIdx.x;
-        float4 o = *d;
+        float4 o = accumulate ? *d : make_float4(0.f, 0.f, 0.f, 0.f);
         o.x += scale * acc[e][0];
         o.y += scale * acc[e][1];
         o.z += scale * acc[e][2];
@@ -267,14 +268,15 @@ __global__ void __launch_bounds__(K / 4) linear_wgrad_kernel(const uint4* __rest
         *d = o;
     }
 }
-int linear_wgrad(const void* ga, const float* z, float scale, float* dw, int B, int K, int C, int S,
+int linear_wgrad(const void* ga, const float* z, float scale, float* dw, int accumulate, int B, int K, int C, int S,
                  cudaStream_t st) {
     if (K != 512 || C % 8) {
         set_error("linear_wgrad: only latent_dim 512 and C %% 8 == 0 are built (got K=%d C=%d)", K, C);
         return NGAN_ERR_UNSUPPORTED;
     }
     dim3 grid(S * S, C / 8);
-    linear_wgrad_kernel<512><<<grid, 128, 0, st>>>(static_cast<const uint4*>(ga), z, scale, dw, B, C, S * S);
+    linear_wgrad_kernel<512><<<grid, 128, 0, st>>>(static_cast<const uint4*>(ga), z, scale, dw, accumulate, B, C,
+                                                   S * S);
     return check_launch("linear_wgrad");
 }
 

@@ -251,8 +251,9 @@ def _g_block_bwd(rec, ga2, y_prev, r_prev, leak, sink, extra_pre=None, extra_w=N
     return ops.up2_bwd_pn_bwd(g_up, y_prev, r_prev, extra_pre, extra_w, leak)
 
 
-def g_backward(net, ctx, g_img, sink):
-    """Gradient of the generator parameters given d loss / d image ([B, R, R] fp32)."""
+def g_backward(net, ctx, g_img, sink, linear_overwrite=False):
+    """Gradient of the generator parameters given d loss / d image ([B, R, R] fp32).  linear_overwrite: the Linear
+    weight's gradient (98 % of the parameters) is stored, not accumulated -- its part of the sink need not be zeroed."""
     leak = net.LeakyReLU_neg_slope
     alpha = ctx.alpha
     g_img = g_img.detach().to(F32).contiguous()
@@ -274,7 +275,7 @@ def g_backward(net, ctx, g_img, sink):
     lin, conv0 = net.layers[0], net.layers[4]
     _wgrad(ctx.y0, ga, conv0.scale_value, _sink_get(sink, conv0.weight))
     ga0, _ = ops.conv3x3_dgrad_pn(ga, conv_images(conv0)[1], conv0.scale_value, leak, ctx.y0, ctx.r0)
-    ops.linear_wgrad(ga0, ctx.z, lin.scale_value, _sink_get(sink, lin.weight))
+    ops.linear_wgrad(ga0, ctx.z, lin.scale_value, _sink_get(sink, lin.weight), accumulate=not linear_overwrite)
 
 
 # ---------------------------------------------------------------------------------------------------------

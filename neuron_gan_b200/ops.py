@@ -321,9 +321,10 @@ def linear_fwd(z, w_img, scale, leak, C, S, want_r=True):
     return y, r
 
 
-def linear_wgrad(ga, z, scale, dw):
+def linear_wgrad(ga, z, scale, dw, accumulate=True):
     B, C, S, _ = c8_dims(ga)
-    _lib.call('ngan_linear_wgrad', _p(ga, BF16), _p(z, F32), scale, _p(dw, F32), B, z.shape[1], C, S, _stream())
+    _lib.call('ngan_linear_wgrad', _p(ga, BF16), _p(z, F32), scale, _p(dw, F32), int(accumulate), B, z.shape[1], C, S,
+              _stream())
 
 
 # ------------------------------------------------------------------------------------------ losses

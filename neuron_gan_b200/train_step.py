@@ -69,7 +69,9 @@ class TrainStep:
                 p.grad = v
                 sink[id(p)] = v
                 off += p.numel()
-            ent = {'key': key, 'flat': flat, 'sink': sink}
+            # `small`: everything but a trailing big tensor (the Linear weight), whose gradient is overwritten
+            big = sum(p.numel() for p in active if p.numel() > (1 << 22))
+            ent = {'key': key, 'flat': flat, 'sink': sink, 'small': flat[:n - big] if big else flat}
             self._bound[id(net)] = ent
         return ent['flat'], ent['sink']
 
@@ -154,14 +156,14 @@ class TrainStep:
         G, D = self.G, self.D
         self.opt_d.launch()
         flat_g, sink_g = self._bind(G)
-        flat_g.zero_()
+        self._bound[id(G)]['small'].zero_()           # the Linear weight's 67 MB gradient is overwritten instead
         fake, gctx = engine.g_forward(G, buf.z3, save=True)
         s_fake, dctx = engine.d_forward(D, fake, save=True)
         buf.out.out1, g_fake = ops.gloss(s_fake)
         g_xp = engine.d_backward(D, dctx, g_fake, None, want_gxp=True)
         gx = ops.unpool_image(g_xp, 0.25) if dctx.pooled else g_xp
         del dctx
-        engine.g_backward(G, gctx, gx, sink_g)
+        engine.g_backward(G, gctx, gx, sink_g, linear_overwrite=True)
         del gctx
         engine.side_join()
         return flat_g

@@ -358,7 +358,8 @@ def test_host_input_path_equals_device_input_path():
                 draws = tuple(t.to(DEV) for t in step.draw_host(B))
                 stats.append(step(h.to(DEV), draws).cpu())
         out.append(torch.stack(stats))
-    # fp32 atomics order is the only difference between the runs: tight for the first iterations; later ones
-    # (graph replays in both runs) only loosely, the two trajectories drift apart through Adam's sign-like updates
-    assert torch.allclose(out[0][:2], out[1][:2], rtol=1e-4, atol=2e-5), (out[0][:2], out[1][:2])
+    # fp32 atomics order is the only difference between the runs: tight for the first iteration; later ones only
+    # loosely -- after an Adam step (sign-like: a ~0 gradient element whose last bits differ moves its weight by
+    # +-lr) the two trajectories drift apart at the 1e-4 level
+    assert torch.allclose(out[0][0], out[1][0], rtol=1e-5, atol=2e-6), (out[0][0], out[1][0])
     assert torch.allclose(out[0], out[1], rtol=1e-2, atol=5e-3), (out[0], out[1])
