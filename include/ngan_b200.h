@@ -15,6 +15,10 @@
  *    channels); C must be a multiple of 16 for the conv kernels.  Images, scores, PixelNorm scales `r`
  *    ([B][H][W]) and all parameters / gradients are fp32 in the reference's (torch) layouts.
  *  - parameter-gradient outputs (gw, gb, dw, what) ACCUMULATE (+=); the caller zeroes them once per step.
+ *  - the conv kernels are launched with the programmatic-stream-serialization attribute: their prologue may overlap
+ *    the tail of the previous kernel in the stream, their first global-memory access waits for it
+ *    (griddepcontrol.wait), so stream order is preserved for any caller; NGAN_NO_PDL=1 in the environment disables it.
+ *  - ngan_adam_multi takes at most 48 tensors per call.
  *  - LeakyReLU + PixelNorm always come as a pair after a conv (models.py:261-268); "pn_bwd" below means
  *    ga = mask(y) * r * (g - y * mean_c(g*y)), the gradient wrt the conv's pre-activation, computed from the
  *    saved PixelNorm output y and scale r = (mean_c(h^2) + 1e-8)^-1/2 (models.py:118, 126).

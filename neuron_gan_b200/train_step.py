@@ -32,7 +32,7 @@ class TrainStep:
     launch kernel by kernel.  Captured or not, the kernels and their order are identical."""
 
     def __init__(self, generator_net, discriminator_net, learning_rate=1e-4, beta1=0.5, grad_pen_lambda=10.0,
-                 drift_epsilon=1e-3, data_parallel=None, use_graph=None):
+                 drift_epsilon=1e-3, data_parallel=None, use_graph=None, n_critic=1):
         self.G, self.D = generator_net, discriminator_net
         self.lam, self.drift = float(grad_pen_lambda), float(drift_epsilon)
         self.opt_g = FusedAdam(self.G.parameters(), lr=learning_rate, betas=(beta1, 0.999), capturable=True)
@@ -41,6 +41,7 @@ class TrainStep:
             data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.dp = data_parallel
         self.use_graph = use_graph
+        self.n_critic = int(n_critic)   # critic steps per generator step (train.py:356; > 1 runs kernel by kernel)
         self.segment_graphs = False     # capture three graphs even on one GPU (lets a caller time the three parts)
         self.segment_events = None      # when a list: 4 CUDA events per replayed iteration are appended (start, D, G, end)
         self.fork_chains = True         # run the two independent halves of the critic step on two streams
@@ -151,10 +152,11 @@ class TrainStep:
         engine.side_join()
         return flat_d
 
-    def _seg_g(self, buf):
+    def _seg_g(self, buf, adam_d=True):
         """Adam(D) (train.py:366), then the generator step up to complete gradients (train.py:375-384)"""
         G, D = self.G, self.D
-        self.opt_d.launch()
+        if adam_d:
+            self.opt_d.launch()
         flat_g, sink_g = self._bind(G)
         self._bound[id(G)]['small'].zero_()           # the Linear weight's 67 MB gradient is overwritten instead
         fake, gctx = engine.g_forward(G, buf.z3, save=True)
@@ -188,6 +190,32 @@ class TrainStep:
         self.opt_g.advance()
         self._allreduce(self._seg_d(buf))
         self._allreduce(self._seg_g(buf))
+        return self._seg_end(buf)
+
+    def _run_multi_critic(self, images, draws, dev):
+        """n_critic > 1 (train.py:356-366): every critic step takes the same images and fresh draws (z, z, eps);
+        the statistics are those of the last critic step, as in the reference.  draws: None, or a list of n_critic
+        (z1, z2, eps) tuples followed by one z3."""
+        B, R = images.shape[0], images.shape[-1]
+        buf = self._buffers(B, R, dev)
+        self._bind(self.D)
+        self._bind(self.G)
+        for j in range(self.n_critic):
+            if draws is None:
+                z1 = sample_latent_vec((B, self.G.latent_dim))
+                z2 = sample_latent_vec((B, self.G.latent_dim))
+                eps = torch.rand((B, 1, 1, 1))
+            else:
+                z1, z2, eps = draws[j]
+            self._load(buf, images, z1, z2, eps, z1)          # (z3 slot: overwritten below)
+            self.opt_d.advance()
+            self._allreduce(self._seg_d(buf))
+            self.opt_d.launch()
+        z3 = sample_latent_vec((B, self.G.latent_dim)) if draws is None else draws[self.n_critic]
+        buf.z3.copy_(z3.to(dev) if not z3.is_cuda else z3)
+        self.opt_g.advance()
+        self._allreduce(self._seg_g(buf, adam_d=False))
+        self._versions_seen = None
         return self._seg_end(buf)
 
     # -- CUDA-graph capture ----------------------------------------------------------------------------------
@@ -226,6 +254,8 @@ class TrainStep:
         """images: [B, 1, R, R] fp32 (this rank's shard; GPU tensor, or pinned host tensor).  Returns a device tensor
         [D_loss, score_real, score_fake, G_loss, D_grad_pen] (D_loss includes the penalty, train.py:362)."""
         dev = next(self.G.parameters()).device
+        if self.n_critic != 1:
+            return self._run_multi_critic(images, draws, dev)
         B, R = images.shape[0], images.shape[-1]
         z1, z2, eps, z3 = draws if draws is not None else self.draw_host(B)
         key = self._config_key(B, R)

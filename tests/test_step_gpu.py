@@ -363,3 +363,44 @@ def test_host_input_path_equals_device_input_path():
     # +-lr) the two trajectories drift apart at the 1e-4 level
     assert torch.allclose(out[0][0], out[1][0], rtol=1e-5, atol=2e-6), (out[0][0], out[1][0])
     assert torch.allclose(out[0], out[1], rtol=1e-2, atol=5e-3), (out[0], out[1])
+
+
+def test_two_critic_steps_per_generator_step():
+    """n_critic = 2 (train.py:356): TrainStep == the reference's call pattern on these modules -- two rounds of
+    D_W_loss + D_grad_pen_loss + backward + Adam(D) with fresh draws, then G_W_loss + backward + Adam(G)."""
+    from neuron_gan_b200.loss_functions import D_W_loss, D_grad_pen_loss, G_W_loss
+    from neuron_gan_b200.optim import FusedAdam
+    from neuron_gan_b200.train_step import TrainStep
+    res, alpha, B = 32, 0.5, 4
+    x = O.synthetic_images(B, res, seed=61).to(DEV)
+    critic_draws = [(O.sample_latent((B, 512)), O.sample_latent((B, 512)), torch.rand((B, 1, 1, 1))) for _ in range(2)]
+    z3 = O.sample_latent((B, 512))
+    G1, D1 = nets(res, alpha)
+    stats = TrainStep.stats_dict(TrainStep(G1, D1, n_critic=2)(x, critic_draws + [z3]).cpu())
+    G2, D2 = nets(res, alpha)
+    opt_d = FusedAdam(D2.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    opt_g = FusedAdam(G2.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    from neuron_gan_b200 import autograd_fns
+    for z1, z2, eps in critic_draws:
+        D2.zero_grad()
+        with torch.no_grad():
+            fake = G2(z1.to(DEV))
+            x_tilde = G2(z2.to(DEV))
+        s_real, s_fake = D2(x), D2(fake)
+        d_loss = -s_real.mean() + s_fake.mean() + 1e-3 * (s_real ** 2).mean()
+        e = eps.to(DEV)
+        pen = autograd_fns.gradient_penalty(D2, e * x + (1 - e) * x_tilde, 10.0)
+        (d_loss + pen).backward()
+        opt_d.step()
+    G2.zero_grad()
+    g_loss = -D2(G2(z3.to(DEV))).mean()
+    g_loss.backward()
+    opt_g.step()
+    got = {'D_loss': (d_loss + pen).item(), 'score_real': s_real.mean().item(), 'score_fake': s_fake.mean().item(),
+           'G_loss': g_loss.item(), 'D_grad_pen': pen.item()}
+    for k in stats:
+        assert abs(got[k] - stats[k]) <= 2e-3 * max(1, abs(stats[k])), (k, got[k], stats[k])
+    for n1, n2 in ((D1, D2), (G1, G2)):
+        for (k, a), (_, b) in zip(n1.state_dict().items(), n2.state_dict().items()):
+            d = (a.float() - b.float()).abs()
+            assert d.max().item() <= 4.2e-4 and d.mean().item() < 1e-5, (k, d.max().item(), d.mean().item())
