@@ -232,17 +232,29 @@ class TrainStep:
         ent = SimpleNamespace(buf=buf, graphs=[], flats=[], stats=None, launches=0)
         torch.cuda.synchronize()
         n0 = _lib.launch_count
-        pool = None
-        segs = [self._seg_d, self._seg_g, self._seg_end]
-        if not self.dp and not self.segment_graphs:          # single GPU: the whole iteration is one graph
-            segs = [lambda b: (self._seg_d(b), self._seg_g(b), self._seg_end(b))[-1]]
-        for seg in segs:         # data parallel: the two gradient all-reduces sit between three graphs
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
-                res = seg(buf)
-            pool = g.pool()
-            ent.graphs.append(g)
-            ent.flats.append(res)
+        def whole(b):      # single GPU: the whole iteration is one graph
+            self._seg_d(b)
+            self._seg_g(b)
+            return self._seg_end(b)
+
+        def capture(segs):
+            pool, graphs, outs = None, [], []
+            for seg in segs:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    outs.append(seg(buf))
+                pool = g.pool()
+                graphs.append(g)
+            return graphs, outs
+
+        # With data parallelism: three graphs, the two all-reduces issued by the host in between.  (Capturing the NCCL
+        # calls into one graph was measured: same iteration time at 2 GPUs, and the process then hung in
+        # destroy_process_group -- not worth it.)
+        three = [self._seg_d, self._seg_g, self._seg_end]
+        if self.dp or self.segment_graphs:
+            ent.graphs, ent.flats = capture(three)
+        else:
+            ent.graphs, ent.flats = capture([whole])
         ent.stats = ent.flats[-1]
         ent.launches = _lib.launch_count - n0
         _lib.launch_count = n0          # captured, not launched
