@@ -28,6 +28,7 @@ struct WgradArgs {
     int ci_g, co_g;       // channels of x / ga handled by one CTA
     int n_ci_groups;
     int n_stage;          // depth of the TMA ring (2..kWgMaxStages)
+    int debug;            // timing experiments (NGAN_WGRAD_DEBUG): 1 = skip the flush, 2 = skip the MMAs
     uint32_t x_stage_bytes, g_stage_bytes;
     float scale;
     float* dw;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
         // B (x):  matrix mi -> pixels +(mi%2)*8, ci plane 2*cib + (mi/2)
         const uint32_t b_lane = xb + (2 * cib + (mi >> 1)) * x_plane + ((mi & 1) * 8 + rowi) * 16;
 
-        for (int r = rs; r < kWgTH; r += rsplit) {
+        for (int r = rs; r < ((a.debug & 2) ? 0 : kWgTH); r += rsplit) {
             for (int w0 = 0; w0 < a.TW; w0 += 16) {
                 uint32_t a0, a1, a2, a3;
                 ldmatrix_x4_trans(a_lane + (r * a.TW + w0) * 16, a0, a1, a2, a3);
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
     // are CAS loops), the CTA then sums the row-split slices of each output and issues one global atomic per
     // output.  Slices are laid out like the gradient tensor itself ([co][ci][tap], tap fastest), so the atomics
     // of a warp run over contiguous addresses: 144 consecutive floats per (block, co) row.
+    if (a.debug & 1) return;
     float* s_red = reinterpret_cast<float*>(smem);   // [8 warps = rsplit x n_blk][16 co][16 ci][9 taps]
     const int g = lane >> 2, t = lane & 3;
     __syncthreads();
@@ -213,6 +215,8 @@ int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int B, 
     if (n_stage > kWgMaxStages) n_stage = kWgMaxStages;
     if (n_stage < 2) n_stage = 2;
     a.n_stage = n_stage;
+    static const int dbg = getenv("NGAN_WGRAD_DEBUG") ? atoi(getenv("NGAN_WGRAD_DEBUG")) : 0;
+    a.debug = dbg;
     const uint32_t stage_total = n_stage * (a.x_stage_bytes + a.g_stage_bytes) + kWgMaxStages * 8;
     const uint32_t red_bytes = 8u * 2304 * sizeof(float);   // flush slices (one per warp) alias the operand slots
     const uint32_t smem_bytes = (stage_total > red_bytes ? stage_total : red_bytes) + 128;
