@@ -29,6 +29,7 @@ struct WgradArgs {
     int n_ci_groups;
     int n_stage;          // depth of the TMA ring (2..kWgMaxStages)
     int debug;            // timing experiments (NGAN_WGRAD_DEBUG): 1 = skip the flush, 2 = skip the MMAs
+    int cluster;          // CTAs per cluster along grid.x (1, 2, 4 or 8): cluster-level reduction before the atomics
     uint32_t x_stage_bytes, g_stage_bytes;
     float scale;
     float* dw;
@@ -50,6 +51,23 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a
         "%2, %3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// ---- thread-block cluster helpers (distributed shared memory)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_saddr, uint32_t rank) {
+    uint32_t ra;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
 }
 
 __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x,
@@ -155,7 +173,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
     float* s_red = reinterpret_cast<float*>(smem);   // [8 warps = rsplit x n_blk][16 co][16 ci][9 taps]
     const int g = lane >> 2, t = lane & 3;
     __syncthreads();
-    if (it > 0) {
+    {                                                 // (zeros when this CTA had no tile: its cluster still reads them)
         float* mine = s_red + warp * 2304;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap)
@@ -169,17 +187,48 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
                 }
     }
     __syncthreads();
-    if (it > 0) {
-        for (int i = threadIdx.x; i < n_blk * 2304; i += blockDim.x) {
+    const int n_out = n_blk * 2304;
+    auto to_global = [&](int i, float v) {
+        const int b = i / 2304, rem = i - b * 2304;
+        const int co = rem / 144, j = rem - co * 144;        // j = ci * 9 + tap
+        const int co_abs = co_group * a.co_g + (b / n_ci_blk) * 16 + co;
+        const int ci0 = ci_group * a.ci_g + (b % n_ci_blk) * 16;
+        atomicAdd(a.dw + (static_cast<size_t>(co_abs) * a.cin + ci0) * 9 + j, a.scale * v);
+    };
+    if (a.cluster == 1) {
+        if (it > 0) {
+            for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
+                const int b = i / 2304, rem = i - b * 2304;
+                float v = 0.f;
+                for (int r = 0; r < rsplit; ++r) v += s_red[(r * n_blk + b) * 2304 + rem];     // warp = rs * n_blk + blk
+                to_global(i, v);
+            }
+        }
+        return;
+    }
+    // Cluster of a.cluster CTAs along the pixel dimension (same channel group, same output addresses): every CTA
+    // first folds its row-split slices into the compact array s_red[0 .. n_out), then CTA q of the cluster sums slice
+    // q of the outputs over all CTAs through distributed shared memory and issues those atomics: a.cluster times fewer
+    // global atomics (they, not the MMAs, are what the low-resolution launches of this kernel cost).
+    if (rsplit > 1) {
+        for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
             const int b = i / 2304, rem = i - b * 2304;
             float v = 0.f;
-            for (int r = 0; r < rsplit; ++r) v += s_red[(r * n_blk + b) * 2304 + rem];     // warp = rs * n_blk + blk
-            const int co = rem / 144, j = rem - co * 144;        // j = ci * 9 + tap
-            const int co_abs = co_group * a.co_g + (b / n_ci_blk) * 16 + co;
-            const int ci0 = ci_group * a.ci_g + (b % n_ci_blk) * 16;
-            atomicAdd(a.dw + (static_cast<size_t>(co_abs) * a.cin + ci0) * 9 + j, a.scale * v);
+            for (int r = 0; r < rsplit; ++r) v += s_red[(r * n_blk + b) * 2304 + rem];
+            s_red[i] = v;          // slice (r = 0, b) starts at b * 2304: only this thread touches element (b, rem)
         }
     }
+    cluster_sync();
+    const int per = n_out / a.cluster;
+    const uint32_t q = cluster_ctarank();
+    const uint32_t base = smem_u32(s_red);
+    for (int k = threadIdx.x; k < per; k += blockDim.x) {
+        const int i = static_cast<int>(q) * per + k;
+        float v = 0.f;
+        for (int rk = 0; rk < a.cluster; ++rk) v += ld_dsmem_f32(base + i * 4, rk);
+        to_global(i, v);
+    }
+    cluster_sync();               // nobody leaves while a neighbour may still read its shared memory
 }
 
 int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int B, int cin, int cout, int H, int W,
@@ -243,7 +292,28 @@ int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int B, 
     int per_group = target / n_groups;
     if (per_group > a.n_tiles) per_group = a.n_tiles;
     if (per_group < 1) per_group = 1;
-    conv3x3_wgrad_kernel<<<dim3(per_group, n_groups), 256, smem_bytes, st>>>(tmx, tmg, a);
+    // Clusters (measured, graph-timed): 4 CTAs help the 16x16 / 32x32 layers, whose launches are all flush
+    // (21 -> 15 us); from 64x64 up the co-scheduling constraint costs more than the saved atomics (512x512: 56 -> 95 us).
+    static const int cluster_env = getenv("NGAN_WGRAD_CLUSTER") ? atoi(getenv("NGAN_WGRAD_CLUSTER")) : -1;
+    const int cluster_max = cluster_env >= 0 ? cluster_env : (H <= 32 ? 4 : 1);
+    int cs = 1;
+    while (cs * 2 <= cluster_max && cs * 2 <= 8 && cs * 2 <= per_group) cs *= 2;
+    per_group = per_group / cs * cs;
+    a.cluster = cs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(per_group, n_groups);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cs > 1 ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv3x3_wgrad_kernel, tmx, tmg, a);
+    if (le != cudaSuccess) return check_cuda(le, "cudaLaunchKernelEx(conv3x3_wgrad)");
     return check_launch("conv3x3_wgrad");
 }
 
