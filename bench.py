@@ -32,8 +32,8 @@ METRIC = 'train images/sec (D+G WGAN-GP step)'
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--res', type=int, default=512)
     ap.add_argument('--alpha', type=float, default=1.0)
@@ -103,7 +103,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
-                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          '-lms', '20', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -207,16 +207,17 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled (nvidia-smi, every 20 ms) from before the warm-up to the end of the
+    # end-to-end loop; the samples between the start of the timed region and the end of the e2e loop are reported
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     # at least 3 untimed iterations: the second sight of a configuration captures its CUDA graph, replays start at 3
     for i in range(max(args.warmup, 3)):
         step(devx[i % n_pool], draws[i % n_pool])
     barrier()
 
     # ---- device-resident throughput
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
     mem0 = torch.cuda.max_memory_allocated()
     launches0 = _lib.launch_count
     barrier()
@@ -231,7 +232,6 @@ def run_b200(args):
     ms = e0.elapsed_time(e1) / args.steps
     launches = (_lib.launch_count - launches0) // args.steps
     graph_replay = bool(step._graphs)
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
     last_stats = TrainStep.stats_dict(stats.cpu())
     TrainStep.check_nan(list(stats.cpu()))
 
@@ -267,6 +267,7 @@ def run_b200(args):
     run_e2e(args.steps)
     f1.record()
     barrier()
+    clocks = sampler.stop(t0, time.perf_counter()) if rank == 0 else None
     ms_e2e = f0.elapsed_time(f1) / args.steps
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
