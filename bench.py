@@ -242,7 +242,8 @@ def run_b200(args):
     h2d = B * res * res * 4 + 3 * B * 512 * 4 + B * 4
     stat_bufs = [torch.empty(5, dtype=torch.float32).pin_memory() for _ in range(2)]
     n_e2e = [0]
-    loader = DevicePrefetcher(lambda: (host[j % n_pool] for j in range(n_e2e[0])), dev)
+    loader = DevicePrefetcher(lambda: (host[j % n_pool] for j in range(n_e2e[0])), dev,
+                              gate=lambda: step.inputs_loaded)
 
     def run_e2e(n):
         n_e2e[0] = n

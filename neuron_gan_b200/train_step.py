@@ -52,6 +52,8 @@ class TrainStep:
         self._last_key = None
         self._versions_seen = None
         self.launches_per_step = 0      # kernels of libngan_b200.so launched (or replayed) by the last iteration
+        self.inputs_loaded = None       # CUDA event: this iteration's host-to-device copies (images, draws, Adam scalars)
+                                        # are done -- a loader may start its next big copy behind it (DevicePrefetcher)
 
     # -- flat gradient buffers ---------------------------------------------------------------------------
     def _bind(self, net):
@@ -287,6 +289,8 @@ class TrainStep:
         self._load(ent.buf, images, z1, z2, eps, z3)
         self.opt_d.advance()
         self.opt_g.advance()
+        self.inputs_loaded = torch.cuda.Event()
+        self.inputs_loaded.record()
         if len(ent.graphs) == 1:
             ent.graphs[0].replay()
         else:
