@@ -140,7 +140,7 @@ def test_autograd_api_equals_train_step(res, alpha, batch):
     for n1, n2 in ((D1, D2), (G1, G2)):
         for (k, a), (_, b) in zip(n1.state_dict().items(), n2.state_dict().items()):
             d = (a.float() - b.float()).abs()
-            assert d.max().item() <= 2.1e-4 and d.mean().item() < 2e-6, (k, d.max().item(), d.mean().item())
+            assert d.max().item() <= 2.3e-4 and d.mean().item() < 6e-6, (k, d.max().item(), d.mean().item())
 
 
 @pytest.mark.parametrize('res,alpha', [(16, 1.0), (32, 0.5), (64, 0.5), (64, 1.0)])
