@@ -20,7 +20,7 @@ if [ -n "$NGAN_VARIANT" ]; then      # tuning variants: NGAN_VARIANT=name NGAN_E
 fi
 mkdir -p $BUILD
 pids=()
-for f in api conv3x3_umma conv3x3_fold wgrad elementwise linear adam; do
+for f in api conv3x3_umma conv3x3_fold wgrad elementwise linear adam augment; do
   ( $NVCC $FLAGS -c $f.cu -o $BUILD/$f.o > $BUILD/$f.log 2>&1 || { cat $BUILD/$f.log; exit 1; } ) &
   pids+=($!)
 done

@@ -387,3 +387,20 @@ def adam_multi(entries, beta1, beta2, eps):
         arr[i].shadow_k, arr[i].shadow_c, arr[i].shadow_ss = e.get('shadow_dims') or (0, 0, 0)
         arr[i].shadow_kind = e.get('shadow_kind', 1 if e.get('shadow_dims') else 0)
     _lib.call('ngan_adam_multi', ctypes.cast(arr, ctypes.c_void_p), n, beta1, beta2, eps, _stream())
+
+
+# ------------------------------------------------------------------------------------------ image pipeline
+def augment_batch(canvases, src_index, params, tap_first, tap_count, tap_weight, out, crop, workspace=None):
+    """canvases [N, P, P] f32, src_index [b] i32, params [b, 16] f32, taps for crop -> R, out [b, 1, R, R] f32
+    (data/NeuronDataset.py:170-205 for one whole batch; see ngan_augment_batch in include/ngan_b200.h)."""
+    b, R = out.shape[0], out.shape[-1]
+    N, P, P2 = canvases.shape
+    assert P == P2 and out.shape == (b, 1, R, R) and params.shape == (b, 16) and src_index.shape == (b,)
+    assert tap_first.shape == (R,) and tap_count.shape == (R,) and tap_weight.shape[0] == R
+    need = _lib.call('ngan_augment_workspace_bytes', b, P)
+    if workspace is None or workspace.numel() * 4 < need:
+        workspace = torch.empty((need + 3) // 4, dtype=F32, device=out.device)
+    _lib.call('ngan_augment_batch', _p(canvases, F32), _p(src_index, torch.int32), _p(params, F32),
+              _p(tap_first, torch.int32), _p(tap_count, torch.int32), _p(tap_weight, F32), tap_weight.shape[1],
+              _p(workspace, F32), _p(out, F32), b, P, crop, R, _stream())
+    return out
