@@ -175,7 +175,7 @@ int ngan_adam_multi(const ngan_adam_tensor* tensors, int n_tensors, float beta1,
 /* ---- on-device image pipeline: DatasetIterator.__next__ (data/NeuronDataset.py:170-205) applying the transform
  * list of NeuronDataset.__init__ / set_image_size (data/NeuronDataset.py:112-126, 149-164) to a whole batch:
  * RandomAffine(nearest, fill 0) -> RandomVerticalFlip -> ColorJitter(brightness, contrast) -> CenterCrop(crop) ->
- * Renormalize((-1,1),(0,1)) -> Resize(out_size, antialias=True).  Two launches, nothing intermediate in HBM.
+ * Renormalize((-1,1),(0,1)) -> Resize(out_size, antialias=True).  Three launches.
  *   canvases  [n_images][canvas][canvas] fp32 in [0,1]: the preloaded padded images (dataset.images), resident
  *   src_index [batch] which canvas each output row is made from
  *   params    [batch][16] fp32, drawn by the host in the reference's RNG order:
@@ -184,8 +184,10 @@ int ngan_adam_multi(const ngan_adam_tensor* tensors, int n_tensors, float beta1,
  *             10 order (0: brightness then contrast, 1: contrast then brightness)  11 identity (no augmentation)
  *   tap_first/tap_count [out_size], tap_weight [out_size][max_taps]: the antialias filter of ATen's
  *             _compute_indices_weights_aa for crop -> out_size (one entry of weight 1 per index when out_size == crop)
- *   workspace ngan_augment_workspace_bytes(batch, canvas) bytes;  out [batch][1][out_size][out_size] fp32 */
-long long ngan_augment_workspace_bytes(int batch, int canvas);
+ *   workspace ngan_augment_workspace_bytes(batch, canvas, crop) bytes, 16-byte aligned (partial sums for the
+ *             per-image mean that adjust_contrast needs, and the resampled crop window of every image);
+ *              out [batch][1][out_size][out_size] fp32 */
+long long ngan_augment_workspace_bytes(int batch, int canvas, int crop);
 int ngan_augment_batch(const float* canvases, const int* src_index, const float* params, const int* tap_first,
                        const int* tap_count, const float* tap_weight, int max_taps, float* workspace, float* out,
                        int batch, int canvas, int crop, int out_size, void* stream);

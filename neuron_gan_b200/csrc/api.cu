@@ -253,16 +253,16 @@ int ngan_adam_multi(const ngan_adam_tensor* tensors, int n_tensors, float beta1,
 }
 
 /* ---- on-device image pipeline (data/NeuronDataset.py:170-205) ---- */
-long long ngan_augment_workspace_bytes(int batch, int canvas) {
-    return static_cast<long long>(augment_workspace_bytes(batch, canvas));
+long long ngan_augment_workspace_bytes(int batch, int canvas, int crop) {
+    return static_cast<long long>(augment_workspace_bytes(batch, canvas, crop));
 }
 int ngan_augment_batch(const float* canvases, const int* src_index, const float* params, const int* tap_first,
                        const int* tap_count, const float* tap_weight, int max_taps, float* workspace, float* out,
                        int batch, int canvas, int crop, int out_size, void* stream) {
     NGAN_REQUIRE(canvases && src_index && params && tap_first && tap_count && tap_weight && workspace && out,
                  "augment_batch: null pointer");
-    NGAN_REQUIRE(batch > 0 && batch <= 65535 && canvas > 0 && crop > 0 && crop <= canvas && out_size > 0 &&
-                     out_size <= crop && max_taps > 0,
+    NGAN_REQUIRE(batch > 0 && batch <= 65535 && canvas > 0 && canvas <= 32768 && crop > 0 && crop <= canvas &&
+                     out_size > 0 && out_size <= crop && max_taps > 0,
                  "augment_batch: bad sizes");
     return augment_batch(canvases, src_index, params, tap_first, tap_count, tap_weight, max_taps, workspace, out,
                          batch, canvas, crop, out_size, S(stream));

@@ -74,7 +74,7 @@ struct AdamEntry;
 int adam_multi_launch(const AdamEntry* entries, int n_tensors, float beta1, float beta2, float eps, cudaStream_t st);
 
 // augment.cu
-size_t augment_workspace_bytes(int batch, int canvas);
+size_t augment_workspace_bytes(int batch, int canvas, int crop);
 int augment_batch(const float* canvases, const int* src_index, const float* params, const int* tap_first,
                   const int* tap_count, const float* tap_weight, int max_taps, float* workspace, float* out, int batch,
                   int canvas, int crop, int out_size, cudaStream_t st);

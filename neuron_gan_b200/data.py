@@ -1,7 +1,7 @@
 """The reference's on-device image pipeline (`config.image_preprocessing = 'device'`, train.py:149-154) behind
 the reference's own names: a dataset object holding the preloaded padded canvases with `image_size`,
 `image_size_max`, `set_image_size()` (data/NeuronDataset.py:149-164), and `DatasetIterator(dataset, batch_size,
-device)` (data/NeuronDataset.py:170-205) whose batches are produced by two CUDA launches (csrc/augment.cu) instead
+device)` (data/NeuronDataset.py:170-205) whose batches are produced by three CUDA launches (csrc/augment.cu) instead
 of six torchvision transforms per image.
 
 Same results for the same torch seed: the random parameters are drawn here, on the host, with the same CPU-generator
@@ -77,7 +77,12 @@ def aa_taps(in_size: int, out_size: int):
         total = np.float32(0.0)
         for j in range(n):
             total = np.float32(total + w[j])
-        rows.append(w / total)
+        w = w / total
+        while n > 1 and w[n - 1] == 0.0:          # taps of weight exactly 0 (e.g. in == out: [1, 0]) cost work only
+            n -= 1
+        while n > 1 and w[0] == 0.0:
+            w, lo, n = w[1:], lo + 1, n - 1
+        rows.append(w[:n])
         first[i], count[i] = lo, n
     weight = np.zeros((out_size, int(count.max())), dtype=np.float32)
     for i, w in enumerate(rows):
@@ -187,7 +192,7 @@ class DatasetIterator:
         self._index[:m].copy_(host_i[lo:hi], non_blocking=True)
         self._ring_f.release(kf)
         self._ring_i.release(ki)
-        need = ops._lib.call('ngan_augment_workspace_bytes', m, P)
+        need = ops._lib.call('ngan_augment_workspace_bytes', m, P, ds.image_size_max)
         if self._workspace is None or self._workspace.numel() * 4 < need:
             self._workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
         out = self.images_tensor[:m]

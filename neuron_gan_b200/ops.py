@@ -397,7 +397,7 @@ def augment_batch(canvases, src_index, params, tap_first, tap_count, tap_weight,
     N, P, P2 = canvases.shape
     assert P == P2 and out.shape == (b, 1, R, R) and params.shape == (b, 16) and src_index.shape == (b,)
     assert tap_first.shape == (R,) and tap_count.shape == (R,) and tap_weight.shape[0] == R
-    need = _lib.call('ngan_augment_workspace_bytes', b, P)
+    need = _lib.call('ngan_augment_workspace_bytes', b, P, crop)
     if workspace is None or workspace.numel() * 4 < need:
         workspace = torch.empty((need + 3) // 4, dtype=F32, device=out.device)
     _lib.call('ngan_augment_batch', _p(canvases, F32), _p(src_index, torch.int32), _p(params, F32),

@@ -79,9 +79,14 @@ def test_antialias_taps(sizes):
     n_in, n_out = sizes
     first, count, weight = data.aa_taps(n_in, n_out)
     for i, (lo, w) in enumerate(do.aa_weights(n_in, n_out)):
-        assert first[i] == lo and count[i] == len(w)
-        assert np.abs(weight[i, :len(w)] - w).max() < 1e-6
-        assert weight[i, len(w):].sum() == 0
+        dense = np.zeros(n_in, dtype=np.float32)            # the product drops taps of weight exactly 0
+        dense[first[i]:first[i] + count[i]] = weight[i, :count[i]]
+        want = np.zeros(n_in, dtype=np.float32)
+        want[lo:lo + len(w)] = w
+        assert np.abs(dense - want).max() < 1e-6
+        assert weight[i, count[i]:].sum() == 0
+    if n_in == n_out:
+        assert (count == 1).all() and (first == np.arange(n_in)).all() and (weight == 1).all()
     x = torch.rand(1, 1, n_in, n_in, generator=torch.Generator().manual_seed(n_in + n_out))
     want = torch.nn.functional.interpolate(x, size=[n_out, n_out], mode='bilinear', align_corners=False,
                                            antialias=True)[0, 0].numpy()
