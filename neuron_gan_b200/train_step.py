@@ -177,6 +177,7 @@ class TrainStep:
         self.opt_g.launch()
         stats = torch.empty(5, dtype=F32, device=buf.z3.device)
         ops.pack_stats(buf.out.out3, buf.out.out1, buf.out.pen, stats)
+        self._last_critic_out = (buf.out.out3, buf.out.pen)
         return stats
 
     def _run_eager(self, buf):
@@ -213,6 +214,13 @@ class TrainStep:
             self.opt_d.advance()
             self._allreduce(self._seg_d(buf))
             self.opt_d.launch()
+            self._last_critic_out = (buf.out.out3, buf.out.pen)
+        if self.n_critic == 0:
+            # adapt_critic can ask for no critic step (train.py:336-340 with N_min = 0): the reference then reports
+            # the critic statistics of the last iteration that had one (its Python variables are simply not updated)
+            if getattr(self, '_last_critic_out', None) is None:
+                raise RuntimeError('n_critic = 0 before any critic step has run: no critic statistics to report')
+            buf.out.out3, buf.out.pen = (t.clone() for t in self._last_critic_out)
         z3 = sample_latent_vec((B, self.G.latent_dim)) if draws is None else draws[self.n_critic]
         buf.z3.copy_(z3.to(dev) if not z3.is_cuda else z3)
         self.opt_g.advance()

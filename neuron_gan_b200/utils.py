@@ -141,6 +141,19 @@ def save_vars(variables: dict, directory='./saved_vars', verbose=True):
     return path
 
 
+def Calculate_D_steps(Loss_real, Loss_fake, N_min, N_max, Period):
+    """`adapt_critic` (reference utils.py:105-120, called at train.py:336-338): critic steps for the next epoch,
+    round(N_max * std(real scores) / mean|fake - real|) over the last `Period` iterations, clipped to [N_min, N_max];
+    N_max while the series are still empty.  Assign the result to `TrainStep.n_critic` between iterations."""
+    if not (Loss_real and Loss_fake):
+        return N_max
+    real = np.asarray(Loss_real[-Period:])
+    fake = np.asarray(Loss_fake[-Period:])
+    spread = np.std(real)
+    gap = np.mean(np.abs(fake - real))
+    return int(max(min(np.round(spread / gap * N_max), N_max), N_min))
+
+
 # ----------------------------------------------------------------------------------------------- testing
 def gen_samples(Generator: nn.Module, N_images=16, seed=None, chunk=256):
     """Generator-only inference (reference utils.py:346-355), chunked so 4096 samples at 512x512 fit."""

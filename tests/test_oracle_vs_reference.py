@@ -88,3 +88,19 @@ def test_pth_interchange_with_the_reference_classes(tmp_path):
             for k in mine:
                 assert torch.equal(mine[k].cpu(), theirs[k].cpu()), k
         assert G2.saved_attrs == Gr2.saved_attrs and D2.saved_attrs == Dr2.saved_attrs
+
+
+def test_adaptive_critic_steps_match_the_reference():
+    """utils.Calculate_D_steps (reference utils.py:105-120) on random score series, incl. the empty-series case."""
+    import numpy as np
+    from neuron_gan_b200 import utils as my_utils
+    _, _, ref_utils = rh.load()
+    assert my_utils.Calculate_D_steps([], [], 0, 5, 10) == ref_utils.Calculate_D_steps([], [], 0, 5, 10) == 5
+    rng = np.random.RandomState(0)
+    for trial in range(50):
+        n = int(rng.randint(1, 40))
+        real = list(rng.randn(n) * rng.rand() * 3)
+        fake = list(rng.randn(n) * rng.rand() * 3 + rng.randn())
+        n_min, n_max, period = int(rng.randint(0, 2)), int(rng.randint(2, 8)), int(rng.randint(1, 30))
+        assert my_utils.Calculate_D_steps(real, fake, n_min, n_max, period) == \
+            ref_utils.Calculate_D_steps(real, fake, n_min, n_max, period)

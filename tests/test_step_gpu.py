@@ -284,7 +284,11 @@ def test_graph_replay_equals_eager(res, alpha, batch):
     after_replay = [[p.detach().clone() for p in n.parameters()] for n in (G, D)]
     _restore((G, D), (step.opt_g, step.opt_d), snap)       # bumps the parameter versions -> next call runs eagerly
     s_eager = step(xs[2], draws[2]).cpu()
-    assert torch.allclose(s_replay, s_eager, rtol=1e-4, atol=2e-5), (s_replay, s_eager)
+    # [D_loss, score_real, score_fake, G_loss, pen]: everything but G_loss is computed before any update; G_loss runs
+    # through the critic just updated (see below), so it carries that update's run-to-run noise
+    tight = [0, 1, 2, 4]
+    assert torch.allclose(s_replay[tight], s_eager[tight], rtol=1e-4, atol=2e-5), (s_replay, s_eager)
+    assert abs(s_replay[3] - s_eager[3]).item() <= 3e-4, (s_replay, s_eager)
     # fp32 atomics make the last bits of the critic's gradients run-dependent; Adam turns a sign change of a ~0
     # gradient element into a 2*lr difference, and the generator step -- which runs through the critic just updated --
     # inherits ~1 % gradient noise from those flips, which Adam amplifies where |g| ~ eps = 1e-8 (most of the 16.8 M
@@ -406,3 +410,32 @@ def test_two_critic_steps_per_generator_step():
         for (k, a), (_, b) in zip(n1.state_dict().items(), n2.state_dict().items()):
             d = (a.float() - b.float()).abs()
             assert d.max().item() <= 4.2e-4 and d.mean().item() < 1e-5, (k, d.max().item(), d.mean().item())
+
+
+def test_adaptive_critic_count_between_calls():
+    """adapt_critic (train.py:336-340): the critic count changes from epoch to epoch, 0 included (N_min = 0 there).
+    n_critic is read at call time: 0 leaves the critic untouched and still steps the generator; going back to 1
+    resumes the captured-graph path."""
+    from neuron_gan_b200.train_step import TrainStep
+    from neuron_gan_b200.utils import Calculate_D_steps
+    res, alpha, B = 32, 0.5, 4
+    x = O.synthetic_images(B, res, seed=62).to(DEV)
+    G, D = nets(res, alpha)
+    step = TrainStep(G, D)
+    for _ in range(3):
+        step(x)
+    assert Calculate_D_steps([], [], 0, 3, 10) == 3
+    step.n_critic = Calculate_D_steps([1.0, 1.0, 1.0], [0.0, 0.5, 0.2], 0, 3, 10)     # zero spread -> 0 steps
+    assert step.n_critic == 0
+    d_before = {k: v.clone() for k, v in D.state_dict().items()}
+    g_before = {k: v.clone() for k, v in G.state_dict().items()}
+    stats = step(x)
+    assert torch.isfinite(stats).all()
+    assert all(torch.equal(v, d_before[k]) for k, v in D.state_dict().items())
+    assert any(not torch.equal(v, g_before[k]) for k, v in G.state_dict().items())
+    step.n_critic = 1
+    d_before = {k: v.clone() for k, v in D.state_dict().items()}
+    for _ in range(2):
+        stats = step(x)
+    assert torch.isfinite(stats).all()
+    assert any(not torch.equal(v, d_before[k]) for k, v in D.state_dict().items())
