@@ -1,0 +1,246 @@
+"""Training launcher: the epoch control of the reference's `pggan_train` (reference train.py:312-451) around
+`TrainStep`, for one GPU or for data-parallel runs with one process per GPU -- the reference's train.py is a
+single-process script that hard-codes `cuda:0` (train.py:128-130), so multi-GPU needs this new entry point
+(SURVEY.md section 8e).
+
+    python -m neuron_gan_b200.launch --synthetic 64 --N_epochs 6 --transit_sch 2 --alpha_step 0.5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \\
+        -m neuron_gan_b200.launch --synthetic 256 --batch_size 128 ...
+
+What is mirrored, with the reference's option names (configs/config.py:19-56): per-epoch fade-in advance and the
+resolution schedule (`transit_sch`, `alpha_step`; train.py:318-333), `n_critic` / `adapt_critic` (train.py:336-340),
+the learning-rate ramp of `update_lr` (train.py:238-265), per-epoch statistics weighted by batch size and divided by
+the dataset size (train.py:388-399), reference-format checkpoints every `checkpointing_period` epochs with a sample
+grid (train.py:432-444) -- on rank 0 only.  Plots, the memory logger and the config-file machinery are not.
+
+Data parallel: `batch_size` is the GLOBAL batch; every rank holds the canvases, draws the whole batch's augmentation
+parameters and latents on identically seeded CPU generators, and keeps its rows (data.DatasetIterator, dp.global_draws);
+TrainStep averages the gradients over ranks before each Adam step, so the replicas stay bit-identical.
+"""
+import argparse
+import os
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import dp
+from .data import DatasetIterator, NeuronImages
+from .train_step import TrainStep, build_networks
+from .utils import Calculate_D_steps, Checkpointer, plot_gen_samples
+
+LR_TRANSIT_TOTAL_DECAY = 1 / 100        # train.py:234
+DISC_ADAPT_UPDATE_PERIOD = 100          # train.py:190
+
+
+@dataclass
+class TrainConfig:
+    """The options of configs/config.py that the PGGAN loop reads, with its defaults."""
+    n_critic: int = 1
+    adapt_critic: bool = False
+    grad_pen_lambda: float = 10
+    transit_sch: list = field(default_factory=lambda: [25000, 50000, 75000, 100000, 125000])
+    alpha_step: float = 0.0001
+    learning_rate: float = 0.0001
+    batch_size: int = 8
+    N_epochs: int = 150000
+    N_epochs_session: int = None
+    beta1: float = 0.5
+    drift_epsilon: float = 0.001
+    seed: int = 1
+    checkpointing_period: int = 100
+    translation: float = 0.05
+    image_size: int = 512
+    N_gen_features: list = field(default_factory=lambda: [128, 64, 32, 32, 16, 16])
+    N_dis_features: list = field(default_factory=lambda: [16, 16, 32, 32, 64, 128])
+
+
+class LrSchedule:
+    """`update_lr` (train.py:238-265): at a phase boundary (epoch 0, a transition start, N_epochs) the rate is reset to
+    `learning_rate`; during the first half of a phase it is learning_rate * gamma^(epochs since the boundary) with
+    gamma chosen to reach 1/100 at mid-phase; in the second half it is left where it is."""
+
+    def __init__(self, learning_rate, transit_sch, N_epochs):
+        self.learning_rate = learning_rate
+        self.transit_sch = list(transit_sch)
+        self.boundaries = [0] + self.transit_sch + [N_epochs]
+        self.gamma = [np.exp(np.log(LR_TRANSIT_TOTAL_DECAY) / ((b - a) / 2))
+                      for a, b in zip(self.boundaries[:-1], self.boundaries[1:])]
+
+    def value(self, epoch):
+        """New rate for `epoch`, or None when update_lr leaves the optimiser untouched."""
+        if epoch in self.boundaries:
+            return self.learning_rate
+        phase = sum(epoch > t for t in self.transit_sch)
+        since = epoch - self.boundaries[phase]
+        if since <= (self.boundaries[phase + 1] - self.boundaries[phase]) / 2:
+            return self.learning_rate * self.gamma[phase] ** since
+        return None
+
+    def apply(self, optimizer, epoch):
+        lr = self.value(epoch)
+        if lr is not None:
+            for group in optimizer.param_groups:
+                group['lr'] = lr
+
+
+def _global_draws(step, global_batch, rank, world):
+    """The iteration's latent / epsilon draws for the GLOBAL batch, in the reference's order (z, z, eps per critic step,
+    then z for the generator step), this rank's rows.  Identical generators on all ranks -> a consistent global draw."""
+    from .utils import sample_latent_vec
+    L = step.G.latent_dim
+    if step.n_critic == 1:
+        return dp.global_draws(sample_latent_vec, global_batch, L, rank, world)
+    rows = lambda t: dp.shard_rows(t, rank, world).contiguous()
+    out = [(rows(sample_latent_vec((global_batch, L))), rows(sample_latent_vec((global_batch, L))),
+            rows(torch.rand((global_batch, 1, 1, 1)))) for _ in range(step.n_critic)]
+    return out + [rows(sample_latent_vec((global_batch, L)))]
+
+
+def _sum_over_ranks(values):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor(values, dtype=torch.float64, device='cuda')
+        dist.all_reduce(t)
+        return t.tolist()
+    return values
+
+
+def pggan_train(cfg: TrainConfig, images: NeuronImages, Generator_net, Discriminator_net, checkpoint=None,
+                samples_dir=None, rank=0, world=1, log=print, epoch_init=1):
+    """Runs epochs [epoch_init, N_epochs] (or N_epochs_session of them).  Returns the per-epoch statistics."""
+    device = next(Generator_net.parameters()).device
+    assert Generator_net.image_size == Discriminator_net.image_size, \
+        'The generator and discriminator are at different resolution'                              # train.py:215-216
+    images.set_image_size(Generator_net.image_size)
+    step = TrainStep(Generator_net, Discriminator_net, cfg.learning_rate, cfg.beta1, cfg.grad_pen_lambda,
+                     cfg.drift_epsilon, n_critic=cfg.n_critic)
+    schedule = LrSchedule(cfg.learning_rate, cfg.transit_sch, cfg.N_epochs)
+    if world > 1 and (cfg.batch_size % world or (len(images) % cfg.batch_size) % world):
+        raise ValueError('data parallel: batch_size and the ragged last batch (len(dataset) % batch_size) must be '
+                         'divisible by the number of ranks, so that every rank gets the same number of rows')
+    dataloader = DatasetIterator(images, cfg.batch_size, device, rank=rank, world=world)
+    epoch_final = epoch_init + cfg.N_epochs_session if cfg.N_epochs_session else cfg.N_epochs + 1
+    schedule.apply(step.opt_d, epoch_init - 1)
+    schedule.apply(step.opt_g, epoch_init - 1)
+    names = ('D_loss', 'score_real', 'score_fake', 'G_loss', 'D_grad_pen')
+    series = {k: [] for k in names}
+    history = []
+    start = time.time()
+    for epoch in range(epoch_init, epoch_final):
+        lr = step.opt_g.param_groups[0]['lr']
+        if Generator_net.alpha < 1 and Discriminator_net.alpha < 1:                                 # train.py:318-325
+            Generator_net.advance_transition(cfg.alpha_step)
+            Discriminator_net.advance_transition(cfg.alpha_step)
+        elif Generator_net.alpha < 1:
+            raise Exception('The networks are not synchronized. Gen_alpha={:.3f}, Disc_alpha={:.3f}'.format(
+                float(Generator_net.alpha), float(Discriminator_net.alpha)))
+        if epoch in cfg.transit_sch:                                                                # train.py:328-333
+            Generator_net.increase_resolution()
+            Discriminator_net.increase_resolution()
+            images.set_image_size(Generator_net.image_size)
+        if cfg.adapt_critic and len(series['score_real']) > DISC_ADAPT_UPDATE_PERIOD:               # train.py:336-340
+            step.n_critic = Calculate_D_steps(series['score_real'], series['score_fake'], 0, cfg.n_critic,
+                                              Period=DISC_ADAPT_UPDATE_PERIOD)
+        else:
+            step.n_critic = cfg.n_critic
+        # one device tensor accumulates batch * statistics (train.py:388-394): no host sync inside the epoch
+        acc = torch.zeros(5, dtype=torch.float64, device=device)
+        for real_images in dataloader:
+            b = real_images.shape[0]
+            if b == 0:
+                continue
+            draws = _global_draws(step, b * world, rank, world) if world > 1 else None
+            acc += b * step(real_images, draws).double()
+        totals = _sum_over_ranks(acc.tolist())
+        stats = {k: v / len(images) for k, v in zip(names, totals)}                                 # train.py:397-399
+        TrainStep.check_nan([stats[k] for k in names])
+        if rank == 0 and epoch % 10 == 0:                                                           # train.py:402-425
+            done = epoch - epoch_init
+            log(', '.join([f'Epoch:{epoch}',
+                           'time(s)/iter:' + ('{:.1f}'.format((time.time() - start) / done) if done > 0 else '----'),
+                           'lr:{:.4g}'.format(lr), 'alpha:{: >5.3f}'.format(float(Generator_net.alpha)),
+                           'Res:{0}x{0}'.format(Generator_net.image_size),
+                           'Loss_real (<D(x)>_x):{: >#7.4g}'.format(stats['score_real']),
+                           'Loss_fake (<D(G(z))>):{: >#7.4g}'.format(stats['score_fake']),
+                           'G_loss:{: >#7.4g}'.format(stats['G_loss']), 'D_loss:{: >#7.4g}'.format(stats['D_loss']),
+                           'D_grad_pen:{: >#7.4g}'.format(stats['D_grad_pen'])]))
+        schedule.apply(step.opt_d, epoch)                                                           # train.py:428-429
+        schedule.apply(step.opt_g, epoch)
+        for k in names:
+            series[k].append(stats[k])
+        history.append(dict(stats, epoch=epoch, lr=lr, alpha=float(Generator_net.alpha),
+                            image_size=Generator_net.image_size, n_critic=step.n_critic))
+        if checkpoint is not None and rank == 0:
+            checkpoint.Loss_real[epoch - 1], checkpoint.Loss_fake[epoch - 1] = stats['score_real'], stats['score_fake']
+            checkpoint.Loss_G[epoch - 1], checkpoint.Loss_D[epoch - 1] = stats['G_loss'], stats['D_loss']
+            if epoch % cfg.checkpointing_period == 0:                                               # train.py:438-444
+                checkpoint.save_state(epoch)
+                if samples_dir is not None:
+                    plot_gen_samples(Generator_net, N_images=16, seed=0,
+                                     filename=os.path.join(samples_dir, 'Samples_{:d}.png'.format(epoch)))
+    return history
+
+
+def synthetic_images(n, image_size, seed=0):
+    """Stand-in canvases (no dataset ships with the repository): smooth random fields in [0, 1], padded like
+    NeuronDataset pads (image_size // 4 per side)."""
+    g = torch.Generator().manual_seed(seed)
+    P = image_size + 2 * (image_size // 4)
+    low = torch.rand(n, 1, P // 16, P // 16, generator=g)
+    return torch.nn.functional.interpolate(low, size=(P, P), mode='bilinear', align_corners=False)[:, 0].contiguous()
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__.split('\n')[0])
+    ap.add_argument('--synthetic', type=int, default=64, help='number of synthetic canvases to train on')
+    ap.add_argument('--weights_dir', default=None, help='write reference-format checkpoints here (rank 0)')
+    for name, f in TrainConfig.__dataclass_fields__.items():
+        default = f.default if f.default_factory is dataclass_missing() else f.default_factory()
+        if isinstance(default, list):
+            ap.add_argument('--' + name, type=int, nargs='*', default=default)
+        elif isinstance(default, bool):
+            ap.add_argument('--' + name, action='store_true')
+        else:
+            ap.add_argument('--' + name, type=type(default) if default is not None else int, default=default)
+    args = ap.parse_args(argv)
+    cfg = TrainConfig(**{k: getattr(args, k) for k in TrainConfig.__dataclass_fields__})
+    rank, world, local = dp.init_from_env()
+    device = torch.device('cuda', local)
+    torch.cuda.set_device(device)
+    if cfg.batch_size % world:
+        raise SystemExit(f'batch_size {cfg.batch_size} (global) must be divisible by the number of ranks {world}')
+    size_init = cfg.image_size // 2 ** (len(cfg.N_gen_features) - 1)
+    G, D = build_networks(size_init, 1.0, seed=cfg.seed, device=device, gen_features=cfg.N_gen_features,
+                          dis_features=cfg.N_dis_features, image_size=cfg.image_size)
+    images = NeuronImages(synthetic_images(args.synthetic, cfg.image_size), cfg.image_size, True, cfg.translation)
+    checkpoint = None
+    if args.weights_dir and rank == 0:
+        os.makedirs(args.weights_dir, exist_ok=True)
+        checkpoint = Checkpointer(G, D, cfg.learning_rate, os.path.join(args.weights_dir, 'GenDisc.pth'),
+                                  N_epochs=cfg.N_epochs, device=device, verbose=False)
+    torch.manual_seed(cfg.seed + 1)          # the augmentation / latent stream, identical on every rank
+    history = pggan_train(cfg, images, G, D, checkpoint, rank=rank, world=world)
+    if rank == 0:
+        last = history[-1]
+        print('done: epoch {epoch}, {image_size}x{image_size}, alpha {alpha:.3f}, D_loss {D_loss:.4g}, '
+              'G_loss {G_loss:.4g}'.format(**last))
+    if dist.is_available() and dist.is_initialized():
+        # replicas must be bit-identical: same initial weights, same averaged gradients, same Adam
+        digest = torch.stack([p.detach().double().sum() for net in (G, D) for p in net.parameters()]).sum().reshape(1)
+        digests = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(digests, digest)
+        if rank == 0:
+            print('replicas identical:', all(torch.equal(d, digests[0]) for d in digests))
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def dataclass_missing():
+    import dataclasses
+    return dataclasses.MISSING
+
+
+if __name__ == '__main__':
+    main()

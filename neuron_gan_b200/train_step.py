@@ -47,7 +47,8 @@ class TrainStep:
         self.fork_chains = True         # run the two independent halves of the critic step on two streams
         self._chain_stream = None
         self._bound = {}
-        self._graphs = {}
+        self._graphs = {}               # configuration key -> captured iteration, least recently used first
+        self.max_graphs = 4             # during a fade-in alpha (part of the key) changes every epoch: old graphs go
         self._rings = {}
         self._last_key = None
         self._versions_seen = None
@@ -269,6 +270,8 @@ class TrainStep:
         ent.launches = _lib.launch_count - n0
         _lib.launch_count = n0          # captured, not launched
         self._graphs[key] = ent
+        while len(self._graphs) > max(1, self.max_graphs):       # dicts keep insertion order: first = least recent
+            self._graphs.pop(next(iter(self._graphs)))
         return ent
 
     @torch.no_grad()
@@ -294,6 +297,7 @@ class TrainStep:
                 self._capture(key, B, R, dev)
             self._last_key = key
             return stats.clone() if ent is not None else stats
+        self._graphs[key] = self._graphs.pop(key)                 # most recently used last
         self._load(ent.buf, images, z1, z2, eps, z3)
         self.opt_d.advance()
         self.opt_g.advance()

@@ -104,3 +104,29 @@ def test_adaptive_critic_steps_match_the_reference():
         n_min, n_max, period = int(rng.randint(0, 2)), int(rng.randint(2, 8)), int(rng.randint(1, 30))
         assert my_utils.Calculate_D_steps(real, fake, n_min, n_max, period) == \
             ref_utils.Calculate_D_steps(real, fake, n_min, n_max, period)
+
+
+def test_lr_schedule_matches_the_reference_update_lr():
+    """launch.LrSchedule against the UNMODIFIED `update_lr` of the reference, lifted out of train.py with ast
+    (train.py is a script: importing it would start a training run) and executed with its own globals."""
+    import ast
+    import os
+    import types
+    import numpy as np
+    import torch
+    from neuron_gan_b200.launch import LrSchedule
+    src = open(os.path.join(rh.REF_DIR, 'train.py')).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == 'update_lr')
+    for transit_sch, n_epochs, lr0 in (([10, 20, 35], 50, 1e-4), ([7], 20, 3e-4), ([4, 9, 15, 22, 30], 41, 1e-3)):
+        config = types.SimpleNamespace(learning_rate=lr0, transit_sch=transit_sch, N_epochs=n_epochs)
+        boundaries = [0] + transit_sch + [n_epochs]                                  # train.py:238-243
+        decay = [np.exp(np.log(1 / 100) / ((b - a) / 2)) for a, b in zip(boundaries[:-1], boundaries[1:])]
+        env = {'config': config, 'transitions_epoch_boundaries': boundaries, 'lr_decay_rate': decay}
+        exec(compile(ast.Module([fn], []), 'train.py', 'exec'), env)
+        p = torch.nn.Parameter(torch.zeros(1))
+        ref_opt, my_opt = torch.optim.Adam([p], lr=lr0), torch.optim.Adam([p], lr=lr0)
+        sched = LrSchedule(lr0, transit_sch, n_epochs)
+        for epoch in range(0, n_epochs + 1):
+            env['update_lr'](ref_opt, epoch)
+            sched.apply(my_opt, epoch)
+            assert ref_opt.param_groups[0]['lr'] == my_opt.param_groups[0]['lr'], (transit_sch, epoch)
