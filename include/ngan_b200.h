@@ -19,6 +19,10 @@
  *    the tail of the previous kernel in the stream, their first global-memory access waits for it
  *    (griddepcontrol.wait), so stream order is preserved for any caller; NGAN_NO_PDL=1 in the environment disables it.
  *  - ngan_adam_multi takes at most 48 tensors per call.
+ *  - `const float* dyn` after a scalar argument (the seven entry points the fade-in coefficient alpha reaches,
+ *    models.py:348-350, 519-521 and their backward passes): optional DEVICE pointer; when non-NULL the effective
+ *    scalar is the host value times *dyn, read by the kernel.  A launch captured in a CUDA graph then follows alpha,
+ *    which the reference advances every epoch during a resolution transition (train.py:318-321).
  *  - LeakyReLU + PixelNorm always come as a pair after a conv (models.py:261-268); "pn_bwd" below means
  *    ga = mask(y) * r * (g - y * mean_c(g*y)), the gradient wrt the conv's pre-activation, computed from the
  *    saved PixelNorm output y and scale r = (mean_c(h^2) + 1e-8)^-1/2 (models.py:118, 126).
@@ -84,7 +88,7 @@ int ngan_upsample2x(const void* x_c8, void* out_c8, int B, int C, int H, int W, 
 int ngan_avgpool2(const void* x_c8, void* out_c8, int B, int C, int H, int W, void* stream);
 /* ga = pn_bwd(gscale * g) (+ addin); unpool != 0 reads g at (H/2, W/2) (adjoint of AvgPool2d(2); fold the 1/4
  * into gscale).  gy_out (optional) receives gscale*g at full resolution. */
-int ngan_pn_bwd(const void* g_c8, int unpool, float gscale, const void* y_c8, const float* r, const void* addin_c8,
+int ngan_pn_bwd(const void* g_c8, int unpool, float gscale, const float* dyn, const void* y_c8, const float* r, const void* addin_c8,
                 void* ga_c8, void* gy_out_c8, float leak, int B, int C, int H, int W, void* stream);
 /* adjoint of the bilinear x2 upsample fused with pn_bwd of the layer below it; extra_pre/extra_w add the
  * faded-out ToImage branch's contribution extra_w[c]*extra_pre[b,y,x] (models.py:348).  H, W: low resolution. */
@@ -95,8 +99,8 @@ int ngan_up2_bwd_pn_bwd(const void* g_up_c8, const void* y_c8, const float* r, c
 int ngan_pool_image(const float* x, float* out, int B, int H, int W, void* stream);
 int ngan_unpool_image(const float* g, float* out, float scale, int B, int H, int W, void* stream);
 int ngan_up2_image(const float* x, float* out, int B, int H, int W, void* stream);
-int ngan_up2_image_bwd(const float* g, float* out, float scale, int B, int H, int W, void* stream);
-int ngan_lerp(const float* a, const float* b, float alpha, float* out, long long n, void* stream);
+int ngan_up2_image_bwd(const float* g, float* out, float scale, const float* dyn, int B, int H, int W, void* stream);
+int ngan_lerp(const float* a, const float* b, float alpha, const float* dyn, float* out, long long n, void* stream);
 int ngan_axpby(const float* a, float ca, const float* b, float cb, float* out, long long n, void* stream);
 int ngan_interp_images(const float* real, const float* fake, const float* eps, float* out, int B,
                        long long per_sample, void* stream);
@@ -108,13 +112,14 @@ int ngan_fromim_fwd(const float* xp, const float* w, const float* b, void* out_c
                     void* stream);
 /* discriminator fade-in, models.py:519-521: out = y_start + alpha*(y_end - y_start), y_start = FromIm_old(xp) */
 int ngan_d_fade_fwd(const void* y_end_c8, const float* xp, const float* w_old, const float* b_old, float alpha,
-                    void* out_c8, int B, int C, int H, int W, void* stream);
-int ngan_fromim_bwd(const void* g_c8, int unpool, float gscale, const float* xp, const float* w, float* gw, float* gb,
+                    const float* dyn, void* out_c8, int B, int C, int H, int W, void* stream);
+int ngan_fromim_bwd(const void* g_c8, int unpool, float gscale, const float* dyn, const float* xp, const float* w, float* gw, float* gb,
                     float* g_img, int g_img_accumulate, int B, int C, int H, int W, void* stream);
-int ngan_fromim_dbl(const float* ghat_xp, float in_scale, const void* g_c8, int unpool, float gscale, const float* w,
+int ngan_fromim_dbl(const float* ghat_xp, float in_scale, const void* g_c8, int unpool, float gscale,
+                    const float* dyn, const float* w,
                     void* ghat_out_c8, float* what, int B, int C, int H, int W, void* stream);
 int ngan_toim_fwd(const void* y_c8, const float* w, float* img, int B, int C, int H, int W, void* stream);
-int ngan_toim_bwd(const float* g_img, float gscale, const float* img, const void* y_c8, const float* r,
+int ngan_toim_bwd(const float* g_img, float gscale, const float* dyn, const float* img, const void* y_c8, const float* r,
                   const float* w, void* ga_c8, float* gpre, float* gw, float leak, int B, int C, int H, int W,
                   void* stream);
 

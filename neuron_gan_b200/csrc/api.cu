@@ -118,11 +118,11 @@ int ngan_avgpool2(const void* x, void* out, int B, int C, int H, int W, void* st
     NGAN_REQUIRE(x && out && !bad_c(C) && B > 0 && H % 2 == 0 && W % 2 == 0, "avgpool2: bad arguments");
     return avgpool2_c8(x, out, B, C, H, W, S(stream));
 }
-int ngan_pn_bwd(const void* g, int unpool, float gscale, const void* y, const float* r, const void* addin, void* ga,
+int ngan_pn_bwd(const void* g, int unpool, float gscale, const float* dyn, const void* y, const float* r, const void* addin, void* ga,
                 void* gy_out, float leak, int B, int C, int H, int W, void* stream) {
     NGAN_REQUIRE(g && y && r && ga && !bad_c(C) && B > 0, "pn_bwd: bad arguments");
     NGAN_REQUIRE(!unpool || (H % 2 == 0 && W % 2 == 0), "pn_bwd: unpool needs even H, W");
-    return pn_bwd_c8(g, unpool, gscale, y, r, addin, ga, gy_out, leak, B, C, H, W, S(stream));
+    return pn_bwd_c8(g, unpool, gscale, dyn, y, r, addin, ga, gy_out, leak, B, C, H, W, S(stream));
 }
 int ngan_up2_bwd_pn_bwd(const void* g_up, const void* y, const float* r, const float* extra_pre, const float* extra_w,
                         void* ga, float leak, int B, int C, int H, int W, void* stream) {
@@ -142,14 +142,14 @@ int ngan_up2_image(const float* x, float* out, int B, int H, int W, void* stream
     NGAN_REQUIRE(x && out && B > 0, "up2_image: bad arguments");
     return up2_image(x, out, B, H, W, S(stream));
 }
-int ngan_up2_image_bwd(const float* g, float* out, float scale, int B, int H, int W, void* stream) {
+int ngan_up2_image_bwd(const float* g, float* out, float scale, const float* dyn, int B, int H, int W, void* stream) {
     NGAN_REQUIRE(g && out && B > 0, "up2_image_bwd: bad arguments");
-    return up2_image_bwd(g, out, scale, B, H, W, S(stream));
+    return up2_image_bwd(g, out, scale, dyn, B, H, W, S(stream));
 }
-int ngan_lerp(const float* a, const float* b, float alpha, float* out, long long n, void* stream) {
+int ngan_lerp(const float* a, const float* b, float alpha, const float* dyn, float* out, long long n, void* stream) {
     NGAN_REQUIRE(a && b && out && n >= 0, "lerp: bad arguments");
     if (n == 0) return NGAN_OK;
-    return lerp_f32(a, b, alpha, out, static_cast<size_t>(n), S(stream));
+    return lerp_f32(a, b, alpha, dyn, out, static_cast<size_t>(n), S(stream));
 }
 int ngan_axpby(const float* a, float ca, const float* b, float cb, float* out, long long n, void* stream) {
     NGAN_REQUIRE(a && out && n >= 0, "axpby: bad arguments");
@@ -171,30 +171,31 @@ int ngan_fromim_fwd(const float* xp, const float* w, const float* b, void* out, 
     NGAN_REQUIRE(xp && w && b && out && !bad_c(C) && B > 0, "fromim_fwd: bad arguments");
     return fromim_fwd(xp, w, b, out, B, C, H, W, S(stream));
 }
-int ngan_d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const float* b_old, float alpha, void* out,
-                    int B, int C, int H, int W, void* stream) {
+int ngan_d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const float* b_old, float alpha,
+                    const float* dyn, void* out, int B, int C, int H, int W, void* stream) {
     NGAN_REQUIRE(y_end && xp && w_old && b_old && out && !bad_c(C) && B > 0, "d_fade_fwd: bad arguments");
-    return d_fade_fwd(y_end, xp, w_old, b_old, alpha, out, B, C, H, W, S(stream));
+    return d_fade_fwd(y_end, xp, w_old, b_old, alpha, dyn, out, B, C, H, W, S(stream));
 }
-int ngan_fromim_bwd(const void* g, int unpool, float gscale, const float* xp, const float* w, float* gw, float* gb,
+int ngan_fromim_bwd(const void* g, int unpool, float gscale, const float* dyn, const float* xp, const float* w, float* gw, float* gb,
                     float* g_img, int g_img_accumulate, int B, int C, int H, int W, void* stream) {
     NGAN_REQUIRE(g && xp && w && !bad_c(C) && B > 0, "fromim_bwd: bad arguments");
-    return fromim_bwd(g, unpool, gscale, xp, w, gw, gb, g_img, g_img_accumulate, B, C, H, W, S(stream));
+    return fromim_bwd(g, unpool, gscale, dyn, xp, w, gw, gb, g_img, g_img_accumulate, B, C, H, W, S(stream));
 }
-int ngan_fromim_dbl(const float* ghat_xp, float in_scale, const void* g, int unpool, float gscale, const float* w,
+int ngan_fromim_dbl(const float* ghat_xp, float in_scale, const void* g, int unpool, float gscale, const float* dyn,
+                    const float* w,
                     void* ghat_out, float* what, int B, int C, int H, int W, void* stream) {
     NGAN_REQUIRE(ghat_xp && g && w && !bad_c(C) && B > 0, "fromim_dbl: bad arguments");
-    return fromim_dbl(ghat_xp, in_scale, g, unpool, gscale, w, ghat_out, what, B, C, H, W, S(stream));
+    return fromim_dbl(ghat_xp, in_scale, g, unpool, gscale, dyn, w, ghat_out, what, B, C, H, W, S(stream));
 }
 int ngan_toim_fwd(const void* y, const float* w, float* img, int B, int C, int H, int W, void* stream) {
     NGAN_REQUIRE(y && w && img && !bad_c(C) && B > 0, "toim_fwd: bad arguments");
     return toim_fwd(y, w, img, B, C, H, W, S(stream));
 }
-int ngan_toim_bwd(const float* g_img, float gscale, const float* img, const void* y, const float* r, const float* w,
+int ngan_toim_bwd(const float* g_img, float gscale, const float* dyn, const float* img, const void* y, const float* r, const float* w,
                   void* ga, float* gpre, float* gw, float leak, int B, int C, int H, int W, void* stream) {
     NGAN_REQUIRE(g_img && img && y && w && !bad_c(C) && B > 0, "toim_bwd: bad arguments");
     NGAN_REQUIRE(!ga || r, "toim_bwd: ga requires r");
-    return toim_bwd(g_img, gscale, img, y, r, w, ga, gpre, gw, leak, B, C, H, W, S(stream));
+    return toim_bwd(g_img, gscale, dyn, img, y, r, w, ga, gpre, gw, leak, B, C, H, W, S(stream));
 }
 int ngan_head_fwd(const void* y, const float* w, const float* bias, float scale, float* score, int B, int C, int Sz,
                   void* stream) {

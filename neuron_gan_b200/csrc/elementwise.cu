@@ -185,7 +185,8 @@ int avgpool2_c8(const void* x, void* out, int B, int C, int H, int W, cudaStream
 // (one thread per pixel; with a run-time channel loop the kernel ran at 40 % of HBM bandwidth on load latency);
 // up to 32 channels the granules of the first pass stay in registers for the second.
 template <int NCH>
-__global__ void __launch_bounds__(128) pn_bwd_c8_kernel(const uint4* __restrict__ g, int unpool, float gscale,
+__global__ void __launch_bounds__(128) pn_bwd_c8_kernel(const uint4* __restrict__ g, int unpool, float gscale_h,
+                                                        const float* __restrict__ dyn,
                                                         const uint4* __restrict__ y, const float* __restrict__ r,
                                                         const uint4* __restrict__ addin, uint4* __restrict__ ga,
                                                         uint4* __restrict__ gy_out, float leak, int H, int W,
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(128) pn_bwd_c8_kernel(const uint4* __restrict_
     pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
+    const float gscale = dyn ? gscale_h * __ldg(dyn) : gscale_h;
     constexpr int C = NCH * 8;
     constexpr bool kKeep = NCH <= 4;
     constexpr int U = NCH < 4 ? NCH : 4;          // granules per unrolled chunk
@@ -258,13 +260,13 @@ __global__ void __launch_bounds__(128) pn_bwd_c8_kernel(const uint4* __restrict_
         }
     }
 }
-int pn_bwd_c8(const void* g, int unpool, float gscale, const void* y, const float* r, const void* addin, void* ga,
+int pn_bwd_c8(const void* g, int unpool, float gscale, const float* dyn, const void* y, const float* r, const void* addin, void* ga,
               void* gy_out, float leak, int B, int C, int H, int W, cudaStream_t st) {
     const size_t total = static_cast<size_t>(B) * H * W;
 #define NGAN_PNB(N)                                                                                                \
     case N:                                                                                                        \
         pn_bwd_c8_kernel<N><<<nblocks(total, 128), 128, 0, st>>>(                                                  \
-            static_cast<const uint4*>(g), unpool, gscale, static_cast<const uint4*>(y), r,                         \
+            static_cast<const uint4*>(g), unpool, gscale, dyn, static_cast<const uint4*>(y), r,                    \
             static_cast<const uint4*>(addin), static_cast<uint4*>(ga), static_cast<uint4*>(gy_out), leak, H, W,    \
             total);                                                                                                \
         break;
@@ -424,8 +426,8 @@ int up2_image(const float* x, float* out, int B, int H, int W, cudaStream_t st) 
     return check_launch("up2_image");
 }
 // adjoint of up2_image: g is [B, 2H, 2W], out [B, H, W] = scale * U^T g
-__global__ void up2_image_bwd_kernel(const float* __restrict__ g, float* __restrict__ out, float scale, int H, int W,
-                                     size_t total) {
+__global__ void up2_image_bwd_kernel(const float* __restrict__ g, float* __restrict__ out, float scale,
+                                     const float* __restrict__ dyn, int H, int W, size_t total) {
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int px, py;
@@ -444,11 +446,11 @@ __global__ void up2_image_bwd_kernel(const float* __restrict__ g, float* __restr
             acc += wy * wx * p[static_cast<size_t>(2 * py - 1 + a) * (2 * W) + (2 * px - 1 + c)];
         }
     }
-    out[i] = scale * acc;
+    out[i] = (dyn ? scale * __ldg(dyn) : scale) * acc;
 }
-int up2_image_bwd(const float* g, float* out, float scale, int B, int H, int W, cudaStream_t st) {
+int up2_image_bwd(const float* g, float* out, float scale, const float* dyn, int B, int H, int W, cudaStream_t st) {
     const size_t total = static_cast<size_t>(B) * H * W;
-    up2_image_bwd_kernel<<<nblocks(total, 256), 256, 0, st>>>(g, out, scale, H, W, total);
+    up2_image_bwd_kernel<<<nblocks(total, 256), 256, 0, st>>>(g, out, scale, dyn, H, W, total);
     return check_launch("up2_image_bwd");
 }
 __global__ void axpby_kernel(const float* __restrict__ a, float ca, const float* __restrict__ b, float cb,
@@ -461,13 +463,14 @@ int axpby_f32(const float* a, float ca, const float* b, float cb, float* out, si
     return check_launch("axpby_f32");
 }
 // a + alpha*(b - a): generator fade-in of the two ToImage branches (models.py:350)
-__global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha,
-                            float* __restrict__ out, size_t n) {
+__global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha_h,
+                            const float* __restrict__ dyn, float* __restrict__ out, size_t n) {
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const float alpha = dyn ? alpha_h * __ldg(dyn) : alpha_h;
     if (i < n) out[i] = a[i] + alpha * (b[i] - a[i]);
 }
-int lerp_f32(const float* a, const float* b, float alpha, float* out, size_t n, cudaStream_t st) {
-    lerp_kernel<<<nblocks(n, 256), 256, 0, st>>>(a, b, alpha, out, n);
+int lerp_f32(const float* a, const float* b, float alpha, const float* dyn, float* out, size_t n, cudaStream_t st) {
+    lerp_kernel<<<nblocks(n, 256), 256, 0, st>>>(a, b, alpha, dyn, out, n);
     return check_launch("lerp_f32");
 }
 // x_hat = eps_b * real + (1 - eps_b) * fake (loss_functions.py:171)
@@ -523,11 +526,13 @@ int fromim_fwd(const float* xp, const float* w, const float* b, void* out, int B
 }
 // Discriminator fade-in (models.py:519-521): y = y_start + alpha*(y_end - y_start), y_start = FromIm_old(xp)
 __global__ void d_fade_fwd_kernel(const uint4* __restrict__ y_end, const float* __restrict__ xp,
-                                  const float* __restrict__ w, const float* __restrict__ bias, float alpha,
-                                  uint4* __restrict__ out, int C, size_t HW, size_t total) {
+                                  const float* __restrict__ w, const float* __restrict__ bias, float alpha_h,
+                                  const float* __restrict__ dyn, uint4* __restrict__ out, int C, size_t HW,
+                                  size_t total) {
     pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
+    const float alpha = dyn ? alpha_h * __ldg(dyn) : alpha_h;
     size_t b, pix;
     split_bpix(i, HW, b, pix);
     const int nch = C / 8;
@@ -543,11 +548,11 @@ __global__ void d_fade_fwd_kernel(const uint4* __restrict__ y_end, const float* 
         out[(b * nch + j) * HW + pix] = pack8(o);
     }
 }
-int d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const float* b_old, float alpha, void* out,
-               int B, int C, int H, int W, cudaStream_t st) {
+int d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const float* b_old, float alpha,
+               const float* dyn, void* out, int B, int C, int H, int W, cudaStream_t st) {
     const size_t HW = static_cast<size_t>(H) * W, total = B * HW;
     d_fade_fwd_kernel<<<nblocks(total, 256), 256, 0, st>>>(static_cast<const uint4*>(y_end), xp, w_old, b_old, alpha,
-                                                            static_cast<uint4*>(out), C, HW, total);
+                                                            dyn, static_cast<uint4*>(out), C, HW, total);
     return check_launch("d_fade_fwd");
 }
 
@@ -561,12 +566,14 @@ int d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const flo
 // kernels shuffle-bound at 512x512 and left the 128-channel 16x16 launches at 36-49 us for 1 MB.)
 constexpr int kPixPerThread = 8;
 template <int NCH>
-__global__ void __launch_bounds__(128) fromim_bwd_kernel(const uint4* __restrict__ g, int unpool, float gscale,
+__global__ void __launch_bounds__(128) fromim_bwd_kernel(const uint4* __restrict__ g, int unpool, float gscale_h,
+                                                         const float* __restrict__ dyn,
                                                          const float* __restrict__ xp, const float* __restrict__ w,
                                                          float* __restrict__ gw, float* __restrict__ gb,
                                                          float* __restrict__ g_img, int accumulate, int H, int W,
                                                          size_t total) {
     constexpr int PL = 128 / NCH, C = NCH * 8;
+    const float gscale = dyn ? gscale_h * __ldg(dyn) : gscale_h;
     __shared__ float red[2][PL][C];
     const int pl = threadIdx.x / NCH, j = threadIdx.x % NCH;
     const size_t HW = static_cast<size_t>(H) * W;
@@ -625,13 +632,13 @@ static int pointwise_blocks(size_t total, int pixel_lanes) {
     if (blocks < 1) blocks = 1;
     return static_cast<int>(blocks);
 }
-int fromim_bwd(const void* g, int unpool, float gscale, const float* xp, const float* w, float* gw, float* gb,
+int fromim_bwd(const void* g, int unpool, float gscale, const float* dyn, const float* xp, const float* w, float* gw, float* gb,
                float* g_img, int g_img_accumulate, int B, int C, int H, int W, cudaStream_t st) {
     const size_t total = static_cast<size_t>(B) * H * W;
 #define NGAN_FIB(N)                                                                                                  \
     case N:                                                                                                          \
         fromim_bwd_kernel<N><<<pointwise_blocks(total, 128 / N), 128, 0, st>>>(                                      \
-            static_cast<const uint4*>(g), unpool, gscale, xp, w, gw, gb, g_img, g_img_accumulate, H, W, total);     \
+            static_cast<const uint4*>(g), unpool, gscale, dyn, xp, w, gw, gb, g_img, g_img_accumulate, H, W, total); \
         break;
     switch (C / 8) {
         NGAN_FIB(2)
@@ -648,9 +655,11 @@ int fromim_bwd(const void* g, int unpool, float gscale, const float* xp, const f
 // Double backward of FromImage's input-gradient: first order was g_xp = sum_c w_c * G_c.  With cotangent
 // X = in_scale * ghat_xp on g_xp:  ghat_out[c] = w_c * X (cotangent on G_c),  what[c] += sum X * G_c.
 __global__ void fromim_dbl_kernel(const float* __restrict__ ghat_xp, float in_scale, const uint4* __restrict__ g,
-                                  int unpool, float gscale, const float* __restrict__ w, uint4* __restrict__ ghat_out,
+                                  int unpool, float gscale_h, const float* __restrict__ dyn,
+                                  const float* __restrict__ w, uint4* __restrict__ ghat_out,
                                   float* __restrict__ what, int C, int H, int W, size_t total) {
     pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
+    const float gscale = dyn ? gscale_h * __ldg(dyn) : gscale_h;
     extern __shared__ float sacc[];  // [C]
     for (int k = threadIdx.x; k < C; k += blockDim.x) sacc[k] = 0.f;
     __syncthreads();
@@ -682,12 +691,13 @@ __global__ void fromim_dbl_kernel(const float* __restrict__ ghat_xp, float in_sc
     if (what)
         for (int k = threadIdx.x; k < C; k += blockDim.x) atomicAdd(what + k, sacc[k]);
 }
-int fromim_dbl(const float* ghat_xp, float in_scale, const void* g, int unpool, float gscale, const float* w,
+int fromim_dbl(const float* ghat_xp, float in_scale, const void* g, int unpool, float gscale, const float* dyn,
+               const float* w,
                void* ghat_out, float* what, int B, int C, int H, int W, cudaStream_t st) {
     const size_t total = static_cast<size_t>(B) * H * W;
     fromim_dbl_kernel<<<nblocks(total, 128), 128, C * sizeof(float), st>>>(
-        ghat_xp, in_scale, static_cast<const uint4*>(g), unpool, gscale, w, static_cast<uint4*>(ghat_out), what, C, H,
-        W, total);
+        ghat_xp, in_scale, static_cast<const uint4*>(g), unpool, gscale, dyn, w, static_cast<uint4*>(ghat_out), what,
+        C, H, W, total);
     return check_launch("fromim_dbl");
 }
 
@@ -717,13 +727,15 @@ int toim_fwd(const void* y, const float* w, float* img, int B, int C, int H, int
 // (if ga != null) the PixelNorm/LeakyReLU backward of the layer that produced y.
 // (thread layout: see fromim_bwd_kernel)
 template <int NCH>
-__global__ void __launch_bounds__(128) toim_bwd_kernel(const float* __restrict__ g_img, float gscale,
+__global__ void __launch_bounds__(128) toim_bwd_kernel(const float* __restrict__ g_img, float gscale_h,
+                                                       const float* __restrict__ dyn,
                                                        const float* __restrict__ img, const uint4* __restrict__ y,
                                                        const float* __restrict__ r, const float* __restrict__ w,
                                                        uint4* __restrict__ ga, float* __restrict__ gpre_out,
                                                        float* __restrict__ gw, float leak, size_t HW, size_t total) {
     pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     constexpr int PL = 128 / NCH, C = NCH * 8;
+    const float gscale = dyn ? gscale_h * __ldg(dyn) : gscale_h;
     __shared__ float red[PL][C];
     const int pl = threadIdx.x / NCH, j = threadIdx.x % NCH;
     float wj[8], sw[8];
@@ -774,13 +786,14 @@ __global__ void __launch_bounds__(128) toim_bwd_kernel(const float* __restrict__
         }
     }
 }
-int toim_bwd(const float* g_img, float gscale, const float* img, const void* y, const float* r, const float* w,
+int toim_bwd(const float* g_img, float gscale, const float* dyn, const float* img, const void* y, const float* r, const float* w,
              void* ga, float* gpre, float* gw, float leak, int B, int C, int H, int W, cudaStream_t st) {
     const size_t HW = static_cast<size_t>(H) * W, total = B * HW;
 #define NGAN_TIB(N)                                                                                                 \
     case N:                                                                                                         \
         toim_bwd_kernel<N><<<pointwise_blocks(total, 128 / N), 128, 0, st>>>(                                       \
-            g_img, gscale, img, static_cast<const uint4*>(y), r, w, static_cast<uint4*>(ga), gpre, gw, leak, HW,    \
+            g_img, gscale, dyn, img, static_cast<const uint4*>(y), r, w, static_cast<uint4*>(ga), gpre, gw, leak,   \
+            HW,                                                                                                     \
             total);                                                                                                 \
         break;
     switch (C / 8) {

@@ -23,28 +23,29 @@ int nchw_to_c8(const float* src, void* dst, int B, int C, int H, int W, cudaStre
 int c8_to_nchw(const void* src, float* dst, int B, int C, int H, int W, cudaStream_t st);
 int upsample2x_c8(const void* x, void* out, int B, int C, int H, int W, cudaStream_t st);
 int avgpool2_c8(const void* x, void* out, int B, int C, int H, int W, cudaStream_t st);
-int pn_bwd_c8(const void* g, int unpool, float gscale, const void* y, const float* r, const void* addin, void* ga,
+int pn_bwd_c8(const void* g, int unpool, float gscale, const float* dyn, const void* y, const float* r, const void* addin, void* ga,
               void* gy_out, float leak, int B, int C, int H, int W, cudaStream_t st);
 int up2_bwd_pn_bwd_c8(const void* g_up, const void* y, const float* r, const float* extra_pre, const float* extra_w,
                       void* ga, float leak, int B, int C, int H, int W, cudaStream_t st);
 int pool_image(const float* x, float* out, int B, int H, int W, cudaStream_t st);
 int unpool_image(const float* g, float* out, float scale, int B, int H, int W, cudaStream_t st);
 int up2_image(const float* x, float* out, int B, int H, int W, cudaStream_t st);
-int up2_image_bwd(const float* g, float* out, float scale, int B, int H, int W, cudaStream_t st);
-int lerp_f32(const float* a, const float* b, float alpha, float* out, size_t n, cudaStream_t st);
+int up2_image_bwd(const float* g, float* out, float scale, const float* dyn, int B, int H, int W, cudaStream_t st);
+int lerp_f32(const float* a, const float* b, float alpha, const float* dyn, float* out, size_t n, cudaStream_t st);
 int axpby_f32(const float* a, float ca, const float* b, float cb, float* out, size_t n, cudaStream_t st);
 int interp_images(const float* real, const float* fake, const float* eps, float* out, int B, size_t per_sample,
                   cudaStream_t st);
 int fromim_fwd(const float* xp, const float* w, const float* b, void* out, int B, int C, int H, int W,
                cudaStream_t st);
-int d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const float* b_old, float alpha, void* out,
-               int B, int C, int H, int W, cudaStream_t st);
-int fromim_bwd(const void* g, int unpool, float gscale, const float* xp, const float* w, float* gw, float* gb,
+int d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const float* b_old, float alpha,
+               const float* dyn, void* out, int B, int C, int H, int W, cudaStream_t st);
+int fromim_bwd(const void* g, int unpool, float gscale, const float* dyn, const float* xp, const float* w, float* gw, float* gb,
                float* g_img, int g_img_accumulate, int B, int C, int H, int W, cudaStream_t st);
-int fromim_dbl(const float* ghat_xp, float in_scale, const void* g, int unpool, float gscale, const float* w,
+int fromim_dbl(const float* ghat_xp, float in_scale, const void* g, int unpool, float gscale, const float* dyn,
+               const float* w,
                void* ghat_out, float* what, int B, int C, int H, int W, cudaStream_t st);
 int toim_fwd(const void* y, const float* w, float* img, int B, int C, int H, int W, cudaStream_t st);
-int toim_bwd(const float* g_img, float gscale, const float* img, const void* y, const float* r, const float* w,
+int toim_bwd(const float* g_img, float gscale, const float* dyn, const float* img, const void* y, const float* r, const float* w,
              void* ga, float* gpre, float* gw, float leak, int B, int C, int H, int W, cudaStream_t st);
 int head_fwd(const void* y, const float* w, const float* bias, float scale, float* score, int B, int C, int S,
              cudaStream_t st);

@@ -198,6 +198,25 @@ def _g_block_fwd(blk, y, leak, save, toim=None, need_y=True, img_out=None):
     return SimpleNamespace(blk=blk, xu=xu if save else None, y1=y1 if save else None, r1=r1, y2=y2, r2=r2, img=img)
 
 
+def _alpha_terms(net, alpha):
+    """(alpha, 1 - alpha) as kernel scalar arguments.  A caller that replays captured graphs (TrainStep) hangs a
+    2-element device tensor [alpha, 1 - alpha] on the network as `_ngan_alpha_dev`; the kernels then read the values
+    from it, so one graph serves every epoch of a fade-in (`_ngan_alpha_dev_value` is the alpha the table holds; a
+    stale table is ignored).  Otherwise plain floats."""
+    tab = getattr(net, '_ngan_alpha_dev', None)
+    if tab is None or getattr(net, '_ngan_alpha_dev_value', None) != alpha:     # no table, or not current: floats
+        return alpha, 1.0 - alpha
+    return (1.0, tab[0:1]), (1.0, tab[1:2])
+
+
+def _times(scale, term):
+    """scale (float, or already carrying a device factor) times an _alpha_terms entry."""
+    if isinstance(term, tuple):
+        assert not isinstance(scale, tuple), 'alpha enters every gradient path at most once'
+        return ops.scalar_mul(scale, term)
+    return ops.scalar_mul(term, scale) if isinstance(scale, tuple) else scale * term
+
+
 def g_forward(net, z, save, img_out=None):
     """Generator_PG.forward (reference models.py:344-353). z: [B, latent] fp32 -> (img [B, R, R] fp32, ctx).
     img_out: optional preallocated [B, R, R] fp32 tensor that receives the image."""
@@ -226,7 +245,7 @@ def g_forward(net, z, save, img_out=None):
         y, r = rec.y2, rec.r2
         if last:
             img_trunk = rec.img
-    ctx = (SimpleNamespace(z=z, y0=y0, r0=r0, yc=yc, rc=rc, recs=recs, alpha=alpha, new=None, toim=net.ToIm,
+    ctx = (SimpleNamespace(z=z, y0=y0, r0=r0, yc=yc, rc=rc, recs=recs, alpha=alpha, net=net, new=None, toim=net.ToIm,
                            toim_new=None) if save else None)
     if not fade:
         if save:
@@ -234,7 +253,8 @@ def g_forward(net, z, save, img_out=None):
         return img_trunk, ctx
     # fade-in: im_start = up(ToIm_old(x)), im_end = ToIm_new(block_new(x))      (models.py:347-350)
     new = _g_block_fwd(net.conv_block_list[0], y, leak, save, toim=net.ToIm_list[0], need_y=False)
-    img = ops.lerp(ops.up2_image(img_trunk), new.img, alpha, out=img_out)
+    a_dev, _ = _alpha_terms(net, alpha)
+    img = ops.lerp(ops.up2_image(img_trunk), new.img, a_dev, out=img_out)
     if save:
         ctx.new, ctx.img_old, ctx.img_end, ctx.toim_new = new, img_trunk, new.img, net.ToIm_list[0]
     return img, ctx
@@ -263,9 +283,10 @@ def g_backward(net, ctx, g_img, sink, linear_overwrite=False):
                              leak=leak)
     else:
         new, toim_new, toim_old = ctx.new, ctx.toim_new, ctx.toim
+        a_dev, oma_dev = _alpha_terms(net, alpha)
         ga2, _ = ops.toim_bwd(g_img, ctx.img_end, new.y2, new.r2, _flat(toim_new.weight),
-                              _sink_get(sink, toim_new.weight), gscale=alpha, leak=leak)
-        g_old = ops.up2_image_bwd(g_img, 1.0 - alpha)
+                              _sink_get(sink, toim_new.weight), gscale=a_dev, leak=leak)
+        g_old = ops.up2_image_bwd(g_img, oma_dev)
         _, gpre_old = ops.toim_bwd(g_old, ctx.img_old, trunk_y, None, _flat(toim_old.weight),
                                    _sink_get(sink, toim_old.weight), want_ga=False, want_gpre=True, leak=leak)
         ga = _g_block_bwd(new, ga2, trunk_y, trunk_r, leak, sink, gpre_old, _flat(toim_old.weight))
@@ -307,7 +328,7 @@ def d_forward(net, x, save):
         stages.append(SimpleNamespace(kind='from', conv=f_new, out=F, consumer_pooled=False))
         stages.append(block(net.conv_block_list[-1], F, False))
         f_old = net.FromIm.conv
-        y = ops.d_fade_fwd(stages[-1].out, xp, _flat(f_old.weight), f_old.bias.detach(), alpha)
+        y = ops.d_fade_fwd(stages[-1].out, xp, _flat(f_old.weight), f_old.bias.detach(), _alpha_terms(net, alpha)[0])
         stages.append(SimpleNamespace(kind='fade', conv=f_old, out=y, consumer_pooled=False))
         rest = trunk
     else:
@@ -341,6 +362,7 @@ def d_backward(net, ctx, gout, sink, addins=None, want_gxp=False, record=None):
     Returns g_xp, the gradient wrt the pooled image `xp` ([B, h, w] fp32) when want_gxp (callers un-pool it)."""
     leak = net.LeakyReLU_neg_slope
     alpha = ctx.alpha
+    a_dev, oma_dev = _alpha_terms(net, alpha)
     last, head = net.last_conv(), net.head_conv()
     rec = record is not None
     ad = addins or {}
@@ -385,7 +407,7 @@ def d_backward(net, ctx, gout, sink, addins=None, want_gxp=False, record=None):
                 recv_unpool = False
             else:
                 _, g, gs, recv_unpool = incoming
-                ga2, gy2 = ops.pn_bwd(g, st.y2, st.r2, gscale=gs * (0.25 if recv_unpool else 1.0),
+                ga2, gy2 = ops.pn_bwd(g, st.y2, st.r2, gscale=ops.scalar_mul(0.25 if recv_unpool else 1.0, gs),
                                       unpool=recv_unpool, addin=a2, want_gy=rec, leak=leak)
             if sink is not None:
                 _wgrad(st.y1, ga2, c2.scale_value, _sink_get(sink, c2.weight))
@@ -399,7 +421,7 @@ def d_backward(net, ctx, gout, sink, addins=None, want_gxp=False, record=None):
                         st.xin_pooled)
         else:
             _, g, gs, unpool = incoming
-            gs_eff = gs * (0.25 if unpool else 1.0)
+            gs_eff = ops.scalar_mul(0.25 if unpool else 1.0, gs)
             if rec:
                 record.stages[id(st)] = SimpleNamespace(g=g, unpool=unpool, gscale=gs_eff)
             need_img = want_gxp
@@ -412,9 +434,9 @@ def d_backward(net, ctx, gout, sink, addins=None, want_gxp=False, record=None):
             if st.kind == 'fade':
                 if sink is not None or need_img:
                     ops.fromim_bwd(g, ctx.xp, w, _sink_get(sink, st.conv.weight), _sink_get(sink, st.conv.bias),
-                                   gscale=gs_eff * (1.0 - alpha), unpool=unpool, g_img=g_xp if need_img else None,
+                                   gscale=_times(gs_eff, oma_dev), unpool=unpool, g_img=g_xp if need_img else None,
                                    accumulate=accumulate)
-                incoming = ('g', g, gs * alpha, unpool)
+                incoming = ('g', g, _times(gs, a_dev), unpool)
             else:  # 'from'
                 if sink is not None or need_img:
                     ops.fromim_bwd(g, ctx.xp, w, _sink_get(sink, st.conv.weight), _sink_get(sink, st.conv.bias),
@@ -429,6 +451,7 @@ def d_double_backward_sweep1(net, ctx, record, ghat_xp, sink):
     Accumulates the "wgrad of dgrad" terms into `sink` and returns the per-stage injections for sweep 2."""
     leak = net.LeakyReLU_neg_slope
     alpha = ctx.alpha
+    a_dev, oma_dev = _alpha_terms(net, alpha)
     addins = {}
     cur = None
     ghat_xp = ghat_xp.contiguous()
@@ -454,9 +477,9 @@ def d_double_backward_sweep1(net, ctx, record, ghat_xp, sink):
         else:  # 'fade': first-order g_y reached FromIm_old with (1-alpha) and the new block with alpha
             w_old = _flat(st.conv.weight)
             ops.fromim_dbl(ghat_xp, r.g, w_old, _sink_get(sink, st.conv.weight), in_scale=1.0,
-                           gscale=r.gscale * (1.0 - alpha), unpool=r.unpool, want_out=False)
+                           gscale=_times(r.gscale, oma_dev), unpool=r.unpool, want_out=False)
             zero_b = torch.zeros_like(st.conv.bias)
-            cur = ops.d_fade_fwd(cur, ghat_xp, w_old, zero_b, alpha)   # alpha*cur + (1-alpha)*w_old*ghat_xp
+            cur = ops.d_fade_fwd(cur, ghat_xp, w_old, zero_b, a_dev)   # alpha*cur + (1-alpha)*w_old*ghat_xp
             if r.unpool:
                 cur = ops.avgpool2(cur)
     last, head = net.last_conv(), net.head_conv()

@@ -29,6 +29,24 @@ def _p(t, dtype=None):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _scalar(v):
+    """A scalar kernel argument: a float, or (float, 1-element fp32 device tensor) meaning their product with the
+    tensor read by the kernel (the `dyn` pointers of include/ngan_b200.h) -- used for the fade-in coefficient alpha
+    so that a captured graph follows it."""
+    if isinstance(v, tuple):
+        c, t = v
+        assert t.numel() == 1
+        return float(c), _p(t, F32)
+    return float(v), None
+
+
+def scalar_mul(c, v):
+    """float * scalar-argument (see _scalar)."""
+    if isinstance(v, tuple):
+        return (float(c) * v[0], v[1])
+    return float(c) * v
+
+
 def c8_empty(B, C, H, W, device):
     return torch.empty((B, C // 8, H, W, 8), dtype=BF16, device=device)
 
@@ -155,7 +173,8 @@ def pn_bwd(g, y, r, gscale=1.0, unpool=False, addin=None, want_gy=False, leak=0.
     B, C, H, W = c8_dims(y)
     ga = torch.empty_like(y)
     gy = torch.empty_like(y) if want_gy else None
-    _lib.call('ngan_pn_bwd', _p(g, BF16), int(unpool), gscale, _p(y, BF16), _p(r, F32),
+    gs, dyn = _scalar(gscale)
+    _lib.call('ngan_pn_bwd', _p(g, BF16), int(unpool), gs, dyn, _p(y, BF16), _p(r, F32),
               _p(addin, BF16) if addin is not None else None, _p(ga), _p(gy), leak, B, C, H, W, _stream())
     return ga, gy
 
@@ -193,13 +212,15 @@ def up2_image(x):
 def up2_image_bwd(g, scale=1.0):
     B, H2, W2 = g.shape
     out = torch.empty((B, H2 // 2, W2 // 2), dtype=F32, device=g.device)
-    _lib.call('ngan_up2_image_bwd', _p(g, F32), _p(out), scale, B, H2 // 2, W2 // 2, _stream())
+    sc, dyn = _scalar(scale)
+    _lib.call('ngan_up2_image_bwd', _p(g, F32), _p(out), sc, dyn, B, H2 // 2, W2 // 2, _stream())
     return out
 
 
 def lerp(a, b, alpha, out=None):
     out = torch.empty_like(a) if out is None else out
-    _lib.call('ngan_lerp', _p(a, F32), _p(b, F32), alpha, _p(out), a.numel(), _stream())
+    al, dyn = _scalar(alpha)
+    _lib.call('ngan_lerp', _p(a, F32), _p(b, F32), al, dyn, _p(out), a.numel(), _stream())
     return out
 
 
@@ -236,7 +257,8 @@ def fromim_fwd(xp, w, b):
 def d_fade_fwd(y_end, xp, w_old, b_old, alpha):
     B, C, H, W = c8_dims(y_end)
     out = torch.empty_like(y_end)
-    _lib.call('ngan_d_fade_fwd', _p(y_end, BF16), _p(xp, F32), _p(w_old, F32), _p(b_old, F32), alpha, _p(out), B, C,
+    al, dyn = _scalar(alpha)
+    _lib.call('ngan_d_fade_fwd', _p(y_end, BF16), _p(xp, F32), _p(w_old, F32), _p(b_old, F32), al, dyn, _p(out), B, C,
               H, W, _stream())
     return out
 
@@ -244,7 +266,8 @@ def d_fade_fwd(y_end, xp, w_old, b_old, alpha):
 def fromim_bwd(g, xp, w, gw, gb, gscale=1.0, unpool=False, g_img=None, accumulate=False):
     B, H, W = xp.shape
     C = w.numel()
-    _lib.call('ngan_fromim_bwd', _p(g, BF16), int(unpool), gscale, _p(xp, F32), _p(w, F32), _p(gw, F32), _p(gb, F32),
+    gs, dyn = _scalar(gscale)
+    _lib.call('ngan_fromim_bwd', _p(g, BF16), int(unpool), gs, dyn, _p(xp, F32), _p(w, F32), _p(gw, F32), _p(gb, F32),
               _p(g_img, F32), int(accumulate), B, C, H, W, _stream())
 
 
@@ -252,7 +275,8 @@ def fromim_dbl(ghat_xp, g, w, what, in_scale=1.0, gscale=1.0, unpool=False, want
     B, H, W = ghat_xp.shape
     C = w.numel()
     out = c8_empty(B, C, H, W, ghat_xp.device) if want_out else None
-    _lib.call('ngan_fromim_dbl', _p(ghat_xp, F32), in_scale, _p(g, BF16), int(unpool), gscale, _p(w, F32), _p(out),
+    gs, dyn = _scalar(gscale)
+    _lib.call('ngan_fromim_dbl', _p(ghat_xp, F32), in_scale, _p(g, BF16), int(unpool), gs, dyn, _p(w, F32), _p(out),
               _p(what, F32), B, C, H, W, _stream())
     return out
 
@@ -269,7 +293,8 @@ def toim_bwd(g_img, img, y, r, w, gw, gscale=1.0, want_ga=True, want_gpre=False,
     B, C, H, W = c8_dims(y)
     ga = torch.empty_like(y) if want_ga else None
     gpre = torch.empty((B, H, W), dtype=F32, device=y.device) if want_gpre else None
-    _lib.call('ngan_toim_bwd', _p(g_img, F32), gscale, _p(img, F32), _p(y, BF16), _p(r, F32), _p(w, F32), _p(ga),
+    gs, dyn = _scalar(gscale)
+    _lib.call('ngan_toim_bwd', _p(g_img, F32), gs, dyn, _p(img, F32), _p(y, BF16), _p(r, F32), _p(w, F32), _p(ga),
               _p(gpre), _p(gw, F32), leak, B, C, H, W, _stream())
     return ga, gpre
 

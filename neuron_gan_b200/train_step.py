@@ -52,6 +52,8 @@ class TrainStep:
         self._rings = {}
         self._last_key = None
         self._versions_seen = None
+        self._alpha_keep = []           # pinned sources of the last alpha uploads (alive until the copies have run)
+        self.last_run = None            # 'eager' | 'replay': how the last iteration was executed
         self.launches_per_step = 0      # kernels of libngan_b200.so launched (or replayed) by the last iteration
         self.inputs_loaded = None       # CUDA event: this iteration's host-to-device copies (images, draws, Adam scalars)
                                         # are done -- a loader may start its next big copy behind it (DevicePrefetcher)
@@ -229,12 +231,28 @@ class TrainStep:
         self._versions_seen = None
         return self._seg_end(buf)
 
+    def _sync_alpha(self, dev):
+        """Keep [alpha, 1 - alpha] of each network in device memory (engine._alpha_terms): the fade-in coefficient
+        advances every epoch (train.py:318-321) and must not force a new graph each time."""
+        for net in (self.G, self.D):
+            a = net.alpha_value()
+            if getattr(net, '_ngan_alpha_dev', None) is None or net._ngan_alpha_dev.device != dev:
+                net._ngan_alpha_dev = torch.zeros(2, dtype=F32, device=dev)
+                net._ngan_alpha_dev_value = None
+            if net._ngan_alpha_dev_value != a:
+                src = torch.tensor([a, 1.0 - a], dtype=torch.float64).to(F32).pin_memory()
+                net._ngan_alpha_dev.copy_(src, non_blocking=True)
+                net._ngan_alpha_dev_value = a
+                self._alpha_keep = self._alpha_keep[-3:] + [src]
+
     # -- CUDA-graph capture ----------------------------------------------------------------------------------
     def _versions(self):
         return tuple(p._version for net in (self.G, self.D) for p in net.parameters())
 
     def _config_key(self, B, R):
-        return (B, R, self.G.alpha_value(), self.D.alpha_value(), self.G.N_layers, self.D.N_layers, self.dp,
+        # alpha itself is NOT part of the key: the kernels read it from device memory (_sync_alpha), so one graph
+        # serves every epoch of a fade-in; only whether a fade is in progress changes the kernel sequence
+        return (B, R, self.G.alpha_value() < 1, self.D.alpha_value() < 1, self.G.N_layers, self.D.N_layers, self.dp,
                 self.lam, self.drift,
                 tuple(id(p) for p in self.G.active_parameters()), tuple(id(p) for p in self.D.active_parameters()))
 
@@ -280,7 +298,10 @@ class TrainStep:
         [D_loss, score_real, score_fake, G_loss, D_grad_pen] (D_loss includes the penalty, train.py:362)."""
         dev = next(self.G.parameters()).device
         if self.n_critic != 1:
+            self._sync_alpha(dev)
+            self.last_run = 'eager'
             return self._run_multi_critic(images, draws, dev)
+        self._sync_alpha(dev)
         B, R = images.shape[0], images.shape[-1]
         z1, z2, eps, z3 = draws if draws is not None else self.draw_host(B)
         key = self._config_key(B, R)
@@ -296,6 +317,7 @@ class TrainStep:
             if self.use_graph is not False and ent is None and key == self._last_key:
                 self._capture(key, B, R, dev)
             self._last_key = key
+            self.last_run = 'eager'
             return stats.clone() if ent is not None else stats
         self._graphs[key] = self._graphs.pop(key)                 # most recently used last
         self._load(ent.buf, images, z1, z2, eps, z3)
@@ -323,6 +345,7 @@ class TrainStep:
             if ev:
                 ev[3].record()
         self._last_key = key
+        self.last_run = 'replay'
         self.launches_per_step = ent.launches
         _lib.launch_count += ent.launches
         return ent.stats.clone()

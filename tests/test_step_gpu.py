@@ -327,10 +327,13 @@ def test_progressive_schedule_through_a_transition():
     G.increase_resolution()
     D.increase_resolution()
     assert G.image_size == D.image_size == 32 and G.alpha_value() == 0.0
+    modes = []
     for _ in range(3):                                    # alpha: 0.25, 0.5, 0.75 (one iteration each, like an epoch)
         G.advance_transition(0.25)
         D.advance_transition(0.25)
         run(1, 32)
+        modes.append(step.last_run)
+    assert modes == ['eager', 'eager', 'replay']
     assert step.opt_g.state[new_g]['step'] == 3 and not torch.equal(new_g.detach(), w_before)
     G.advance_transition(0.25)                            # alpha reaches 1: the block moves into `layers`
     D.advance_transition(0.25)
@@ -338,7 +341,9 @@ def test_progressive_schedule_through_a_transition():
     run(3, 32)
     assert step.opt_g.state[new_g]['step'] == 6
     assert step.opt_d.state[D.head_conv().weight]['step'] == 9      # the trunk trained in every iteration
-    assert len(seen_keys) == 5 and len(step._graphs) == 2             # graphs only for the two repeated configurations
+    # three configurations (16 stable, 32 fading, 32 stable): alpha is read from device memory, so the three fade-in
+    # iterations at alpha = 0.25, 0.5, 0.75 share one key -- and one graph, replayed for the third of them
+    assert len(seen_keys) == 3 and len(step._graphs) == 3
 
 
 def test_host_input_path_equals_device_input_path():
@@ -439,3 +444,47 @@ def test_adaptive_critic_count_between_calls():
         stats = step(x)
     assert torch.isfinite(stats).all()
     assert any(not torch.equal(v, d_before[k]) for k, v in D.state_dict().items())
+
+
+def test_captured_graph_follows_alpha():
+    """During a fade-in alpha advances every epoch (train.py:318-321).  The graph captured at alpha = 0.25 is replayed
+    at alpha = 0.75 -- the kernels read alpha from device memory -- and must do what a kernel-by-kernel iteration at
+    alpha = 0.75 does from the same weights, optimiser state, images and draws."""
+    from neuron_gan_b200.train_step import TrainStep
+    res, batch = 64, 4
+    G, D = nets(res, 0.25)
+    step = TrainStep(G, D)
+    xs = [O.synthetic_images(batch, res, seed=80 + i).to(DEV) for i in range(3)]
+    draws = [tuple(t.to(DEV) for t in draws_like_reference(batch)) for _ in range(3)]
+    step(xs[0], draws[0])
+    step(xs[1], draws[1])
+    assert len(step._graphs) == 1 and step.last_run == 'eager'
+    G.advance_transition(0.5)
+    D.advance_transition(0.5)
+    assert G.alpha_value() == 0.75 and G.image_size == res and len(G.conv_block_list) > 0
+    snap = _snapshot((G, D), (step.opt_g, step.opt_d))
+    s_replay = step(xs[2], draws[2]).cpu()
+    assert step.last_run == 'replay' and len(step._graphs) == 1
+    after_replay = [[p.detach().clone() for p in n.parameters()] for n in (G, D)]
+    _restore((G, D), (step.opt_g, step.opt_d), snap)
+    # the restore bumped the parameter versions -> the next call runs kernel by kernel; make it use plain host-side
+    # float scalars for alpha (no device table), i.e. the path every non-graph caller takes
+    G._ngan_alpha_dev_value = D._ngan_alpha_dev_value = None
+    sync, step._sync_alpha = step._sync_alpha, lambda dev: None
+    s_eager = step(xs[2], draws[2]).cpu()
+    step._sync_alpha = sync
+    assert step.last_run == 'eager'
+    tight = [0, 1, 2, 4]
+    assert torch.allclose(s_replay[tight], s_eager[tight], rtol=1e-4, atol=2e-5), (s_replay, s_eager)
+    assert abs(s_replay[3] - s_eager[3]).item() <= 3e-4, (s_replay, s_eager)
+    for n, saved in zip((G, D), after_replay):
+        for (k, p), v in zip(n.named_parameters(), saved):
+            d = (p.detach() - v).abs()
+            assert d.max().item() <= 2.3e-4 and d.mean().item() < 6e-6, (k, d.max().item(), d.mean().item())
+    # the comparison has teeth: the same iteration at the alpha the graph was captured with gives other statistics
+    _restore((G, D), (step.opt_g, step.opt_d), snap)
+    with torch.no_grad():
+        G.alpha.fill_(0.25)
+        D.alpha.fill_(0.25)
+    s_stale = step(xs[2], draws[2]).cpu()
+    assert (s_stale[tight] - s_replay[tight]).abs().max().item() > 1e-3, (s_stale, s_replay)
