@@ -46,8 +46,7 @@ for size in (512, 256, 128, 64, 32, 16):
     it._prepare()
     n_rep = 20
     t0 = time.perf_counter()
-    tables = torch.from_numpy(np.stack([np.stack([data.draw_augment_params(P, 0.05) for _ in range(B)])
-                                        for _ in range(n_rep)])).cuda()
+    tables = torch.from_numpy(np.stack([data.draw_augment_params_batch(B, P, 0.05) for _ in range(n_rep)])).cuda()
     host_ms = (time.perf_counter() - t0) / n_rep * 1e3
     index = torch.arange(B, dtype=torch.int32, device='cuda')
     out = torch.empty(B, 1, size, size, device='cuda')

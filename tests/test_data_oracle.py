@@ -115,3 +115,21 @@ def test_dataset_mirror_bookkeeping():
         data.NeuronImages(torch.rand(3, 3, 96, 96), image_size=64)
     with pytest.raises(NganError):                  # no CPU fallback
         data.DatasetIterator(ds, 2, torch.device('cpu'))
+
+
+@pytest.mark.parametrize('seed,warm,n', [(0, 0, 1), (1, 5, 16), (2, 617, 64), (3, 1000, 70), (4, 3, 139)])
+def test_batched_param_draw_is_bit_identical_to_the_per_image_draw(seed, warm, n):
+    """data.draw_augment_params_batch generates the MT19937 outputs itself (torch.get/set_rng_state): same parameter
+    rows AND same generator state afterwards as n per-image draws, across state regenerations (624 outputs)."""
+    from neuron_gan_b200 import data
+    torch.manual_seed(seed)
+    torch.rand(warm)                               # start somewhere inside the 624-word state
+    start = torch.get_rng_state()
+    slow = np.stack([data.draw_augment_params(96, 0.05) for _ in range(n)])
+    after_slow, next_slow = torch.get_rng_state(), torch.randn(4)
+    torch.set_rng_state(start)
+    fast = data.draw_augment_params_batch(n, 96, 0.05)
+    assert data._fast_draws_ok is True             # the fast path is live on this torch build
+    assert torch.equal(torch.get_rng_state(), after_slow)
+    assert np.array_equal(fast, slow)
+    assert torch.equal(torch.randn(4), next_slow)  # latent draws that follow see the same stream
