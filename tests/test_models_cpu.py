@@ -125,3 +125,25 @@ def test_latent_sampler_matches_oracle_and_memoises():
     assert torch.allclose(a.norm(dim=1), torch.ones(4))
     with pytest.raises(ValueError):
         utils.sample_latent_vec((2, 4), mode='bogus')
+
+
+def test_launcher_schedule_and_options_on_cpu():
+    """Host logic of neuron_gan_b200/launch.py that needs no GPU: the learning-rate ramp (train.py:238-265; compared with
+    the reference's own function in tests/test_oracle_vs_reference.py) and the option defaults (configs/config.py)."""
+    import math
+    from neuron_gan_b200.launch import LrSchedule, TrainConfig
+    cfg = TrainConfig()
+    assert (cfg.learning_rate, cfg.beta1, cfg.grad_pen_lambda, cfg.drift_epsilon) == (1e-4, 0.5, 10, 1e-3)
+    assert cfg.transit_sch == [25000, 50000, 75000, 100000, 125000] and cfg.alpha_step == 1e-4 and cfg.batch_size == 8
+    s = LrSchedule(1e-4, [10, 20], 30)
+    assert s.value(0) == s.value(10) == s.value(20) == s.value(30) == 1e-4            # phase boundaries reset
+    assert math.isclose(s.value(5), 1e-6, rel_tol=1e-9)                               # 1/100 at mid-phase
+    assert math.isclose(s.value(1), 1e-4 * 0.01 ** (1 / 5), rel_tol=1e-12)
+    assert s.value(6) is None and s.value(9) is None                                  # second half: left alone
+    assert math.isclose(s.value(13), 1e-4 * 0.01 ** (3 / 5), rel_tol=1e-12)
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1e-4)
+    seen = []
+    for epoch in range(0, 12):
+        s.apply(opt, epoch)
+        seen.append(opt.param_groups[0]['lr'])
+    assert seen[5] == seen[6] == seen[9] and seen[10] == 1e-4 and seen[11] < 1e-4
