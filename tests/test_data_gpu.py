@@ -12,11 +12,13 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'data_pipeline_golden.pt')
 
 
-def _close(got, want, what):
-    """Nearest-neighbour resampling is discontinuous (oracle/data_oracle.py header): at most 1 pixel in 1000 may
-    differ by more than 1e-5; the rest agrees to float rounding of the filter sums."""
+def _close(got, want, crop):
+    """Nearest-neighbour resampling is discontinuous (oracle/data_oracle.py header): a source coordinate on a
+    half-integer to within float rounding may pick the other neighbour.  Allow 1 source pixel in 4000 per image to do
+    so, each reaching at most 2x2 antialiased outputs; everything else agrees to float rounding of the filter sums."""
     d = np.abs(got - want)
-    assert (d > 1e-5).mean() <= 1e-3 and np.median(d) <= 1e-6, (what, d.max(), (d > 1e-5).mean())
+    allowed = got.shape[0] * 4 * int(np.ceil(2.5e-4 * crop * crop))
+    assert (d > 1e-5).sum() <= allowed and np.median(d) <= 2e-6, (crop, d.max(), (d > 1e-5).sum(), allowed)
 
 
 def test_reference_batches():
@@ -30,7 +32,7 @@ def test_reference_batches():
         got = [b.cpu().clone() for b in it]
         assert [tuple(b.shape) for b in got] == [tuple(b.shape) for b in ep['batches']]
         for a, b in zip(got, ep['batches']):
-            _close(a.numpy(), b.numpy(), ep['size'])
+            _close(a.numpy(), b.numpy(), g['image_size_max'])
     ds2 = data.NeuronImages(g['canvases'], g['image_size_max'], False)
     ds2.set_image_size(16)
     for a, b in zip(data.DatasetIterator(ds2, g['batch_size'], 'cuda'), g['plain16']):
@@ -53,8 +55,25 @@ def test_full_geometry_vs_oracle(size):
     want = [b for b, _ in do.epoch_batches(cv, 2, 512, size, 0.05)]
     assert [b.shape for b in got] == [b.shape for b in want] == [(2, 1, size, size), (1, 1, size, size)]
     for a, b in zip(got, want):
-        _close(a, b, size)
+        _close(a, b, 512)
         assert a.min() >= -1.0 and a.max() <= 1.0
+
+
+@pytest.mark.parametrize('canvas,crop,size', [(97, 64, 64), (97, 64, 16), (75, 50, 50), (75, 50, 20), (100, 64, 32)])
+def test_odd_geometries_vs_oracle(canvas, crop, size):
+    """canvas - crop odd: the crop window and its mirror under the vertical flip differ by one row (the staging window
+    of csrc/augment.cu then holds crop + 1 rows); sizes that are not powers of two."""
+    from neuron_gan_b200 import data
+    cv = torch.rand(5, canvas, canvas, generator=torch.Generator().manual_seed(canvas + size)).numpy()
+    ds = data.NeuronImages(torch.from_numpy(cv), crop, True, 0.05)
+    ds.set_image_size(size)
+    torch.manual_seed(canvas * size)
+    got = [b.cpu().numpy().copy() for b in data.DatasetIterator(ds, 3, 'cuda')]
+    torch.manual_seed(canvas * size)
+    want = [b for b, _ in do.epoch_batches(cv, 3, crop, size, 0.05)]
+    for a, b in zip(got, want):
+        assert a.shape == b.shape
+        _close(a, b, crop)
 
 
 def test_rank_sharding_matches_single_process():
