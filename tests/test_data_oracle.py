@@ -115,6 +115,15 @@ def test_dataset_mirror_bookkeeping():
         data.NeuronImages(torch.rand(3, 3, 96, 96), image_size=64)
     with pytest.raises(NganError):                  # no CPU fallback
         data.DatasetIterator(ds, 2, torch.device('cpu'))
+    # from a loaded reference dataset: a list of [1, P, P] tensors ([1, 1, P, P] once its own iterator has run)
+    import types
+    ref_like = types.SimpleNamespace(images=[torch.rand(1, 96, 96), torch.rand(1, 1, 96, 96)], image_size_max=64,
+                                     load_all=True)
+    ds2 = data.NeuronImages.from_dataset(ref_like, im_translation=0.05)
+    assert ds2.canvases.shape == (2, 96, 96) and ds2.image_size == 64 and ds2.im_translation == 0.05
+    assert torch.equal(ds2.canvases[1], ref_like.images[1][0, 0])
+    with pytest.raises(Exception, match='only possible when all images are loaded'):
+        data.NeuronImages.from_dataset(types.SimpleNamespace(images=[], image_size_max=64, load_all=False))
 
 
 @pytest.mark.parametrize('seed,warm,n', [(0, 0, 1), (1, 5, 16), (2, 617, 64), (3, 1000, 70), (4, 3, 139)])
