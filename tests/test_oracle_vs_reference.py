@@ -130,3 +130,40 @@ def test_lr_schedule_matches_the_reference_update_lr():
             env['update_lr'](ref_opt, epoch)
             sched.apply(my_opt, epoch)
             assert ref_opt.param_groups[0]['lr'] == my_opt.param_groups[0]['lr'], (transit_sch, epoch)
+
+
+def test_generator_legacy_checkpoint_surgery_matches_the_reference(tmp_path):
+    """from_state_dict on an OLD-format generator checkpoint (already-merged modules still in ToIm_list /
+    conv_block_list, plus ToIm_prev.* and last_conv_block.* keys; reference models.py:411-436 with
+    pop_state_dict_modules, models.py:37-63): same surviving keys and tensors as the reference's loader."""
+    import os
+    from collections import OrderedDict
+    from neuron_gan_b200 import models as my_models
+    ref_models, _, ref_utils = rh.load()
+    torch.manual_seed(3)
+    G = ref_models.Generator_PG([32, 16, 16, 8], image_size_init=16)
+    G.set_resolution(64, 1.0)
+    new_sd = G.state_dict()
+    old_sd = OrderedDict()
+    extra = 2                                     # two merged modules that the old format kept at the list heads
+    for k, v in new_sd.items():
+        for name in ('ToIm_list.', 'conv_block_list.'):
+            if k.startswith(name):
+                rest = k[len(name):]
+                i, tail = rest.split('.', 1)
+                k = f'{name}{int(i) + extra}.{tail}'
+        old_sd[k] = v
+    for i in range(extra):
+        old_sd[f'ToIm_list.{i}.layers.0.weight'] = torch.randn(1, 8, 1, 1)
+        old_sd[f'conv_block_list.{i}.1.weight'] = torch.randn(8, 8, 3, 3)
+        old_sd[f'conv_block_list.{i}.4.weight'] = torch.randn(8, 8, 3, 3)
+    old_sd['ToIm_prev.layers.0.weight'] = torch.randn(1, 16, 1, 1)
+    old_sd['last_conv_block.1.weight'] = torch.randn(16, 16, 3, 3)
+    old_sd['last_conv_block.4.weight'] = torch.randn(16, 16, 3, 3)
+    path = os.path.join(tmp_path, 'old.pth')
+    torch.save({'Generator_attrs': ref_utils.get_saved_attrs(G), 'Generator_state': old_sd}, path)
+    theirs = ref_models.Generator_PG.from_state_dict(path, verbose=False).state_dict()
+    mine = my_models.Generator_PG.from_state_dict(path, verbose=False).state_dict()
+    assert list(mine.keys()) == list(theirs.keys()) == list(new_sd.keys())
+    for k in theirs:
+        assert torch.equal(mine[k], theirs[k]) and torch.equal(mine[k], new_sd[k]), k
