@@ -11,7 +11,10 @@ What is mirrored, with the reference's option names (configs/config.py:19-56): p
 resolution schedule (`transit_sch`, `alpha_step`; train.py:318-333), `n_critic` / `adapt_critic` (train.py:336-340),
 the learning-rate ramp of `update_lr` (train.py:238-265), per-epoch statistics weighted by batch size and divided by
 the dataset size (train.py:388-399), reference-format checkpoints every `checkpointing_period` epochs with a sample
-grid (train.py:432-444) -- on rank 0 only.  Plots, the memory logger and the config-file machinery are not.
+grid (train.py:432-444) -- on rank 0 only -- and `--resume` (train.py:202-204).  Plots, the memory logger and the
+config-file machinery are not.  One deliberate difference: `adapt_critic` looks at the scores of the epochs actually run;
+the reference indexes its preallocated N_epochs-long arrays (train.py:336-338), whose last `Period` entries are zeros
+until the very end of training (0/0 in Calculate_D_steps).
 
 Data parallel: `batch_size` is the GLOBAL batch; every rank holds the canvases, draws the whole batch's augmentation
 parameters and latents on identically seeded CPU generators, and keeps its rows (data.DatasetIterator, dp.global_draws);
@@ -183,6 +186,23 @@ def pggan_train(cfg: TrainConfig, images: NeuronImages, Generator_net, Discrimin
     return history
 
 
+def open_checkpoint(cfg, Generator_net, Discriminator_net, weights_dir, resume, device):
+    """train.py:195-208: a Checkpointer on <weights_dir>/GenDisc.pth and, with `resume` and the file present, the whole
+    last training state restored into the networks (weights, resolution, alpha) and the loss series.  Every rank
+    loads (the replicas must start identical); only rank 0 writes (pggan_train).  Like the reference's checkpoints
+    there is no optimiser state: Adam restarts.  Returns (checkpointer or None, first epoch to run)."""
+    if not weights_dir:
+        return None, 1
+    os.makedirs(weights_dir, exist_ok=True)
+    path = os.path.join(weights_dir, 'GenDisc.pth')
+    checkpoint = Checkpointer(Generator_net, Discriminator_net, cfg.learning_rate, path, N_epochs=cfg.N_epochs,
+                              device=device, verbose=False)
+    if resume and os.path.exists(path):
+        checkpoint.load_state()
+        return checkpoint, checkpoint.epoch + 1
+    return checkpoint, 1
+
+
 def synthetic_images(n, image_size, seed=0):
     """Stand-in canvases (no dataset ships with the repository): smooth random fields in [0, 1], padded like
     NeuronDataset pads (image_size // 4 per side)."""
@@ -196,6 +216,7 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split('\n')[0])
     ap.add_argument('--synthetic', type=int, default=64, help='number of synthetic canvases to train on')
     ap.add_argument('--weights_dir', default=None, help='write reference-format checkpoints here (rank 0)')
+    ap.add_argument('--resume', action='store_true', help='continue from <weights_dir>/GenDisc.pth if it exists')
     for name, f in TrainConfig.__dataclass_fields__.items():
         default = f.default if f.default_factory is dataclass_missing() else f.default_factory()
         if isinstance(default, list):
@@ -215,13 +236,9 @@ def main(argv=None):
     G, D = build_networks(size_init, 1.0, seed=cfg.seed, device=device, gen_features=cfg.N_gen_features,
                           dis_features=cfg.N_dis_features, image_size=cfg.image_size)
     images = NeuronImages(synthetic_images(args.synthetic, cfg.image_size), cfg.image_size, True, cfg.translation)
-    checkpoint = None
-    if args.weights_dir and rank == 0:
-        os.makedirs(args.weights_dir, exist_ok=True)
-        checkpoint = Checkpointer(G, D, cfg.learning_rate, os.path.join(args.weights_dir, 'GenDisc.pth'),
-                                  N_epochs=cfg.N_epochs, device=device, verbose=False)
-    torch.manual_seed(cfg.seed + 1)          # the augmentation / latent stream, identical on every rank
-    history = pggan_train(cfg, images, G, D, checkpoint, rank=rank, world=world)
+    checkpoint, epoch_init = open_checkpoint(cfg, G, D, args.weights_dir, args.resume, device)
+    torch.manual_seed(cfg.seed + epoch_init)  # the augmentation / latent stream, identical on every rank
+    history = pggan_train(cfg, images, G, D, checkpoint, rank=rank, world=world, epoch_init=epoch_init)
     if rank == 0:
         last = history[-1]
         print('done: epoch {epoch}, {image_size}x{image_size}, alpha {alpha:.3f}, D_loss {D_loss:.4g}, '

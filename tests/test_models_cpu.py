@@ -147,3 +147,37 @@ def test_launcher_schedule_and_options_on_cpu():
         s.apply(opt, epoch)
         seen.append(opt.param_groups[0]['lr'])
     assert seen[5] == seen[6] == seen[9] and seen[10] == 1e-4 and seen[11] < 1e-4
+
+
+def test_launcher_resume_restores_the_last_training_state(tmp_path):
+    """launch.open_checkpoint (train.py:195-208) on CPU modules: a state saved mid fade-in at 32x32 comes back into
+    freshly built 16x16 networks -- resolution, alpha, weights, loss series -- and training continues at epoch + 1."""
+    from neuron_gan_b200 import models
+    from neuron_gan_b200.launch import TrainConfig, open_checkpoint
+    cfg = TrainConfig(N_gen_features=[32, 16, 16], N_dis_features=[16, 16, 32], image_size=64, N_epochs=20)
+
+    def fresh(seed):
+        torch.manual_seed(seed)
+        return (models.Generator_PG(list(cfg.N_gen_features), image_size_init=16),
+                models.Discriminator_PG(list(cfg.N_dis_features), image_size_init=16))
+
+    G, D = fresh(1)
+    for net in (G, D):
+        net.increase_resolution()
+        net.advance_transition(0.25)
+    ckpt, first = open_checkpoint(cfg, G, D, str(tmp_path), resume=True, device=torch.device('cpu'))
+    assert first == 1 and ckpt is not None                     # nothing to resume from yet
+    ckpt.Loss_real[:6] = torch.arange(6).numpy()
+    ckpt.save_state(6)
+    G2, D2 = fresh(2)
+    assert G2.image_size == 16 and not torch.equal(G2.state_dict()['layers.0.weight'], G.state_dict()['layers.0.weight'])
+    ckpt2, first2 = open_checkpoint(cfg, G2, D2, str(tmp_path), resume=True, device=torch.device('cpu'))
+    assert first2 == 7 and ckpt2.epoch == 6 and list(ckpt2.Loss_real[:6]) == [0, 1, 2, 3, 4, 5]
+    assert G2.image_size == D2.image_size == 32 and abs(float(G2.alpha) - 0.25) < 1e-7 and abs(float(D2.alpha) - 0.25) < 1e-7
+    for a, b in ((G, G2), (D, D2)):
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa.keys()) == list(sb.keys())
+        assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    _, first3 = open_checkpoint(cfg, *fresh(3), str(tmp_path), resume=False, device=torch.device('cpu'))
+    assert first3 == 1
+    assert open_checkpoint(cfg, G, D, None, True, torch.device('cpu')) == (None, 1)
