@@ -14,7 +14,14 @@
  *  - "c8" tensors are bf16 feature maps in C8-planar layout [B][C/8][H][W][8] (16-byte granules of 8 consecutive
  *    channels); C must be a multiple of 16 for the conv kernels.  Images, scores, PixelNorm scales `r`
  *    ([B][H][W]) and all parameters / gradients are fp32 in the reference's (torch) layouts.
- *  - parameter-gradient outputs (gw, gb, dw, what) ACCUMULATE (+=); the caller zeroes them once per step.
+ *  - parameter-gradient outputs (gw, gb, dw, what) are produced WITHOUT atomics, so they are bit-reproducible:
+ *    the kernel writes per-block partial sums into a caller-provided fp32 `workspace` (sized by the matching
+ *    *_workspace_bytes query) and a second launch adds the partials in index order; `accumulate` != 0 adds the
+ *    result to the output, 0 overwrites it (no prior zeroing needed).  Two launches that accumulate into the SAME
+ *    tensor must be ordered by the caller (they read-modify-write it); concurrent contributions go to separate
+ *    tensors that are summed afterwards (ngan_sum_slots) -- neuron_gan_b200/train_step.py does that for the three
+ *    contributions to every critic parameter (Wasserstein backward, and the two sweeps of the penalty's double
+ *    backward, loss_functions.py:175 + train.py:365).
  *  - the conv kernels are launched with the programmatic-stream-serialization attribute: their prologue may overlap
  *    the tail of the previous kernel in the stream, their first global-memory access waits for it
  *    (griddepcontrol.wait), so stream order is preserved for any caller; NGAN_NO_PDL=1 in the environment disables it.
@@ -77,11 +84,26 @@ int ngan_conv3x3_dgrad_pn(const void* ga_c8, const void* w_dgrad, float scale, f
 int ngan_conv3x3_dbl(const void* ghat_x_c8, const void* w_fwd, float scale, float leak, const void* y_c8,
                      const float* r, const void* gy_c8, void* ghat_y_c8, void* ahat_c8, int B, int cin, int cout,
                      int H, int W, void* stream);
-/* dw[cout][cin][3][3] += scale * corr(x, ga): convolution_backward (weight gradient) of models.py:204 */
-int ngan_conv3x3_wgrad(const void* x_c8, const void* ga_c8, float scale, float* dw, int B, int cin, int cout, int H,
-                       int W, void* stream);
-/* gb[c] += sum_{b,y,x} ga: bias gradient of the biased 128->128 conv, models.py:469-471 */
-int ngan_bias_grad(const void* ga_c8, float* gb, int B, int C, int H, int W, void* stream);
+/* dw[cout][cin][3][3] (+)= scale * corr(x, ga): convolution_backward (weight gradient) of models.py:204.
+ * Two launches: the persistent mma.sync kernel writes one partial dW image per pixel CTA into `workspace`
+ * (ngan_conv3x3_wgrad_workspace_bytes), ngan_reduce_partials adds them in order. */
+long long ngan_conv3x3_wgrad_workspace_bytes(int B, int cin, int cout, int H, int W);
+int ngan_conv3x3_wgrad(const void* x_c8, const void* ga_c8, float scale, float* dw, int accumulate, float* workspace,
+                       int B, int cin, int cout, int H, int W, void* stream);
+/* upper bound of the workspace any of the per-pixel parameter-gradient reductions below (bias_grad, fromim_bwd,
+ * fromim_dbl, toim_bwd) needs on a [B][C][H][W] tensor */
+long long ngan_pixel_reduction_workspace_bytes(int B, int C, int H, int W);
+/* gb[c] (+)= sum_{b,y,x} ga: bias gradient of the biased 128->128 conv, models.py:469-471 */
+int ngan_bias_grad(const void* ga_c8, float* gb, int accumulate, float* workspace, int B, int C, int H, int W,
+                   void* stream);
+/* out[i] (+)= scale * sum_p partials[p*ld + i], i < n, rows added in index order (the second stage of every
+ * parameter-gradient reduction; exported for hosts that want to place it on another stream) */
+int ngan_reduce_partials(const float* partials, int n_partials, long long n, long long ld, float scale, float* out,
+                         int accumulate, void* stream);
+/* out[i] = slots[i] + slots[ld + i] + ... (n_slots terms, in slot order) */
+int ngan_sum_slots(const float* slots, int n_slots, long long n, long long ld, float* out, void* stream);
+/* cudaMemsetAsync through the C ABI (gradient-slot zeroing inside a captured iteration; D.zero_grad(), train.py:357) */
+int ngan_memset(void* dst, int value, long long bytes, void* stream);
 
 /* ---- resampling: Interpolate(x2, bilinear) models.py:78-89, 257; AvgPool2d(2) models.py:254 ---- */
 int ngan_upsample2x(const void* x_c8, void* out_c8, int B, int C, int H, int W, void* stream);
@@ -110,27 +132,30 @@ int ngan_scale_rows(const float* x, const float* coeff, float scale, float* out,
 /* ---- FromImage / ToImage 1x1 convolutions, models.py:133-165 ---- */
 int ngan_fromim_fwd(const float* xp, const float* w, const float* b, void* out_c8, int B, int C, int H, int W,
                     void* stream);
-/* discriminator fade-in, models.py:519-521: out = y_start + alpha*(y_end - y_start), y_start = FromIm_old(xp) */
+/* discriminator fade-in, models.py:519-521: out = y_start + alpha*(y_end - y_start), y_start = FromIm_old(xp);
+ * b_old may be NULL (no bias: the double backward reuses the kernel for the bias-free cotangent blend) */
 int ngan_d_fade_fwd(const void* y_end_c8, const float* xp, const float* w_old, const float* b_old, float alpha,
                     const float* dyn, void* out_c8, int B, int C, int H, int W, void* stream);
 int ngan_fromim_bwd(const void* g_c8, int unpool, float gscale, const float* dyn, const float* xp, const float* w, float* gw, float* gb,
-                    float* g_img, int g_img_accumulate, int B, int C, int H, int W, void* stream);
+                    int grad_accumulate, float* workspace, float* g_img, int g_img_accumulate, int B, int C, int H,
+                    int W, void* stream);
 int ngan_fromim_dbl(const float* ghat_xp, float in_scale, const void* g_c8, int unpool, float gscale,
                     const float* dyn, const float* w,
-                    void* ghat_out_c8, float* what, int B, int C, int H, int W, void* stream);
+                    void* ghat_out_c8, float* what, int grad_accumulate, float* workspace, int B, int C, int H, int W,
+                    void* stream);
 int ngan_toim_fwd(const void* y_c8, const float* w, float* img, int B, int C, int H, int W, void* stream);
 int ngan_toim_bwd(const float* g_img, float gscale, const float* dyn, const float* img, const void* y_c8, const float* r,
-                  const float* w, void* ga_c8, float* gpre, float* gw, float leak, int B, int C, int H, int W,
-                  void* stream);
+                  const float* w, void* ga_c8, float* gpre, float* gw, int grad_accumulate, float* workspace, float leak,
+                  int B, int C, int H, int W, void* stream);
 
 /* ---- critic head: Conv2d_normalized(F -> 1, kernel S x S, pad 0) + Flatten, models.py:485-490 ---- */
 int ngan_head_fwd(const void* y_c8, const float* w, const float* bias, float scale, float* score, int B, int C,
                   int S, void* stream);
 int ngan_head_bwd_pn(const float* gout, const float* w, float scale, const void* y_c8, const float* r, void* ga_c8,
                      void* gy_out_c8, float leak, int B, int C, int S, void* stream);
-/* gw[c,p] += scale * sum_b coeff[b] * t[b,c,p] (atomics); gb (optional): gb[0] += sum_b coeff[b], the bias gradient */
-int ngan_head_wgrad(const void* t_c8, const float* coeff, float scale, float* gw, float* gb, int B, int C, int S,
-                    void* stream);
+/* gw[c,p] (+)= scale * sum_b coeff[b] * t[b,c,p]; gb (optional): gb[0] (+)= sum_b coeff[b], the bias gradient */
+int ngan_head_wgrad(const void* t_c8, const float* coeff, float scale, float* gw, float* gb, int accumulate, int B,
+                    int C, int S, void* stream);
 
 /* ---- generator stem: Linear_normalized + Unflatten + LeakyReLU + PixelNorm, models.py:299-311 ---- */
 /* fp32 master [C*S*S][K] -> bf16 operand image [S*S][K/8][C][8] (the C weight rows of one pixel form one
@@ -149,9 +174,11 @@ int ngan_linear_wgrad(const void* ga_c8, const float* z, float scale, float* dw,
 int ngan_wloss(const float* s_real, const float* s_fake, float drift, float* out3, float* g_real, float* g_fake,
                float gscale, int B, void* stream);
 int ngan_gloss(const float* s_fake, float* out1, float* g_fake, float gscale, int B, void* stream);
-/* pen = lambda*mean_b((norm_scale*||g_b|| - 1)^2); coeff_b = gscale * dpen/dnorm_b / norm_b */
-int ngan_gp_loss(const float* g, float norm_scale, float lambda, float* pen, float* coeff, float gscale, int B,
-                 long long per_sample, void* stream);
+/* pen = lambda*mean_b((norm_scale*||g_b|| - 1)^2); coeff_b = gscale * dpen/dnorm_b / norm_b (0 where the norm is 0,
+ * torch's subgradient).  workspace: ngan_gp_loss_workspace_bytes(B) bytes for the per-sample partial sums. */
+long long ngan_gp_loss_workspace_bytes(int B);
+int ngan_gp_loss(const float* g, float norm_scale, float lambda, float* pen, float* coeff, float gscale,
+                 float* workspace, int B, long long per_sample, void* stream);
 
 /* stats[5] = {D_loss + pen, score_real, score_fake, G_loss, pen}: train.py:362 and the six .item() reads of
  * train.py:389-394 as one packed device tensor */

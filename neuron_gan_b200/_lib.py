@@ -64,9 +64,13 @@ def load():
     return lib
 
 
-_QUERIES = {'ngan_linear_fwd_workspace_bytes', 'ngan_augment_workspace_bytes', 'ngan_conv_weight_is_folded', 'ngan_version'}   # no launch, value returned
-# kernels launched per C-ABI call (everything not listed launches exactly one)
-_LAUNCHES = {'ngan_gp_loss': 2, 'ngan_augment_batch': 3}
+_QUERIES = {'ngan_linear_fwd_workspace_bytes', 'ngan_augment_workspace_bytes', 'ngan_conv_weight_is_folded', 'ngan_version',
+            'ngan_conv3x3_wgrad_workspace_bytes', 'ngan_pixel_reduction_workspace_bytes',
+            'ngan_gp_loss_workspace_bytes'}   # no launch, value returned
+# kernels launched per C-ABI call (everything not listed launches exactly one; callers pass `launches=` where the
+# count depends on the arguments, e.g. one reduction per requested parameter gradient)
+_LAUNCHES = {'ngan_gp_loss': 2, 'ngan_augment_batch': 3, 'ngan_conv3x3_wgrad': 2, 'ngan_bias_grad': 2,
+             'ngan_memset': 0}
 launch_count = 0          # running count of kernels launched through this binding (bench.py reads it)
 _profile = None           # when a list: (name, int args, start event, end event) per call
 
@@ -87,7 +91,7 @@ def stop_profile():
     return out
 
 
-def call(name, *args):
+def call(name, *args, launches=None):
     global launch_count
     lib = load()
     if _profile is not None:
@@ -99,7 +103,7 @@ def call(name, *args):
         return rc
     if rc != 0:
         raise NganError(f'{name} failed ({rc}): {lib.ngan_last_error().decode()}')
-    launch_count += _LAUNCHES.get(name, 1)
+    launch_count += _LAUNCHES.get(name, 1) if launches is None else launches
     if _profile is not None:
         e1.record()
         _profile.append((name, tuple(a for a in args if isinstance(a, int)), e0, e1))

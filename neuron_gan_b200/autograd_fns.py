@@ -82,6 +82,7 @@ class _CriticBackwardFn(Function):
         ghat_xp = ops.pool_image(gh) if ectx.pooled else gh
         sink = _zeros_sink(plist)
         addins = engine.d_double_backward_sweep1(net, ectx, ctx.rec, ghat_xp, sink)
+        engine.side_join()      # sweep 2 adds to the tensors sweep 1's side-stream kernels are still writing
         engine.d_backward(net, ectx, None, sink, addins=addins)
         engine.side_join()
         return (None, None, None, None, None) + tuple(sink[id(p)] for p in plist)

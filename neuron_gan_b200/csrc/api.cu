@@ -101,14 +101,35 @@ int ngan_conv3x3_dbl(const void* ghat_x, const void* w_fwd, float scale, float l
     return conv3x3_dispatch(EPI_DBL, ghat_x, w_fwd, B, cin, cout, H, W, scale, leak, nullptr, ghat_y, ahat, nullptr, y,
                             r, gy, nullptr, S(stream));
 }
-int ngan_conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int B, int cin, int cout, int H, int W,
-                       void* stream) {
-    NGAN_REQUIRE(x && ga && dw && B > 0, "conv3x3_wgrad: null pointer or empty batch");
-    return conv3x3_wgrad(x, ga, scale, dw, B, cin, cout, H, W, S(stream));
+long long ngan_conv3x3_wgrad_workspace_bytes(int B, int cin, int cout, int H, int W) {
+    return static_cast<long long>(conv3x3_wgrad_workspace_bytes(B, cin, cout, H, W));
 }
-int ngan_bias_grad(const void* ga, float* gb, int B, int C, int H, int W, void* stream) {
-    NGAN_REQUIRE(ga && gb && !bad_c(C) && B > 0, "bias_grad: bad arguments");
-    return bias_grad_c8(ga, gb, B, C, H, W, S(stream));
+int ngan_conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int accumulate, float* workspace, int B,
+                       int cin, int cout, int H, int W, void* stream) {
+    NGAN_REQUIRE(x && ga && dw && workspace && B > 0, "conv3x3_wgrad: null pointer or empty batch");
+    return conv3x3_wgrad(x, ga, scale, dw, accumulate, workspace, B, cin, cout, H, W, S(stream));
+}
+long long ngan_pixel_reduction_workspace_bytes(int B, int C, int H, int W) {
+    return static_cast<long long>(pixel_reduction_workspace_bytes(B, C, H, W));
+}
+int ngan_bias_grad(const void* ga, float* gb, int accumulate, float* workspace, int B, int C, int H, int W,
+                   void* stream) {
+    NGAN_REQUIRE(ga && gb && workspace && !bad_c(C) && B > 0, "bias_grad: bad arguments");
+    return bias_grad_c8(ga, gb, accumulate, workspace, B, C, H, W, S(stream));
+}
+int ngan_reduce_partials(const float* partials, int n_partials, long long n, long long ld, float scale, float* out,
+                         int accumulate, void* stream) {
+    NGAN_REQUIRE(partials && out && n_partials > 0 && n > 0 && ld >= n, "reduce_partials: bad arguments");
+    return reduce_partials(partials, n_partials, n, ld, scale, out, accumulate, S(stream));
+}
+int ngan_sum_slots(const float* slots, int n_slots, long long n, long long ld, float* out, void* stream) {
+    NGAN_REQUIRE(slots && out && n_slots > 0 && n > 0 && ld >= n, "sum_slots: bad arguments");
+    return sum_slots(slots, n_slots, n, ld, out, S(stream));
+}
+int ngan_memset(void* dst, int value, long long bytes, void* stream) {
+    NGAN_REQUIRE(dst && bytes >= 0, "memset: bad arguments");
+    if (bytes == 0) return NGAN_OK;
+    return check_cuda(cudaMemsetAsync(dst, value, static_cast<size_t>(bytes), S(stream)), "cudaMemsetAsync");
 }
 int ngan_upsample2x(const void* x, void* out, int B, int C, int H, int W, void* stream) {
     NGAN_REQUIRE(x && out && !bad_c(C) && B > 0, "upsample2x: bad arguments");
@@ -173,29 +194,38 @@ int ngan_fromim_fwd(const float* xp, const float* w, const float* b, void* out, 
 }
 int ngan_d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const float* b_old, float alpha,
                     const float* dyn, void* out, int B, int C, int H, int W, void* stream) {
-    NGAN_REQUIRE(y_end && xp && w_old && b_old && out && !bad_c(C) && B > 0, "d_fade_fwd: bad arguments");
+    NGAN_REQUIRE(y_end && xp && w_old && out && !bad_c(C) && B > 0, "d_fade_fwd: bad arguments");
     return d_fade_fwd(y_end, xp, w_old, b_old, alpha, dyn, out, B, C, H, W, S(stream));
 }
 int ngan_fromim_bwd(const void* g, int unpool, float gscale, const float* dyn, const float* xp, const float* w, float* gw, float* gb,
-                    float* g_img, int g_img_accumulate, int B, int C, int H, int W, void* stream) {
+                    int grad_accumulate, float* workspace, float* g_img, int g_img_accumulate, int B, int C, int H,
+                    int W, void* stream) {
     NGAN_REQUIRE(g && xp && w && !bad_c(C) && B > 0, "fromim_bwd: bad arguments");
-    return fromim_bwd(g, unpool, gscale, dyn, xp, w, gw, gb, g_img, g_img_accumulate, B, C, H, W, S(stream));
+    NGAN_REQUIRE(workspace || !(gw || gb), "fromim_bwd: parameter gradients need a workspace");
+    return fromim_bwd(g, unpool, gscale, dyn, xp, w, gw, gb, grad_accumulate, workspace, g_img, g_img_accumulate, B, C,
+                      H, W, S(stream));
 }
 int ngan_fromim_dbl(const float* ghat_xp, float in_scale, const void* g, int unpool, float gscale, const float* dyn,
                     const float* w,
-                    void* ghat_out, float* what, int B, int C, int H, int W, void* stream) {
+                    void* ghat_out, float* what, int grad_accumulate, float* workspace, int B, int C, int H, int W,
+                    void* stream) {
     NGAN_REQUIRE(ghat_xp && g && w && !bad_c(C) && B > 0, "fromim_dbl: bad arguments");
-    return fromim_dbl(ghat_xp, in_scale, g, unpool, gscale, dyn, w, ghat_out, what, B, C, H, W, S(stream));
+    NGAN_REQUIRE(workspace || !what, "fromim_dbl: the weight gradient needs a workspace");
+    return fromim_dbl(ghat_xp, in_scale, g, unpool, gscale, dyn, w, ghat_out, what, grad_accumulate, workspace, B, C,
+                      H, W, S(stream));
 }
 int ngan_toim_fwd(const void* y, const float* w, float* img, int B, int C, int H, int W, void* stream) {
     NGAN_REQUIRE(y && w && img && !bad_c(C) && B > 0, "toim_fwd: bad arguments");
     return toim_fwd(y, w, img, B, C, H, W, S(stream));
 }
 int ngan_toim_bwd(const float* g_img, float gscale, const float* dyn, const float* img, const void* y, const float* r, const float* w,
-                  void* ga, float* gpre, float* gw, float leak, int B, int C, int H, int W, void* stream) {
+                  void* ga, float* gpre, float* gw, int grad_accumulate, float* workspace, float leak, int B, int C,
+                  int H, int W, void* stream) {
     NGAN_REQUIRE(g_img && img && y && w && !bad_c(C) && B > 0, "toim_bwd: bad arguments");
     NGAN_REQUIRE(!ga || r, "toim_bwd: ga requires r");
-    return toim_bwd(g_img, gscale, dyn, img, y, r, w, ga, gpre, gw, leak, B, C, H, W, S(stream));
+    NGAN_REQUIRE(workspace || !gw, "toim_bwd: the weight gradient needs a workspace");
+    return toim_bwd(g_img, gscale, dyn, img, y, r, w, ga, gpre, gw, grad_accumulate, workspace, leak, B, C, H, W,
+                    S(stream));
 }
 int ngan_head_fwd(const void* y, const float* w, const float* bias, float scale, float* score, int B, int C, int Sz,
                   void* stream) {
@@ -207,10 +237,10 @@ int ngan_head_bwd_pn(const float* gout, const float* w, float scale, const void*
     NGAN_REQUIRE(gout && w && y && r && ga && !bad_c(C) && B > 0, "head_bwd_pn: bad arguments");
     return head_bwd_pn(gout, w, scale, y, r, ga, gy_out, leak, B, C, Sz, S(stream));
 }
-int ngan_head_wgrad(const void* t, const float* coeff, float scale, float* gw, float* gb, int B, int C, int Sz,
-                    void* stream) {
+int ngan_head_wgrad(const void* t, const float* coeff, float scale, float* gw, float* gb, int accumulate, int B,
+                    int C, int Sz, void* stream) {
     NGAN_REQUIRE(t && coeff && gw && !bad_c(C) && B > 0, "head_wgrad: bad arguments");
-    return head_wgrad(t, coeff, scale, gw, gb, B, C, Sz, S(stream));
+    return head_wgrad(t, coeff, scale, gw, gb, accumulate, B, C, Sz, S(stream));
 }
 int ngan_prep_linear_weight(const float* w, void* wb, int K, int C, int Sz, void* stream) {
     NGAN_REQUIRE(w && wb && K > 0 && C > 0 && Sz > 0, "prep_linear_weight: bad arguments");
@@ -242,10 +272,11 @@ int ngan_pack_stats(const float* out3, const float* out1, const float* pen, floa
     NGAN_REQUIRE(out3 && out1 && pen && stats, "pack_stats: null pointer");
     return pack_stats(out3, out1, pen, stats, S(stream));
 }
-int ngan_gp_loss(const float* g, float norm_scale, float lambda, float* pen, float* coeff, float gscale, int B,
-                 long long per_sample, void* stream) {
-    NGAN_REQUIRE(g && pen && coeff && B > 0 && per_sample > 0, "gp_loss: bad arguments");
-    return gp_loss(g, norm_scale, lambda, pen, coeff, gscale, B, static_cast<size_t>(per_sample), S(stream));
+long long ngan_gp_loss_workspace_bytes(int B) { return static_cast<long long>(B) * 64 * sizeof(float); }
+int ngan_gp_loss(const float* g, float norm_scale, float lambda, float* pen, float* coeff, float gscale,
+                 float* workspace, int B, long long per_sample, void* stream) {
+    NGAN_REQUIRE(g && pen && coeff && workspace && B > 0 && per_sample > 0, "gp_loss: bad arguments");
+    return gp_loss(g, norm_scale, lambda, pen, coeff, gscale, workspace, B, static_cast<size_t>(per_sample), S(stream));
 }
 int ngan_adam_multi(const ngan_adam_tensor* tensors, int n_tensors, float beta1, float beta2, float eps,
                     void* stream) {

@@ -31,13 +31,74 @@ __device__ __forceinline__ float up2_adj_w(int o, int i, int n_in) {
     return (i0 == i ? 1.f - l1 : 0.f) + (i1 == i ? l1 : 0.f);
 }
 
-// Sum 8 per-thread values over the warp and add them to smem[0..8) (one shared atomic per value per warp).
-__device__ __forceinline__ void warp_accum8(const float* v, float* smem8, int lane) {
+// Sum 8 per-thread values over the warp into this warp's own row of shared memory (plain stores: the block adds
+// its warps' rows in warp order afterwards, so the result does not depend on scheduling).
+__device__ __forceinline__ void warp_store8(const float* v, float* row8, int lane) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         float s = warp_sum(v[e]);
-        if (lane == 0) atomicAdd(smem8 + e, s);
+        if (lane == 0) row8[e] = s;
     }
+}
+
+// ------------------------------------------------------------------------------- deterministic reductions
+// Parameter-gradient kernels never use atomics: every block writes its partial sums as one row of a workspace
+// ([n_partials][ld] fp32) and this kernel adds the rows in index order:
+//     out[i] (+)= scale * sum_p partials[p * ld + i],   i < n
+// A block owns OPB outputs and splits the rows over 256 / OPB slices (slice s takes rows s, s + S, ...), the slices
+// are combined in slice order: the order of additions depends only on (n_partials, OPB).
+template <int OPB>
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int n_partials,
+                                                              long long n, long long ld, float scale,
+                                                              float* __restrict__ out, int accumulate) {
+    pdl_trigger();
+    pdl_wait();           // launched right behind the kernel that writes the partials
+    constexpr int S = 256 / OPB;
+    __shared__ float red[S][OPB];
+    const int o = threadIdx.x % OPB, s = threadIdx.x / OPB;
+    const long long i = static_cast<long long>(blockIdx.x) * OPB + o;
+    float v = 0.f;
+    if (i < n)
+        for (int p = s; p < n_partials; p += S) v += partials[p * ld + i];
+    red[s][o] = v;
+    __syncthreads();
+    if (s == 0 && i < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < S; ++k) t += red[k][o];
+        t *= scale;
+        out[i] = accumulate ? out[i] + t : t;
+    }
+}
+int reduce_partials(const float* partials, int n_partials, long long n, long long ld, float scale, float* out,
+                    int accumulate, cudaStream_t st) {
+    cudaError_t e;
+    if (n >= 2048)
+        e = launch_pdl(reduce_partials_kernel<64>, dim3(static_cast<unsigned>((n + 63) / 64)), dim3(256), 0, st,
+                       partials, n_partials, n, ld, scale, out, accumulate);
+    else
+        e = launch_pdl(reduce_partials_kernel<8>, dim3(static_cast<unsigned>((n + 7) / 8)), dim3(256), 0, st, partials,
+                       n_partials, n, ld, scale, out, accumulate);
+    if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(reduce_partials)");
+    return check_launch("reduce_partials");
+}
+// out[i] = sum_k slots[k * ld + i] in slot order (the critic's three gradient contributions, train_step.py)
+__global__ void sum_slots_kernel(const float* __restrict__ slots, int n_slots, long long n, long long ld,
+                                 float* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = slots[i];
+    for (int k = 1; k < n_slots; ++k) v += slots[k * ld + i];
+    out[i] = v;
+}
+int sum_slots(const float* slots, int n_slots, long long n, long long ld, float* out, cudaStream_t st) {
+    sum_slots_kernel<<<nblocks(static_cast<size_t>(n), 256), 256, 0, st>>>(slots, n_slots, n, ld, out);
+    return check_launch("sum_slots");
+}
+size_t pixel_reduction_workspace_bytes(int B, int C, int H, int W) {
+    size_t rows = (static_cast<size_t>(B) * H * W + 127) / 128;       // fromim_dbl: one row per 128 pixels
+    if (rows < 148 * 16) rows = 148 * 16;                              // fromim_bwd / toim_bwd: at most 148*16 blocks
+    return rows * 2 * C * sizeof(float);
 }
 
 // ------------------------------------------------------------------------------- layout conversion
@@ -542,7 +603,7 @@ __global__ void d_fade_fwd_kernel(const uint4* __restrict__ y_end, const float* 
         unpack8(__ldg(y_end + (b * nch + j) * HW + pix), ye);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float ys = __ldg(w + j * 8 + e) * xv + __ldg(bias + j * 8 + e);
+            const float ys = __ldg(w + j * 8 + e) * xv + (bias ? __ldg(bias + j * 8 + e) : 0.f);
             o[e] = ys + alpha * (ye[e] - ys);
         }
         out[(b * nch + j) * HW + pix] = pack8(o);
@@ -561,15 +622,16 @@ int d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const flo
 // Thread layout of the two 1x1-conv backward kernels below: a block of 128 threads = (128 / NCH) pixel lanes x NCH
 // channel groups, the NCH threads of a pixel being adjacent lanes.  Each thread walks many pixels (grid-stride) and
 // keeps the per-channel sums of its group (weight / bias gradient) in registers; per pixel, sums over all channels
-// go through xor-shuffles over the NCH lanes; the per-channel sums meet once per block in shared memory, then one
-// global atomic per channel per block.  (Warp-reducing 8 values per group per pixel, as before, made these
+// go through xor-shuffles over the NCH lanes; the per-channel sums meet once per block in shared memory (summed in
+// lane order) and leave as one row [gw | gb] of the partials workspace, which reduce_partials adds in block order
+// (no atomics: bit-reproducible gradients).  (Warp-reducing 8 values per group per pixel, as before, made these
 // kernels shuffle-bound at 512x512 and left the 128-channel 16x16 launches at 36-49 us for 1 MB.)
 constexpr int kPixPerThread = 8;
 template <int NCH>
 __global__ void __launch_bounds__(128) fromim_bwd_kernel(const uint4* __restrict__ g, int unpool, float gscale_h,
                                                          const float* __restrict__ dyn,
                                                          const float* __restrict__ xp, const float* __restrict__ w,
-                                                         float* __restrict__ gw, float* __restrict__ gb,
+                                                         float* __restrict__ partials,
                                                          float* __restrict__ g_img, int accumulate, int H, int W,
                                                          size_t total) {
     constexpr int PL = 128 / NCH, C = NCH * 8;
@@ -616,14 +678,13 @@ __global__ void __launch_bounds__(128) fromim_bwd_kernel(const uint4* __restrict
         red[1][pl][j * 8 + e] = sb[e];
     }
     __syncthreads();
+    if (!partials) return;
     for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
         const int which = c / C, cc = c - which * C;
-        float* dst = which ? gb : gw;
-        if (!dst) continue;
         float v = 0.f;
 #pragma unroll 4
         for (int q = 0; q < PL; ++q) v += red[which][q][cc];
-        atomicAdd(dst + cc, v);
+        partials[static_cast<size_t>(blockIdx.x) * 2 * C + c] = v;
     }
 }
 static int pointwise_blocks(size_t total, int pixel_lanes) {
@@ -633,12 +694,16 @@ static int pointwise_blocks(size_t total, int pixel_lanes) {
     return static_cast<int>(blocks);
 }
 int fromim_bwd(const void* g, int unpool, float gscale, const float* dyn, const float* xp, const float* w, float* gw, float* gb,
-               float* g_img, int g_img_accumulate, int B, int C, int H, int W, cudaStream_t st) {
+               int grad_accumulate, float* workspace, float* g_img, int g_img_accumulate, int B, int C, int H, int W,
+               cudaStream_t st) {
     const size_t total = static_cast<size_t>(B) * H * W;
+    float* partials = (gw || gb) ? workspace : nullptr;
+    const int blocks = pointwise_blocks(total, 128 / (C / 8));
 #define NGAN_FIB(N)                                                                                                  \
     case N:                                                                                                          \
-        fromim_bwd_kernel<N><<<pointwise_blocks(total, 128 / N), 128, 0, st>>>(                                      \
-            static_cast<const uint4*>(g), unpool, gscale, dyn, xp, w, gw, gb, g_img, g_img_accumulate, H, W, total); \
+        fromim_bwd_kernel<N><<<blocks, 128, 0, st>>>(                                                                \
+            static_cast<const uint4*>(g), unpool, gscale, dyn, xp, w, partials, g_img, g_img_accumulate, H, W,       \
+            total);                                                                                                  \
         break;
     switch (C / 8) {
         NGAN_FIB(2)
@@ -650,20 +715,22 @@ int fromim_bwd(const void* g, int unpool, float gscale, const float* dyn, const 
             return NGAN_ERR_UNSUPPORTED;
     }
 #undef NGAN_FIB
-    return check_launch("fromim_bwd");
+    int rc = check_launch("fromim_bwd");
+    if (rc || !partials) return rc;
+    if (gw) rc = reduce_partials(partials, blocks, C, 2 * C, 1.f, gw, grad_accumulate, st);
+    if (!rc && gb) rc = reduce_partials(partials + C, blocks, C, 2 * C, 1.f, gb, grad_accumulate, st);
+    return rc;
 }
 // Double backward of FromImage's input-gradient: first order was g_xp = sum_c w_c * G_c.  With cotangent
 // X = in_scale * ghat_xp on g_xp:  ghat_out[c] = w_c * X (cotangent on G_c),  what[c] += sum X * G_c.
 __global__ void fromim_dbl_kernel(const float* __restrict__ ghat_xp, float in_scale, const uint4* __restrict__ g,
                                   int unpool, float gscale_h, const float* __restrict__ dyn,
                                   const float* __restrict__ w, uint4* __restrict__ ghat_out,
-                                  float* __restrict__ what, int C, int H, int W, size_t total) {
+                                  float* __restrict__ partials, int C, int H, int W, size_t total) {
     pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     const float gscale = dyn ? gscale_h * __ldg(dyn) : gscale_h;
-    extern __shared__ float sacc[];  // [C]
-    for (int k = threadIdx.x; k < C; k += blockDim.x) sacc[k] = 0.f;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
+    extern __shared__ float sacc[];  // [4 warps][C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t HW = static_cast<size_t>(H) * W;
     const size_t gHW = unpool ? HW / 4 : HW;
     const int nch = C / 8;
@@ -685,20 +752,26 @@ __global__ void fromim_dbl_kernel(const float* __restrict__ ghat_xp, float in_sc
             sw[e] = X * gscale * gv[e];
         }
         if (ok && ghat_out) ghat_out[q0 + j * HW] = pack8(o);
-        warp_accum8(sw, sacc + j * 8, lane);
+        if (partials) warp_store8(sw, sacc + warp * C + j * 8, lane);
     }
+    if (!partials) return;
     __syncthreads();
-    if (what)
-        for (int k = threadIdx.x; k < C; k += blockDim.x) atomicAdd(what + k, sacc[k]);
+    for (int k = threadIdx.x; k < C; k += blockDim.x)
+        partials[static_cast<size_t>(blockIdx.x) * C + k] = (sacc[k] + sacc[C + k]) + (sacc[2 * C + k] + sacc[3 * C + k]);
 }
 int fromim_dbl(const float* ghat_xp, float in_scale, const void* g, int unpool, float gscale, const float* dyn,
                const float* w,
-               void* ghat_out, float* what, int B, int C, int H, int W, cudaStream_t st) {
+               void* ghat_out, float* what, int grad_accumulate, float* workspace, int B, int C, int H, int W,
+               cudaStream_t st) {
     const size_t total = static_cast<size_t>(B) * H * W;
-    fromim_dbl_kernel<<<nblocks(total, 128), 128, C * sizeof(float), st>>>(
-        ghat_xp, in_scale, static_cast<const uint4*>(g), unpool, gscale, dyn, w, static_cast<uint4*>(ghat_out), what,
-        C, H, W, total);
-    return check_launch("fromim_dbl");
+    const int blocks = nblocks(total, 128);
+    float* partials = what ? workspace : nullptr;
+    fromim_dbl_kernel<<<blocks, 128, 4 * C * sizeof(float), st>>>(
+        ghat_xp, in_scale, static_cast<const uint4*>(g), unpool, gscale, dyn, w, static_cast<uint4*>(ghat_out),
+        partials, C, H, W, total);
+    int rc = check_launch("fromim_dbl");
+    if (rc || !partials) return rc;
+    return reduce_partials(partials, blocks, C, C, 1.f, what, grad_accumulate, st);
 }
 
 // ------------------------------------------------------------------------------- ToImage (models.py:133-149)
@@ -732,7 +805,8 @@ __global__ void __launch_bounds__(128) toim_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ img, const uint4* __restrict__ y,
                                                        const float* __restrict__ r, const float* __restrict__ w,
                                                        uint4* __restrict__ ga, float* __restrict__ gpre_out,
-                                                       float* __restrict__ gw, float leak, size_t HW, size_t total) {
+                                                       float* __restrict__ partials, float leak, size_t HW,
+                                                       size_t total) {
     pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     constexpr int PL = 128 / NCH, C = NCH * 8;
     const float gscale = dyn ? gscale_h * __ldg(dyn) : gscale_h;
@@ -774,7 +848,7 @@ __global__ void __launch_bounds__(128) toim_bwd_kernel(const float* __restrict__
             if (ok) ga[q] = pack8(o8);
         }
     }
-    if (gw) {
+    if (partials) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) red[pl][j * 8 + e] = sw[e];
         __syncthreads();
@@ -782,19 +856,21 @@ __global__ void __launch_bounds__(128) toim_bwd_kernel(const float* __restrict__
             float v = 0.f;
 #pragma unroll 4
             for (int q = 0; q < PL; ++q) v += red[q][c];
-            atomicAdd(gw + c, v);
+            partials[static_cast<size_t>(blockIdx.x) * C + c] = v;
         }
     }
 }
 int toim_bwd(const float* g_img, float gscale, const float* dyn, const float* img, const void* y, const float* r, const float* w,
-             void* ga, float* gpre, float* gw, float leak, int B, int C, int H, int W, cudaStream_t st) {
+             void* ga, float* gpre, float* gw, int grad_accumulate, float* workspace, float leak, int B, int C, int H,
+             int W, cudaStream_t st) {
     const size_t HW = static_cast<size_t>(H) * W, total = B * HW;
+    float* partials = gw ? workspace : nullptr;
+    const int blocks = pointwise_blocks(total, 128 / (C / 8));
 #define NGAN_TIB(N)                                                                                                 \
     case N:                                                                                                         \
-        toim_bwd_kernel<N><<<pointwise_blocks(total, 128 / N), 128, 0, st>>>(                                       \
-            g_img, gscale, dyn, img, static_cast<const uint4*>(y), r, w, static_cast<uint4*>(ga), gpre, gw, leak,   \
-            HW,                                                                                                     \
-            total);                                                                                                 \
+        toim_bwd_kernel<N><<<blocks, 128, 0, st>>>(                                                                 \
+            g_img, gscale, dyn, img, static_cast<const uint4*>(y), r, w, static_cast<uint4*>(ga), gpre, partials,   \
+            leak, HW, total);                                                                                       \
         break;
     switch (C / 8) {
         NGAN_TIB(2)
@@ -806,7 +882,9 @@ int toim_bwd(const float* g_img, float gscale, const float* dyn, const float* im
             return NGAN_ERR_UNSUPPORTED;
     }
 #undef NGAN_TIB
-    return check_launch("toim_bwd");
+    int rc = check_launch("toim_bwd");
+    if (rc || !partials) return rc;
+    return reduce_partials(partials, blocks, C, C, 1.f, gw, grad_accumulate, st);
 }
 
 // ------------------------------------------------------------------------------- critic head (models.py:485-490)
@@ -901,16 +979,17 @@ int head_bwd_pn(const float* gout, const float* w, float scale, const void* y, c
 }
 // gw[c,p] += scale * sum_b coeff[b] * t[b,c,p]: head weight gradient (t = y, coeff = gout) and its double-backward
 // twin (t = cotangent on gy, coeff = gout).
-// Accumulates with atomics: the two halves of the critic step run on concurrent streams and both add to gw.
-// gb (optional): the head bias gradient, gb[0] += sum_b coeff[b].
+// One thread per output element walks the batch in order (no atomics: concurrent contributions to one parameter
+// go to separate gradient slots, train_step.py).  gb (optional): the head bias gradient, gb[0] (+)= sum_b coeff[b].
 __global__ void head_wgrad_kernel(const uint4* __restrict__ t, const float* __restrict__ coeff, float scale,
-                                  float* __restrict__ gw, float* __restrict__ gb, int B, int C, int HW) {
+                                  float* __restrict__ gw, float* __restrict__ gb, int accumulate, int B, int C,
+                                  int HW) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int nch = C / 8;
     if (gb && k == 0) {
         float sum = 0.f;
         for (int b = 0; b < B; ++b) sum += coeff[b];
-        atomicAdd(gb, sum);
+        gb[0] = accumulate ? gb[0] + sum : sum;
     }
     if (k >= nch * HW) return;
     const int j = k / HW, pix = k % HW;
@@ -923,22 +1002,24 @@ __global__ void head_wgrad_kernel(const uint4* __restrict__ t, const float* __re
         for (int e = 0; e < 8; ++e) acc[e] += c * tv[e];
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(gw + static_cast<size_t>(j * 8 + e) * HW + pix, scale * acc[e]);
+    for (int e = 0; e < 8; ++e) {
+        float* dst = gw + static_cast<size_t>(j * 8 + e) * HW + pix;
+        *dst = accumulate ? *dst + scale * acc[e] : scale * acc[e];
+    }
 }
-int head_wgrad(const void* t, const float* coeff, float scale, float* gw, float* gb, int B, int C, int S,
-               cudaStream_t st) {
+int head_wgrad(const void* t, const float* coeff, float scale, float* gw, float* gb, int accumulate, int B, int C,
+               int S, cudaStream_t st) {
     const int n = (C / 8) * S * S;
-    head_wgrad_kernel<<<nblocks(n, 128), 128, 0, st>>>(static_cast<const uint4*>(t), coeff, scale, gw, gb, B, C, S * S);
+    head_wgrad_kernel<<<nblocks(n, 128), 128, 0, st>>>(static_cast<const uint4*>(t), coeff, scale, gw, gb, accumulate,
+                                                       B, C, S * S);
     return check_launch("head_wgrad");
 }
 
 // gb[c] += sum over batch and pixels of ga[b,c,p]   (bias of the 128->128 conv, models.py:469-471)
-__global__ void bias_grad_c8_kernel(const uint4* __restrict__ ga, float* __restrict__ gb, int C, size_t HW,
+__global__ void bias_grad_c8_kernel(const uint4* __restrict__ ga, float* __restrict__ partials, int C, size_t HW,
                                     size_t total) {
-    extern __shared__ float sacc[];
-    for (int k = threadIdx.x; k < C; k += blockDim.x) sacc[k] = 0.f;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
+    extern __shared__ float sacc[];   // [8 warps][C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const bool ok = i < total;
     const size_t ii = ok ? i : 0;
@@ -948,16 +1029,25 @@ __global__ void bias_grad_c8_kernel(const uint4* __restrict__ ga, float* __restr
     for (int j = 0; j < nch; ++j) {
         float v[8];
         unpack8(ok ? __ldg(ga + (b * nch + j) * HW + pix) : make_uint4(0, 0, 0, 0), v);
-        warp_accum8(v, sacc + j * 8, lane);
+        warp_store8(v, sacc + warp * C + j * 8, lane);
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < C; k += blockDim.x) atomicAdd(gb + k, sacc[k]);
+    for (int k = threadIdx.x; k < C; k += blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += sacc[q * C + k];
+        partials[static_cast<size_t>(blockIdx.x) * C + k] = v;
+    }
 }
-int bias_grad_c8(const void* ga, float* gb, int B, int C, int H, int W, cudaStream_t st) {
+int bias_grad_c8(const void* ga, float* gb, int accumulate, float* workspace, int B, int C, int H, int W,
+                 cudaStream_t st) {
     const size_t HW = static_cast<size_t>(H) * W, total = B * HW;
-    bias_grad_c8_kernel<<<nblocks(total, 256), 256, C * sizeof(float), st>>>(static_cast<const uint4*>(ga), gb, C, HW,
-                                                                             total);
-    return check_launch("bias_grad_c8");
+    const int blocks = nblocks(total, 256);
+    bias_grad_c8_kernel<<<blocks, 256, 8 * C * sizeof(float), st>>>(static_cast<const uint4*>(ga), workspace, C, HW,
+                                                                    total);
+    int rc = check_launch("bias_grad_c8");
+    if (rc) return rc;
+    return reduce_partials(workspace, blocks, C, C, 1.f, gb, accumulate, st);
 }
 
 // ------------------------------------------------------------------------------- loss reductions
@@ -1032,7 +1122,8 @@ int pack_stats(const float* out3, const float* out1, const float* pen, float* st
 }
 // Gradient penalty (loss_functions.py:176): norm_b = norm_scale * ||g_b||_2, pen = lambda*mean((norm_b-1)^2),
 // coeff_b = gscale * d pen / d norm_b / norm_b  (so that d pen/d g_x = coeff_b * g_x).
-__global__ void gp_sumsq_kernel(const float* __restrict__ g, float* __restrict__ sumsq, size_t per_sample) {
+__global__ void gp_sumsq_kernel(const float* __restrict__ g, float* __restrict__ partial /* [B][gridDim.x] */,
+                                size_t per_sample) {
     __shared__ float red[32];
     const int b = blockIdx.y;
     const float* p = g + static_cast<size_t>(b) * per_sample;
@@ -1041,28 +1132,31 @@ __global__ void gp_sumsq_kernel(const float* __restrict__ g, float* __restrict__
          i += static_cast<size_t>(gridDim.x) * blockDim.x)
         s += p[i] * p[i];
     s = block_sum(s, red);
-    if (threadIdx.x == 0) atomicAdd(sumsq + b, s);
+    if (threadIdx.x == 0) partial[b * gridDim.x + blockIdx.x] = s;
 }
-__global__ void gp_finish_kernel(float* __restrict__ coeff /* in: sumsq */, float norm_scale, float lambda,
-                                 float* __restrict__ pen_out, float gscale, int B) {
+// The per-sample partial sums are added in block order (deterministic).  A sample whose input gradient is exactly
+// zero gets coefficient 0 -- torch's norm backward yields the zero subgradient there (loss_functions.py:176) --
+// instead of -inf, which the double backward would turn into NaN.
+__global__ void gp_finish_kernel(const float* __restrict__ partial, int n_part, float* __restrict__ coeff,
+                                 float norm_scale, float lambda, float* __restrict__ pen_out, float gscale, int B) {
     __shared__ float red[32];
     float acc = 0.f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        const float n = norm_scale * sqrtf(coeff[b]);
+        float ss = 0.f;
+        for (int k = 0; k < n_part; ++k) ss += partial[b * n_part + k];
+        const float n = norm_scale * sqrtf(ss);
         acc += (n - 1.f) * (n - 1.f);
-        coeff[b] = gscale * lambda * 2.f * (n - 1.f) / (B * n);
+        coeff[b] = n > 0.f ? gscale * lambda * 2.f * (n - 1.f) / (B * n) : 0.f;
     }
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) pen_out[0] = lambda * acc / B;
 }
-int gp_loss(const float* g, float norm_scale, float lambda, float* pen_out, float* coeff_out, float gscale, int B,
-            size_t per_sample, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(coeff_out, 0, B * sizeof(float), st);
-    if (e != cudaSuccess) return check_cuda(e, "memset(gp)");
+int gp_loss(const float* g, float norm_scale, float lambda, float* pen_out, float* coeff_out, float gscale,
+            float* workspace /* B * 64 floats */, int B, size_t per_sample, cudaStream_t st) {
     int bx = static_cast<int>((per_sample + 1023) / 1024);
     if (bx > 64) bx = 64;
-    gp_sumsq_kernel<<<dim3(bx, B), 256, 0, st>>>(g, coeff_out, per_sample);
-    gp_finish_kernel<<<1, 256, 0, st>>>(coeff_out, norm_scale, lambda, pen_out, gscale, B);
+    gp_sumsq_kernel<<<dim3(bx, B), 256, 0, st>>>(g, workspace, per_sample);
+    gp_finish_kernel<<<1, 256, 0, st>>>(workspace, bx, coeff_out, norm_scale, lambda, pen_out, gscale, B);
     return check_launch("gp_loss");
 }
 

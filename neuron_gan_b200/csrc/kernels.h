@@ -15,10 +15,15 @@ int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, 
 int prep_conv_weight(const float* w, void* fwd, void* dgrad, int cin, int cout, cudaStream_t st);
 
 // wgrad.cu
-int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int B, int cin, int cout, int H, int W,
-                  cudaStream_t st);
+size_t conv3x3_wgrad_workspace_bytes(int B, int cin, int cout, int H, int W);
+int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int accumulate, float* workspace, int B,
+                  int cin, int cout, int H, int W, cudaStream_t st);
 
 // elementwise.cu
+int reduce_partials(const float* partials, int n_partials, long long n, long long ld, float scale, float* out,
+                    int accumulate, cudaStream_t st);
+int sum_slots(const float* slots, int n_slots, long long n, long long ld, float* out, cudaStream_t st);
+size_t pixel_reduction_workspace_bytes(int B, int C, int H, int W);
 int nchw_to_c8(const float* src, void* dst, int B, int C, int H, int W, cudaStream_t st);
 int c8_to_nchw(const void* src, float* dst, int B, int C, int H, int W, cudaStream_t st);
 int upsample2x_c8(const void* x, void* out, int B, int C, int H, int W, cudaStream_t st);
@@ -40,25 +45,29 @@ int fromim_fwd(const float* xp, const float* w, const float* b, void* out, int B
 int d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const float* b_old, float alpha,
                const float* dyn, void* out, int B, int C, int H, int W, cudaStream_t st);
 int fromim_bwd(const void* g, int unpool, float gscale, const float* dyn, const float* xp, const float* w, float* gw, float* gb,
-               float* g_img, int g_img_accumulate, int B, int C, int H, int W, cudaStream_t st);
+               int grad_accumulate, float* workspace, float* g_img, int g_img_accumulate, int B, int C, int H, int W,
+               cudaStream_t st);
 int fromim_dbl(const float* ghat_xp, float in_scale, const void* g, int unpool, float gscale, const float* dyn,
                const float* w,
-               void* ghat_out, float* what, int B, int C, int H, int W, cudaStream_t st);
+               void* ghat_out, float* what, int grad_accumulate, float* workspace, int B, int C, int H, int W,
+               cudaStream_t st);
 int toim_fwd(const void* y, const float* w, float* img, int B, int C, int H, int W, cudaStream_t st);
 int toim_bwd(const float* g_img, float gscale, const float* dyn, const float* img, const void* y, const float* r, const float* w,
-             void* ga, float* gpre, float* gw, float leak, int B, int C, int H, int W, cudaStream_t st);
+             void* ga, float* gpre, float* gw, int grad_accumulate, float* workspace, float leak, int B, int C, int H,
+             int W, cudaStream_t st);
 int head_fwd(const void* y, const float* w, const float* bias, float scale, float* score, int B, int C, int S,
              cudaStream_t st);
 int head_bwd_pn(const float* gout, const float* w, float scale, const void* y, const float* r, void* ga,
                 void* gy_out, float leak, int B, int C, int S, cudaStream_t st);
-int head_wgrad(const void* t, const float* coeff, float scale, float* gw, float* gb, int B, int C, int S,
-               cudaStream_t st);
-int bias_grad_c8(const void* ga, float* gb, int B, int C, int H, int W, cudaStream_t st);
+int head_wgrad(const void* t, const float* coeff, float scale, float* gw, float* gb, int accumulate, int B, int C,
+               int S, cudaStream_t st);
+int bias_grad_c8(const void* ga, float* gb, int accumulate, float* workspace, int B, int C, int H, int W,
+                 cudaStream_t st);
 int wloss_fwd(const float* s_real, const float* s_fake, float drift, float* out3, float* g_real, float* g_fake,
               float gscale, int B, cudaStream_t st);
 int gloss_fwd(const float* s_fake, float* out1, float* g_fake, float gscale, int B, cudaStream_t st);
-int gp_loss(const float* g, float norm_scale, float lambda, float* pen_out, float* coeff_out, float gscale, int B,
-            size_t per_sample, cudaStream_t st);
+int gp_loss(const float* g, float norm_scale, float lambda, float* pen_out, float* coeff_out, float gscale,
+            float* workspace, int B, size_t per_sample, cudaStream_t st);
 int pack_stats(const float* out3, const float* out1, const float* pen, float* stats, cudaStream_t st);
 int scale_rows_f32(const float* x, const float* coeff, float scale, float* out, int B, size_t per_sample,
                    cudaStream_t st);

@@ -14,7 +14,11 @@ Here each pass is an explicit kernel sequence over saved activations:
     head and leaves, per stage, the cotangent to inject at its pre-activation; sweep 2 is the ordinary
     backward with those injections.  Formulas: SURVEY.md section 8a row 3.
 
-Parameter gradients ACCUMULATE into the fp32 tensors of a `sink` (dict id(param) -> tensor).
+Parameter gradients go to the fp32 tensors of a `sink` (Sink: id(param) -> tensor).  Every pass (a backward, a sweep of
+the double backward) touches each parameter with exactly ONE kernel, and no kernel uses atomics, so a sink with
+accumulate=False needs no zeroing and its content is bit-reproducible.  Passes that may run concurrently (the
+Wasserstein backward and the two sweeps of the penalty's double backward all contribute to every critic weight)
+must get SEPARATE sinks, which the caller adds afterwards (TrainStep: three slots + ops.sum_slots).
 """
 import os
 import weakref
@@ -138,10 +142,23 @@ def _on_side(fn, *tensors):
     _Side.used.add(i)
 
 
-def _wgrad(x, ga, scale, dw):
-    """conv3x3_wgrad on a side stream (dw accumulates with atomics, so concurrent wgrads into one tensor are fine)."""
+class Sink(dict):
+    """id(param) -> fp32 gradient tensor.  accumulate=True: kernels add to the tensors (the caller zeroed them and no
+    other pass writes them concurrently); accumulate=False: kernels overwrite them."""
+
+    def __init__(self, *args, accumulate=True, **kw):
+        super().__init__(*args, **kw)
+        self.accumulate = accumulate
+
+
+def _acc(sink):
+    return getattr(sink, 'accumulate', True)
+
+
+def _wgrad(x, ga, scale, dw, acc=True):
+    """conv3x3_wgrad on a side stream (nothing downstream waits for it until the optimiser)."""
     if dw is not None:
-        _on_side(lambda: ops.conv3x3_wgrad(x, ga, scale, dw), x, ga)
+        _on_side(lambda: ops.conv3x3_wgrad(x, ga, scale, dw, accumulate=acc), x, ga)
 
 
 def side_join():
@@ -264,9 +281,10 @@ def _g_block_bwd(rec, ga2, y_prev, r_prev, leak, sink, extra_pre=None, extra_w=N
     """Backward through one generator block given ga2 (gradient at conv2's pre-activation); returns the
     gradient at the pre-activation of the stage below (whose output y_prev was upsampled into this block)."""
     c1, c2 = rec.blk.conv1, rec.blk.conv2
-    _wgrad(rec.y1, ga2, c2.scale_value, _sink_get(sink, c2.weight))
+    acc = _acc(sink)
+    _wgrad(rec.y1, ga2, c2.scale_value, _sink_get(sink, c2.weight), acc)
     ga1, _ = ops.conv3x3_dgrad_pn(ga2, conv_images(c2)[1], c2.scale_value, leak, rec.y1, rec.r1)
-    _wgrad(rec.xu, ga1, c1.scale_value, _sink_get(sink, c1.weight))
+    _wgrad(rec.xu, ga1, c1.scale_value, _sink_get(sink, c1.weight), acc)
     g_up = ops.conv3x3_dgrad(ga1, conv_images(c1)[1], c1.scale_value, c1.in_channels)
     return ops.up2_bwd_pn_bwd(g_up, y_prev, r_prev, extra_pre, extra_w, leak)
 
@@ -276,27 +294,29 @@ def g_backward(net, ctx, g_img, sink, linear_overwrite=False):
     weight's gradient (98 % of the parameters) is stored, not accumulated -- its part of the sink need not be zeroed."""
     leak = net.LeakyReLU_neg_slope
     alpha = ctx.alpha
+    acc = _acc(sink)
     g_img = g_img.detach().to(F32).contiguous()
     trunk_y, trunk_r = (ctx.recs[-1].y2, ctx.recs[-1].r2) if ctx.recs else (ctx.yc, ctx.rc)
     if ctx.new is None:
         ga, _ = ops.toim_bwd(g_img, ctx.img, trunk_y, trunk_r, _flat(ctx.toim.weight), _sink_get(sink, ctx.toim.weight),
-                             leak=leak)
+                             leak=leak, grad_accumulate=acc)
     else:
         new, toim_new, toim_old = ctx.new, ctx.toim_new, ctx.toim
         a_dev, oma_dev = _alpha_terms(net, alpha)
         ga2, _ = ops.toim_bwd(g_img, ctx.img_end, new.y2, new.r2, _flat(toim_new.weight),
-                              _sink_get(sink, toim_new.weight), gscale=a_dev, leak=leak)
+                              _sink_get(sink, toim_new.weight), gscale=a_dev, leak=leak, grad_accumulate=acc)
         g_old = ops.up2_image_bwd(g_img, oma_dev)
         _, gpre_old = ops.toim_bwd(g_old, ctx.img_old, trunk_y, None, _flat(toim_old.weight),
-                                   _sink_get(sink, toim_old.weight), want_ga=False, want_gpre=True, leak=leak)
+                                   _sink_get(sink, toim_old.weight), want_ga=False, want_gpre=True, leak=leak,
+                                   grad_accumulate=acc)
         ga = _g_block_bwd(new, ga2, trunk_y, trunk_r, leak, sink, gpre_old, _flat(toim_old.weight))
     for i in range(len(ctx.recs) - 1, -1, -1):
         y_prev, r_prev = (ctx.recs[i - 1].y2, ctx.recs[i - 1].r2) if i > 0 else (ctx.yc, ctx.rc)
         ga = _g_block_bwd(ctx.recs[i], ga, y_prev, r_prev, leak, sink)
     lin, conv0 = net.layers[0], net.layers[4]
-    _wgrad(ctx.y0, ga, conv0.scale_value, _sink_get(sink, conv0.weight))
+    _wgrad(ctx.y0, ga, conv0.scale_value, _sink_get(sink, conv0.weight), acc)
     ga0, _ = ops.conv3x3_dgrad_pn(ga, conv_images(conv0)[1], conv0.scale_value, leak, ctx.y0, ctx.r0)
-    ops.linear_wgrad(ga0, ctx.z, lin.scale_value, _sink_get(sink, lin.weight), accumulate=not linear_overwrite)
+    ops.linear_wgrad(ga0, ctx.z, lin.scale_value, _sink_get(sink, lin.weight), accumulate=acc and not linear_overwrite)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -366,13 +386,14 @@ def d_backward(net, ctx, gout, sink, addins=None, want_gxp=False, record=None):
     last, head = net.last_conv(), net.head_conv()
     rec = record is not None
     ad = addins or {}
+    acc = _acc(sink)
     if gout is not None:
         gout = gout.detach().to(F32).contiguous()
         ga_l, gy_l = ops.head_bwd_pn(gout, head.weight.detach(), head.scale_value, ctx.yl, ctx.rl, want_gy=rec,
                                      leak=leak)
         if sink is not None:
             hw, hb, yl = _sink_get(sink, head.weight), _sink_get(sink, head.bias), ctx.yl
-            _on_side(lambda: ops.head_wgrad(yl, gout, head.scale_value, hw, hb), yl, gout)
+            _on_side(lambda: ops.head_wgrad(yl, gout, head.scale_value, hw, hb, accumulate=acc), yl, gout)
     else:
         ga_l, gy_l = ad['last'], None
     if rec:
@@ -380,9 +401,9 @@ def d_backward(net, ctx, gout, sink, addins=None, want_gxp=False, record=None):
         record.gout = gout
         record.stages = {}
     if sink is not None:
-        _wgrad(ctx.last_x, ga_l, last.scale_value, _sink_get(sink, last.weight))
+        _wgrad(ctx.last_x, ga_l, last.scale_value, _sink_get(sink, last.weight), acc)
         lb = _sink_get(sink, last.bias)
-        _on_side(lambda: ops.bias_grad(ga_l, lb), ga_l)
+        _on_side(lambda: ops.bias_grad(ga_l, lb, accumulate=acc), ga_l)
 
     top = ctx.stages[-1]
     if top.kind == 'block':
@@ -410,11 +431,11 @@ def d_backward(net, ctx, gout, sink, addins=None, want_gxp=False, record=None):
                 ga2, gy2 = ops.pn_bwd(g, st.y2, st.r2, gscale=ops.scalar_mul(0.25 if recv_unpool else 1.0, gs),
                                       unpool=recv_unpool, addin=a2, want_gy=rec, leak=leak)
             if sink is not None:
-                _wgrad(st.y1, ga2, c2.scale_value, _sink_get(sink, c2.weight))
+                _wgrad(st.y1, ga2, c2.scale_value, _sink_get(sink, c2.weight), acc)
             ga1, gy1 = ops.conv3x3_dgrad_pn(ga2, conv_images(c2)[1], c2.scale_value, leak, st.y1, st.r1, addin=a1,
                                             want_gy=rec)
             if sink is not None:
-                _wgrad(st.xin, ga1, c1.scale_value, _sink_get(sink, c1.weight))
+                _wgrad(st.xin, ga1, c1.scale_value, _sink_get(sink, c1.weight), acc)
             if rec:
                 record.stages[id(st)] = SimpleNamespace(gy1=gy1, ga1=ga1, gy2=gy2, ga2=ga2, recv_unpool=recv_unpool)
             incoming = ('g', ops.conv3x3_dgrad(ga1, conv_images(c1)[1], c1.scale_value, c1.in_channels), 1.0,
@@ -435,13 +456,13 @@ def d_backward(net, ctx, gout, sink, addins=None, want_gxp=False, record=None):
                 if sink is not None or need_img:
                     ops.fromim_bwd(g, ctx.xp, w, _sink_get(sink, st.conv.weight), _sink_get(sink, st.conv.bias),
                                    gscale=_times(gs_eff, oma_dev), unpool=unpool, g_img=g_xp if need_img else None,
-                                   accumulate=accumulate)
+                                   accumulate=accumulate, grad_accumulate=acc)
                 incoming = ('g', g, _times(gs, a_dev), unpool)
             else:  # 'from'
                 if sink is not None or need_img:
                     ops.fromim_bwd(g, ctx.xp, w, _sink_get(sink, st.conv.weight), _sink_get(sink, st.conv.bias),
                                    gscale=gs_eff, unpool=unpool, g_img=g_xp if need_img else None,
-                                   accumulate=accumulate)
+                                   accumulate=accumulate, grad_accumulate=acc)
     return g_xp
 
 
@@ -454,19 +475,20 @@ def d_double_backward_sweep1(net, ctx, record, ghat_xp, sink):
     a_dev, oma_dev = _alpha_terms(net, alpha)
     addins = {}
     cur = None
+    acc = _acc(sink)
     ghat_xp = ghat_xp.contiguous()
     for st in ctx.stages:
         r = record.stages[id(st)]
         if st.kind == 'from':
             cur = ops.fromim_dbl(ghat_xp, r.g, _flat(st.conv.weight), _sink_get(sink, st.conv.weight), in_scale=1.0,
-                                 gscale=r.gscale, unpool=r.unpool)
+                                 gscale=r.gscale, unpool=r.unpool, grad_accumulate=acc)
             if r.unpool:            # cannot happen with the reference's topology, kept for completeness
                 cur = ops.avgpool2(cur)
         elif st.kind == 'block':
             c1, c2 = st.blk.conv1, st.blk.conv2
-            _wgrad(cur, r.ga1, c1.scale_value, _sink_get(sink, c1.weight))
+            _wgrad(cur, r.ga1, c1.scale_value, _sink_get(sink, c1.weight), acc)
             gh1, ah1 = ops.conv3x3_dbl(cur, conv_images(c1)[0], c1.scale_value, leak, st.y1, st.r1, r.gy1)
-            _wgrad(gh1, r.ga2, c2.scale_value, _sink_get(sink, c2.weight))
+            _wgrad(gh1, r.ga2, c2.scale_value, _sink_get(sink, c2.weight), acc)
             gh2, ah2 = ops.conv3x3_dbl(gh1, conv_images(c2)[0], c2.scale_value, leak, st.y2, st.r2, r.gy2)
             addins[id(st)] = (ah1, ah2)
             cur = gh2          # cotangent on gy2; the fade stage (if next) applies alpha and the pooling itself
@@ -477,18 +499,29 @@ def d_double_backward_sweep1(net, ctx, record, ghat_xp, sink):
         else:  # 'fade': first-order g_y reached FromIm_old with (1-alpha) and the new block with alpha
             w_old = _flat(st.conv.weight)
             ops.fromim_dbl(ghat_xp, r.g, w_old, _sink_get(sink, st.conv.weight), in_scale=1.0,
-                           gscale=_times(r.gscale, oma_dev), unpool=r.unpool, want_out=False)
-            zero_b = torch.zeros_like(st.conv.bias)
-            cur = ops.d_fade_fwd(cur, ghat_xp, w_old, zero_b, a_dev)   # alpha*cur + (1-alpha)*w_old*ghat_xp
+                           gscale=_times(r.gscale, oma_dev), unpool=r.unpool, want_out=False, grad_accumulate=acc)
+            cur = ops.d_fade_fwd(cur, ghat_xp, w_old, None, a_dev)     # alpha*cur + (1-alpha)*w_old*ghat_xp
             if r.unpool:
                 cur = ops.avgpool2(cur)
     last, head = net.last_conv(), net.head_conv()
-    _wgrad(cur, record.last.ga, last.scale_value, _sink_get(sink, last.weight))
+    _wgrad(cur, record.last.ga, last.scale_value, _sink_get(sink, last.weight), acc)
     gh_l, ah_l = ops.conv3x3_dbl(cur, conv_images(last)[0], last.scale_value, leak, ctx.yl, ctx.rl, record.last.gy)
     hw, rgout = _sink_get(sink, head.weight), record.gout
-    _on_side(lambda: ops.head_wgrad(gh_l, rgout, head.scale_value, hw), gh_l, rgout)
+    _on_side(lambda: ops.head_wgrad(gh_l, rgout, head.scale_value, hw, accumulate=acc), gh_l, rgout)
     addins['last'] = ah_l
     return addins
+
+
+_ones_cache = {}
+
+
+def _ones(n, device):
+    """[n] fp32 ones, created once per (n, device): no fill kernel inside a captured iteration."""
+    key = (n, str(device))
+    t = _ones_cache.get(key)
+    if t is None:
+        t = _ones_cache[key] = torch.ones(n, dtype=F32, device=device)
+    return t
 
 
 def d_grad_penalty(net, x_hat, lam, sink, gscale=1.0):
@@ -497,17 +530,22 @@ def d_grad_penalty(net, x_hat, lam, sink, gscale=1.0):
     (scaled by gscale).  Returns (penalty [1] fp32, callable that runs the double backward into a sink)."""
     scores, ctx = d_forward(net, x_hat, save=True)
     B = ctx.B
-    ones = torch.ones(B, dtype=F32, device=scores.device)
+    ones = _ones(B, scores.device)
     record = SimpleNamespace()
     g_xp = d_backward(net, ctx, ones, None, want_gxp=True, record=record)
     ns = 0.5 if ctx.pooled else 1.0       # ||unpool(g)/4|| = ||g|| / 2
     pen, coeff = ops.gp_loss(g_xp, ns, float(lam), gscale=1.0)
 
     def backward(into, scale=1.0, scale_tensor=None):
+        """into: one sink for both sweeps (its kernels then run in stream order on ONE stream -- see below), or a pair
+        (sink of sweep 1, sink of sweep 2): the two sweeps contribute to the same parameters from side streams."""
         c = coeff if scale_tensor is None else coeff * scale_tensor
         ghat_xp = ops.scale_rows(g_xp, c, ns * ns * scale)
-        addins = d_double_backward_sweep1(net, ctx, record, ghat_xp, into)
-        d_backward(net, ctx, None, into, addins=addins)
+        s1, s2 = into if isinstance(into, tuple) else (into, into)
+        addins = d_double_backward_sweep1(net, ctx, record, ghat_xp, s1)
+        if s1 is s2 and s1 is not None:
+            side_join()        # sweep 2 read-modify-writes what sweep 1's side-stream kernels are still producing
+        d_backward(net, ctx, None, s2, addins=addins)
 
     if sink is not None:
         backward(sink, gscale)

@@ -141,17 +141,50 @@ def conv3x3_dbl(ghat_x, w_fwd, scale, leak, y, r, gy):
     return ghat_y, ahat
 
 
-def conv3x3_wgrad(x, ga, scale, dw):
-    """dw (fp32 [cout, cin, 3, 3]) += scale * corr(x, ga)"""
+def _workspace(nbytes, device):
+    """fp32 scratch from torch's caching allocator, allocated on the CURRENT stream (so a kernel launched on a side
+    stream gets a block that only that stream's later allocations can reuse)."""
+    return torch.empty((int(nbytes) + 3) // 4, dtype=F32, device=device)
+
+
+def _pixel_ws(B, C, H, W, device):
+    return _workspace(_lib.call('ngan_pixel_reduction_workspace_bytes', B, C, H, W), device)
+
+
+def conv3x3_wgrad(x, ga, scale, dw, accumulate=True):
+    """dw (fp32 [cout, cin, 3, 3]) (+)= scale * corr(x, ga); deterministic (per-CTA partials added in order)"""
     B, cin, H, W = c8_dims(x)
     cout = c8_dims(ga)[1]
     assert dw.numel() == cout * cin * 9
-    _lib.call('ngan_conv3x3_wgrad', _p(x, BF16), _p(ga, BF16), scale, _p(dw, F32), B, cin, cout, H, W, _stream())
+    ws = _workspace(_lib.call('ngan_conv3x3_wgrad_workspace_bytes', B, cin, cout, H, W), x.device)
+    _lib.call('ngan_conv3x3_wgrad', _p(x, BF16), _p(ga, BF16), scale, _p(dw, F32), int(accumulate), _p(ws, F32), B,
+              cin, cout, H, W, _stream())
 
 
-def bias_grad(ga, gb):
+def bias_grad(ga, gb, accumulate=True):
     B, C, H, W = c8_dims(ga)
-    _lib.call('ngan_bias_grad', _p(ga, BF16), _p(gb, F32), B, C, H, W, _stream())
+    ws = _pixel_ws(B, C, H, W, ga.device)
+    _lib.call('ngan_bias_grad', _p(ga, BF16), _p(gb, F32), int(accumulate), _p(ws, F32), B, C, H, W, _stream())
+
+
+def reduce_partials(partials, n_partials, n, ld, out, scale=1.0, accumulate=False):
+    _lib.call('ngan_reduce_partials', _p(partials, F32), n_partials, n, ld, scale, _p(out, F32), int(accumulate),
+              _stream())
+
+
+def sum_slots(slots, out):
+    """out = slots[0] + slots[1] + ... in slot order; slots: [n_slots, n] fp32"""
+    n_slots, n = slots.shape
+    _lib.call('ngan_sum_slots', _p(slots, F32), n_slots, n, n, _p(out, F32), _stream())
+    return out
+
+
+def memset_zero(t):
+    """cudaMemsetAsync on the current stream (no ATen fill kernel inside the captured iteration)"""
+    if not t.is_contiguous():
+        raise _lib.NganError('memset_zero needs a contiguous tensor')
+    _lib.call('ngan_memset', ctypes.c_void_p(t.data_ptr()), 0, t.numel() * t.element_size(), _stream())
+    return t
 
 
 # ------------------------------------------------------------------------------------------ resampling
@@ -263,21 +296,27 @@ def d_fade_fwd(y_end, xp, w_old, b_old, alpha):
     return out
 
 
-def fromim_bwd(g, xp, w, gw, gb, gscale=1.0, unpool=False, g_img=None, accumulate=False):
+def fromim_bwd(g, xp, w, gw, gb, gscale=1.0, unpool=False, g_img=None, accumulate=False, grad_accumulate=True):
+    """accumulate: g_img += (else =); grad_accumulate: gw / gb += (else =)"""
     B, H, W = xp.shape
     C = w.numel()
     gs, dyn = _scalar(gscale)
+    want = gw is not None or gb is not None
+    ws = _pixel_ws(B, C, H, W, xp.device) if want else None
     _lib.call('ngan_fromim_bwd', _p(g, BF16), int(unpool), gs, dyn, _p(xp, F32), _p(w, F32), _p(gw, F32), _p(gb, F32),
-              _p(g_img, F32), int(accumulate), B, C, H, W, _stream())
+              int(grad_accumulate), _p(ws, F32), _p(g_img, F32), int(accumulate), B, C, H, W, _stream(),
+              launches=1 + (gw is not None) + (gb is not None))
 
 
-def fromim_dbl(ghat_xp, g, w, what, in_scale=1.0, gscale=1.0, unpool=False, want_out=True):
+def fromim_dbl(ghat_xp, g, w, what, in_scale=1.0, gscale=1.0, unpool=False, want_out=True, grad_accumulate=True):
     B, H, W = ghat_xp.shape
     C = w.numel()
     out = c8_empty(B, C, H, W, ghat_xp.device) if want_out else None
     gs, dyn = _scalar(gscale)
+    ws = _pixel_ws(B, C, H, W, ghat_xp.device) if what is not None else None
     _lib.call('ngan_fromim_dbl', _p(ghat_xp, F32), in_scale, _p(g, BF16), int(unpool), gs, dyn, _p(w, F32), _p(out),
-              _p(what, F32), B, C, H, W, _stream())
+              _p(what, F32), int(grad_accumulate), _p(ws, F32), B, C, H, W, _stream(),
+              launches=1 + (what is not None))
     return out
 
 
@@ -289,13 +328,15 @@ def toim_fwd(y, w, out=None):
     return img
 
 
-def toim_bwd(g_img, img, y, r, w, gw, gscale=1.0, want_ga=True, want_gpre=False, leak=0.2):
+def toim_bwd(g_img, img, y, r, w, gw, gscale=1.0, want_ga=True, want_gpre=False, leak=0.2, grad_accumulate=True):
     B, C, H, W = c8_dims(y)
     ga = torch.empty_like(y) if want_ga else None
     gpre = torch.empty((B, H, W), dtype=F32, device=y.device) if want_gpre else None
     gs, dyn = _scalar(gscale)
+    ws = _pixel_ws(B, C, H, W, y.device) if gw is not None else None
     _lib.call('ngan_toim_bwd', _p(g_img, F32), gs, dyn, _p(img, F32), _p(y, BF16), _p(r, F32), _p(w, F32), _p(ga),
-              _p(gpre), _p(gw, F32), leak, B, C, H, W, _stream())
+              _p(gpre), _p(gw, F32), int(grad_accumulate), _p(ws, F32), leak, B, C, H, W, _stream(),
+              launches=1 + (gw is not None))
     return ga, gpre
 
 
@@ -316,10 +357,11 @@ def head_bwd_pn(gout, w, scale, y, r, want_gy=False, leak=0.2):
     return ga, gy
 
 
-def head_wgrad(t, coeff, scale, gw, gb=None):
-    """gw += scale * sum_b coeff[b] * t[b]; gb (the head's bias gradient, optional) += sum_b coeff[b]."""
+def head_wgrad(t, coeff, scale, gw, gb=None, accumulate=True):
+    """gw (+)= scale * sum_b coeff[b] * t[b]; gb (the head's bias gradient, optional) (+)= sum_b coeff[b]."""
     B, C, H, W = c8_dims(t)
-    _lib.call('ngan_head_wgrad', _p(t, BF16), _p(coeff, F32), scale, _p(gw, F32), _p(gb, F32), B, C, H, _stream())
+    _lib.call('ngan_head_wgrad', _p(t, BF16), _p(coeff, F32), scale, _p(gw, F32), _p(gb, F32), int(accumulate), B, C,
+              H, _stream())
 
 
 # ------------------------------------------------------------------------------------------ generator stem
@@ -383,7 +425,9 @@ def gp_loss(g, norm_scale, lam, gscale=1.0):
     B = g.shape[0]
     pen = torch.empty(1, dtype=F32, device=g.device)
     coeff = torch.empty(B, dtype=F32, device=g.device)
-    _lib.call('ngan_gp_loss', _p(g, F32), norm_scale, lam, _p(pen), _p(coeff), gscale, B, g.numel() // B, _stream())
+    ws = _workspace(_lib.call('ngan_gp_loss_workspace_bytes', B), g.device)
+    _lib.call('ngan_gp_loss', _p(g, F32), norm_scale, lam, _p(pen), _p(coeff), gscale, _p(ws, F32), B, g.numel() // B,
+              _stream())
     return pen, coeff
 
 

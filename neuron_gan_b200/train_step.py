@@ -59,27 +59,33 @@ class TrainStep:
                                         # are done -- a loader may start its next big copy behind it (DevicePrefetcher)
 
     # -- flat gradient buffers ---------------------------------------------------------------------------
-    def _bind(self, net):
+    def _bind(self, net, n_slots=1):
+        """One flat fp32 gradient buffer per network (`p.grad` are views of it -> one all-reduce, one Adam launch).
+        Every gradient kernel OVERWRITES its parameter's tensor without atomics (bit-reproducible).  The critic's
+        weights receive three contributions per step that run concurrently -- the Wasserstein backward and the two
+        sweeps of the penalty's double backward -- so the critic gets three slot buffers (one sink each) that
+        ops.sum_slots adds in a fixed order into the flat buffer; (parameter, slot) pairs no kernel writes stay zero
+        from allocation.  Nothing is zeroed per step (the reference's zero_grad(), train.py:357, 375)."""
         active = net.active_parameters()
         key = tuple(id(p) for p in active)
         ent = self._bound.get(id(net))
         if ent is None or ent['key'] != key:
             n = sum(p.numel() for p in active)
-            flat = torch.zeros(n, dtype=F32, device=active[0].device)
-            sink, off = {}, 0
+            dev = active[0].device
+            flat = torch.zeros(n, dtype=F32, device=dev)
+            slots = torch.zeros((n_slots, n), dtype=F32, device=dev) if n_slots > 1 else flat.view(1, n)
+            sinks, off = [engine.Sink(accumulate=False) for _ in range(n_slots)], 0
             for p in net.parameters():
                 p.grad = None
             # the generator's Linear weight goes last: it is produced last in backward and is its own bucket
             for p in sorted(active, key=lambda q: q.numel() > (1 << 22)):
-                v = flat[off:off + p.numel()].view(p.shape)
-                p.grad = v
-                sink[id(p)] = v
+                p.grad = flat[off:off + p.numel()].view(p.shape)
+                for k in range(n_slots):
+                    sinks[k][id(p)] = slots[k, off:off + p.numel()].view(p.shape)
                 off += p.numel()
-            # `small`: everything but a trailing big tensor (the Linear weight), whose gradient is overwritten
-            big = sum(p.numel() for p in active if p.numel() > (1 << 22))
-            ent = {'key': key, 'flat': flat, 'sink': sink, 'small': flat[:n - big] if big else flat}
+            ent = {'key': key, 'flat': flat, 'sinks': sinks, 'slots': slots if n_slots > 1 else None}
             self._bound[id(net)] = ent
-        return ent['flat'], ent['sink']
+        return ent['flat'], ent['sinks']
 
     def _allreduce(self, flat):
         if self.dp:
@@ -133,8 +139,7 @@ class TrainStep:
         (atomics): they run on two streams, so the narrow low-resolution kernels of one fill the SMs the other
         leaves idle."""
         G, D, B = self.G, self.D, buf.B
-        flat_d, sink_d = self._bind(D)
-        flat_d.zero_()
+        flat_d, (sink_w, sink_s1, sink_s2) = self._bind(D, 3)
         engine.g_forward(G, buf.z12, save=False, img_out=buf.imgs[B:])
         main = torch.cuda.current_stream()
         fork = self.fork_chains
@@ -145,16 +150,17 @@ class TrainStep:
             self._chain_stream.wait_stream(main)
         with torch.cuda.stream(self._chain_stream if fork else main):
             x_hat = ops.interp_images(buf.imgs[:B], buf.imgs[2 * B:], buf.eps)
-            buf.out.pen, _, _ = engine.d_grad_penalty(D, x_hat, self.lam, sink_d)
+            buf.out.pen, _, _ = engine.d_grad_penalty(D, x_hat, self.lam, (sink_s1, sink_s2))
             del x_hat
         scores, ctx = engine.d_forward(D, buf.imgs[:2 * B], save=True)
         gout = torch.empty(2 * B, dtype=F32, device=scores.device)
         buf.out.out3, _, _ = ops.wloss_into(scores[:B], scores[B:], self.drift, gout[:B], gout[B:])
-        engine.d_backward(D, ctx, gout, sink_d)
+        engine.d_backward(D, ctx, gout, sink_w)
         del ctx
         if fork:
             main.wait_stream(self._chain_stream)
         engine.side_join()
+        ops.sum_slots(self._bound[id(D)]['slots'], flat_d)
         return flat_d
 
     def _seg_g(self, buf, adam_d=True):
@@ -162,8 +168,7 @@ class TrainStep:
         G, D = self.G, self.D
         if adam_d:
             self.opt_d.launch()
-        flat_g, sink_g = self._bind(G)
-        self._bound[id(G)]['small'].zero_()           # the Linear weight's 67 MB gradient is overwritten instead
+        flat_g, (sink_g,) = self._bind(G)
         fake, gctx = engine.g_forward(G, buf.z3, save=True)
         s_fake, dctx = engine.d_forward(D, fake, save=True)
         buf.out.out1, g_fake = ops.gloss(s_fake)
@@ -190,7 +195,7 @@ class TrainStep:
         return stats
 
     def _run_eager_body(self, buf):
-        self._bind(self.D)          # p.grad views must exist before advance(): it skips parameters without grad
+        self._bind(self.D, 3)       # p.grad views must exist before advance(): it skips parameters without grad
         self._bind(self.G)
         self.opt_d.advance()
         self.opt_g.advance()
@@ -204,7 +209,7 @@ class TrainStep:
         (z1, z2, eps) tuples followed by one z3."""
         B, R = images.shape[0], images.shape[-1]
         buf = self._buffers(B, R, dev)
-        self._bind(self.D)
+        self._bind(self.D, 3)
         self._bind(self.G)
         for j in range(self.n_critic):
             if draws is None:
@@ -379,24 +384,3 @@ def build_networks(res=16, alpha=1.0, seed=1, device='cuda', gen_features=None, 
         G.set_resolution(res, alpha)
         D.set_resolution(res, alpha)
     return G.to(device), D.to(device)
-
-
-def smoke_check(device, res=16, batch=4, tol=1e-2):
-    """One tiny iteration on the GPU, compared with the CPU oracle on the same seeds (used by
-    __graft_entry__.smoke; the oracle is only the checker here)."""
-    from oracle import pggan_oracle as O
-    arch = O.Arch()
-    tr = O.Trainer(arch, seed=1, res=res, alpha=1.0)
-    rng = torch.get_rng_state()
-    x = O.synthetic_images(batch, res)
-    ref = tr.iteration(x)
-    G, D = build_networks(res, 1.0, seed=1, device=device)
-    step = TrainStep(G, D)
-    torch.set_rng_state(rng)
-    stats = step(x.to(device)).cpu()
-    got = TrainStep.stats_dict(stats)
-    for k, v in ref.items():
-        if abs(got[k] - v) > tol * max(1.0, abs(v)):
-            raise AssertionError(f'smoke: {k} = {got[k]} differs from the oracle {v}')
-    print('smoke ok:', got)
-    return got

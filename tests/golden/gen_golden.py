@@ -36,6 +36,7 @@ CASES = [  # (res, alpha, batch)
     (256, 1.0, 1),
     (512, 0.5, 1),
     (512, 1.0, 2),     # BASELINE config 3 shape (reduced batch)
+    (512, 1.0, 16),    # BASELINE config 3 at its per-GPU batch (16 images per GPU)
 ]
 
 

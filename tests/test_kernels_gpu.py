@@ -42,6 +42,10 @@ CONV_SHAPES = [  # B, cin, cout, H, W
     (3, 128, 128, 16, 16), (1, 16, 16, 256, 256), (1, 16, 16, 40, 72),
     (9, 16, 16, 256, 256), (40, 32, 32, 64, 64), (48, 64, 64, 32, 32),     # several tiles per persistent CTA
 ]
+# the tile plans of the benched configuration (BASELINE config 3: 512x512, 16 images per GPU; the critic batches
+# [real; fake] -> 32) -- the launches bench.py's roofline line is measured on
+BENCH_SHAPES = [(16, 16, 16, 512, 512), (32, 16, 16, 512, 512), (16, 32, 16, 256, 256), (32, 16, 32, 128, 128)]
+CONV_SHAPES_ALL = CONV_SHAPES + BENCH_SHAPES
 
 
 def test_layout_roundtrip():
@@ -53,7 +57,7 @@ def test_layout_roundtrip():
     assert torch.equal(o.c8_to_nchw(c8), x)
 
 
-@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES)
+@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES_ALL)
 @pytest.mark.parametrize('use_bias', [False, True])
 def test_conv3x3_fwd(B, cin, cout, H, W, use_bias):
     o = ops()
@@ -70,7 +74,7 @@ def test_conv3x3_fwd(B, cin, cout, H, W, use_bias):
     assert rel(r, r_ref[:, 0]) < 2e-3
 
 
-@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES)
+@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES_ALL)
 def test_conv3x3_dgrad_and_pn(B, cin, cout, H, W):
     o = ops()
     ga = rnd(B, cout, H, W, seed=4)
@@ -93,7 +97,7 @@ def test_conv3x3_dgrad_and_pn(B, cin, cout, H, W):
     assert rel(o.c8_to_nchw(gy), gx_ref) < 6e-3
 
 
-@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES[:11])
+@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES[:11] + BENCH_SHAPES[:1] + BENCH_SHAPES[2:])
 def test_conv3x3_double_backward(B, cin, cout, H, W):
     """conv3x3_dbl against autograd's double backward of conv -> LeakyReLU -> PixelNorm."""
     o = ops()
@@ -117,7 +121,7 @@ def test_conv3x3_double_backward(B, cin, cout, H, W):
     assert rel(o.c8_to_nchw(ahat), cot_a) < 2e-2
 
 
-@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES[:12] + CONV_SHAPES[13:14])
+@pytest.mark.parametrize('B,cin,cout,H,W', CONV_SHAPES[:12] + CONV_SHAPES[13:] + BENCH_SHAPES)
 def test_conv3x3_wgrad(B, cin, cout, H, W):
     o = ops()
     x = rnd(B, cin, H, W, seed=12)
@@ -125,10 +129,16 @@ def test_conv3x3_wgrad(B, cin, cout, H, W):
     s = 0.37
     dw_ref = s * torch.nn.grad.conv2d_weight(x, (cout, cin, 3, 3), ga, padding=1)
     dw = torch.zeros(cout, cin, 3, 3, device='cuda')
-    o.conv3x3_wgrad(o.nchw_to_c8(x), o.nchw_to_c8(ga), s, dw)
+    xc, gc = o.nchw_to_c8(x), o.nchw_to_c8(ga)
+    o.conv3x3_wgrad(xc, gc, s, dw)
     assert rel(dw, dw_ref) < 2e-3
-    o.conv3x3_wgrad(o.nchw_to_c8(x), o.nchw_to_c8(ga), s, dw)          # accumulates
+    first = dw.clone()
+    o.conv3x3_wgrad(xc, gc, s, dw)                                     # accumulates
     assert rel(dw, 2 * dw_ref) < 2e-3
+    # overwrite mode needs no zeroing, and the reduction is deterministic: bit-identical from run to run
+    dw2 = torch.full_like(dw, float('nan'))
+    o.conv3x3_wgrad(xc, gc, s, dw2, accumulate=False)
+    assert torch.equal(dw2, first)
 
 
 @pytest.mark.parametrize('C,H,W', [(16, 8, 8), (32, 16, 24), (128, 16, 16)])
@@ -223,6 +233,20 @@ def test_fromim_toim(C):
     assert rel(gpre, gpre_ref) < 1e-4
     assert rel(o.c8_to_nchw(ga), ga_ref) < 8e-3
     assert rel(gw, (gpre_ref.unsqueeze(1) * y).sum((0, 2, 3))) < 1e-4
+    # overwrite mode (no zeroing) gives the same bits as accumulation into zeros, run after run
+    gw_o = torch.full((C,), float('nan'), device='cuda')
+    o.toim_bwd(g_img, img, o.nchw_to_c8(y), r[:, 0].contiguous(), wt, gw_o, gscale=0.7, grad_accumulate=False)
+    assert torch.equal(gw_o, gw)
+    gw_f, gb_f = torch.full((C,), float('nan'), device='cuda'), torch.full((C,), float('nan'), device='cuda')
+    o.fromim_bwd(o.nchw_to_c8(g), xp, w, gw_f, gb_f, gscale=0.5, grad_accumulate=False)
+    assert rel(gw_f, 0.5 * (g * xp.unsqueeze(1)).sum((0, 2, 3))) < 1e-4 and rel(gb_f, 0.5 * g.sum((0, 2, 3))) < 1e-4
+    what_o = torch.full((C,), float('nan'), device='cuda')
+    o.fromim_dbl(ghat, o.nchw_to_c8(g), w, what_o, in_scale=2.0, gscale=0.5, grad_accumulate=False)
+    assert torch.equal(what_o, what)
+    # the fade kernel without a bias (the double backward's cotangent blend)
+    fade0 = o.d_fade_fwd(o.nchw_to_c8(y_end), xp, w, None, 0.3)
+    f0 = w.view(1, C, 1, 1) * xp.unsqueeze(1)
+    assert rel(o.c8_to_nchw(fade0), f0 + 0.3 * (y_end - f0)) < 4e-3
 
 
 @pytest.mark.parametrize('B', [1, 5])
@@ -253,6 +277,11 @@ def test_head(B):
     gb = torch.zeros(C, device='cuda')
     o.bias_grad(o.nchw_to_c8(y), gb)
     assert rel(gb, y.sum((0, 2, 3))) < 1e-4
+    # overwrite mode, bit-reproducible (no atomics anywhere in the parameter-gradient kernels)
+    gw2, gb2 = torch.full_like(gw, float('nan')), torch.full((C,), float('nan'), device='cuda')
+    o.head_wgrad(o.nchw_to_c8(y), gout, s, gw2, accumulate=False)
+    o.bias_grad(o.nchw_to_c8(y), gb2, accumulate=False)
+    assert rel(gw2, s * (y * gout.view(B, 1, 1, 1)).sum(0, keepdim=True)) < 1e-4 and torch.equal(gb2, gb)
 
 
 @pytest.mark.parametrize('B', [3, 16, 40])
@@ -293,6 +322,19 @@ def test_losses():
     assert torch.allclose(pen[0], pen_ref, rtol=1e-5)
     # d pen / d g = coeff_b * norm_scale^2 * g
     assert torch.allclose(o.scale_rows(g.detach(), coeff, 0.25), gref, rtol=1e-4, atol=1e-8)
+    pen2, coeff2 = o.gp_loss(g.detach(), 0.5, 10.0)
+    assert torch.equal(pen, pen2) and torch.equal(coeff, coeff2)              # deterministic reduction
+    # a sample with an exactly zero input gradient: torch's norm backward gives the zero subgradient there
+    # (loss_functions.py:176); the coefficient must be 0, not -inf (which scale_rows would turn into NaN)
+    gz = g.detach().clone()
+    gz[3] = 0
+    pen_z, coeff_z = o.gp_loss(gz, 0.5, 10.0)
+    gzr = gz.clone().requires_grad_()
+    pen_zr = 10 * (((0.5 * gzr.flatten(1).norm(dim=1)) - 1) ** 2).mean()
+    gz_ref, = torch.autograd.grad(pen_zr, gzr)
+    assert torch.allclose(pen_z[0], pen_zr, rtol=1e-5) and coeff_z[3].item() == 0.0
+    out = o.scale_rows(gz, coeff_z, 0.25)
+    assert torch.isfinite(out).all() and torch.allclose(out, gz_ref, rtol=1e-4, atol=1e-8)
 
 
 def test_adam_multi():
