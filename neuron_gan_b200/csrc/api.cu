@@ -45,7 +45,7 @@ using namespace ngan;
         }                              \
     } while (0)
 
-namespace ngan { extern long long* g_conv_trace; }
+namespace ngan { extern long long* g_conv_trace; extern long long* g_wgrad_trace; }
 
 extern "C" {
 
@@ -54,6 +54,11 @@ int ngan_version(void) { return 100; }
 int ngan_debug_conv_trace(long long* host_out) {
     if (!ngan::g_conv_trace) return -1;
     return check_cuda(cudaMemcpy(host_out, ngan::g_conv_trace, 32 * 8 * sizeof(long long), cudaMemcpyDeviceToHost), "trace");
+}
+// undocumented debug hook: device buffer (8 long long per CTA) that the next wgrad launches stamp with %globaltimer
+int ngan_debug_wgrad_trace(long long* device_buf) {
+    ngan::g_wgrad_trace = device_buf;
+    return 0;
 }
 const char* ngan_last_error(void) { return g_err; }
 

@@ -58,8 +58,19 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     const int o = threadIdx.x % OPB, s = threadIdx.x / OPB;
     const long long i = static_cast<long long>(blockIdx.x) * OPB + o;
     float v = 0.f;
-    if (i < n)
-        for (int p = s; p < n_partials; p += S) v += partials[p * ld + i];
+    if (i < n) {
+        const float* src = partials + i;
+        int p = s;
+        // eight loads in flight, added in row order (the order of additions is part of the contract)
+        for (; p + 7 * S < n_partials; p += 8 * S) {
+            float t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = __ldg(src + static_cast<long long>(p + k * S) * ld);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v += t[k];
+        }
+        for (; p < n_partials; p += S) v += __ldg(src + static_cast<long long>(p) * ld);
+    }
     red[s][o] = v;
     __syncthreads();
     if (s == 0 && i < n) {
@@ -72,9 +83,14 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 }
 int reduce_partials(const float* partials, int n_partials, long long n, long long ld, float scale, float* out,
                     int accumulate, cudaStream_t st) {
+    // outputs per block: wide results with few partial rows take 64 (coalesced 256-byte rows, 4 slices); many partial
+    // rows are split over 16 or 32 slices so that no thread walks more than a few dozen rows
     cudaError_t e;
-    if (n >= 2048)
+    if (n >= 2048 && n_partials <= 32)
         e = launch_pdl(reduce_partials_kernel<64>, dim3(static_cast<unsigned>((n + 63) / 64)), dim3(256), 0, st,
+                       partials, n_partials, n, ld, scale, out, accumulate);
+    else if (n >= 2048)
+        e = launch_pdl(reduce_partials_kernel<16>, dim3(static_cast<unsigned>((n + 15) / 16)), dim3(256), 0, st,
                        partials, n_partials, n, ld, scale, out, accumulate);
     else
         e = launch_pdl(reduce_partials_kernel<8>, dim3(static_cast<unsigned>((n + 7) / 8)), dim3(256), 0, st, partials,

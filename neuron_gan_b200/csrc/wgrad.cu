@@ -17,10 +17,10 @@
 // horizontal tap kx serves the three vertical taps (ga rows rho, rho-1, rho-2), so a strip of RB rows costs
 // 3*(RB+2) + RB ldmatrix instead of 10*RB -- the kernel was bound by that shared-memory traffic, not by HMMA.
 //
-// Reduction over pixels is DETERMINISTIC: CTAs are persistent over pixel tiles in a fixed order, each writes
-// its partial block sums with plain coalesced stores into a workspace laid out like dW ([pixel CTA][cout][cin][9]),
-// and reduce_partials (elementwise.cu) adds the partials in index order.  No atomics: the gradient is bit-identical
-// from run to run, and the low-resolution launches no longer pay 1-2.6 M global atomics for a 10-600 KB result.
+// Reduction over pixels is DETERMINISTIC: CTAs are persistent over pixel tiles in a fixed order, each writes its
+// partial block sums with plain coalesced stores into a workspace (one image of cout*cin*9 floats per pixel CTA or
+// cluster, in register order), and wgrad_reduce_kernel adds the images in index order.  No atomics: the gradient
+// is bit-identical from run to run.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -38,15 +38,27 @@ struct WgradArgs {
     int ci_g, co_g;       // channels of x / ga handled by one CTA
     int n_ci_groups;
     int n_stage;          // depth of the TMA ring (2..kWgMaxStages)
+    int cluster;          // CTAs per cluster along grid.x (1, 2, 4 or 8): DSMEM reduction before the partial store
     uint32_t x_stage_bytes, g_stage_bytes;
-    float* partial;       // [gridDim.x][cout][cin][9]
+    float* partial;       // [gridDim.x / cluster][gridDim.y groups][n_blk][18][32][4]: register order, see the flush
+    long long* dbg;       // timing experiments (ngan_debug_wgrad_trace): 8 globaltimer stamps per CTA, or null
 };
+long long* g_wgrad_trace = nullptr;
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define WG_STAMP(k)                                                                                        \
+    do {                                                                                                   \
+        if (a.dbg && threadIdx.x == 0) a.dbg[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (k)] = gtime(); \
+    } while (0)
 
 constexpr int kWgTH = 8;
 constexpr int kWgMaxStages = 6;
 
 struct WgradPlan {
-    int ci_g, co_g, n_ci_groups, n_groups, n_blk, TW, tiles_x, tiles_y, n_tiles, per_group, rb;
+    int ci_g, co_g, n_ci_groups, n_groups, n_blk, TW, tiles_x, tiles_y, n_tiles, per_group, rb, cluster;
 };
 
 static bool wgrad_plan(int B, int cin, int cout, int H, int W, WgradPlan* p) {
@@ -66,20 +78,22 @@ static bool wgrad_plan(int B, int cin, int cout, int H, int W, WgradPlan* p) {
     p->n_tiles = p->tiles_x * p->tiles_y * B;
     // rows per strip: with one accumulator block per CTA all eight warps split the tile, so strips are half height
     p->rb = p->n_blk == 1 ? 4 : 8;
-    // CTAs along the pixel dimension.  Large problems: two CTAs per SM over all channel groups.  Small ones: every
-    // pixel CTA costs one partial image of the group's block (written, then read by the reduction), so no more CTAs
-    // than keep that traffic near the operand traffic, and never more than tiles.
+    // CTAs along the pixel dimension: one resident wave (148 CTAs over all channel groups) up to a few tiles per
+    // CTA, two CTAs per SM beyond that (measured in round 1, graph-timed).  Every pixel CTA (or cluster) ends with one
+    // partial image of its group's blocks, so low-resolution launches -- few pixels, up to 590 KB of gradient --
+    // first add the partials of 4 neighbouring CTAs through distributed shared memory (in rank order).
     static const int target_env = getenv("NGAN_WGRAD_CTAS") ? atoi(getenv("NGAN_WGRAD_CTAS")) : 0;
     const long long work = static_cast<long long>(p->n_tiles) * p->n_groups;
     const int target = target_env ? target_env : (work >= 4LL * 148 ? 2 * 148 : 148);
     int per_group = target / p->n_groups;
-    const long long in_bytes = static_cast<long long>(B) * H * W * (cin + cout) * 2;
-    const long long blk_bytes = static_cast<long long>(cin) * cout * 9 * 4;
-    long long cap = 2 * in_bytes / blk_bytes;
-    if (cap < 4) cap = 4;
-    if (!target_env && per_group > cap) per_group = static_cast<int>(cap);
     if (per_group > p->n_tiles) per_group = p->n_tiles;
     if (per_group < 1) per_group = 1;
+    static const int cluster_env = getenv("NGAN_WGRAD_CLUSTER") ? atoi(getenv("NGAN_WGRAD_CLUSTER")) : -1;
+    const int cluster_max = cluster_env >= 0 ? cluster_env : (H <= 32 ? 4 : 1);
+    int cs = 1;
+    while (cs * 2 <= cluster_max && cs * 2 <= 8 && cs * 2 <= per_group) cs *= 2;
+    per_group = per_group / cs * cs;
+    p->cluster = cs;
     p->per_group = per_group;
     return true;
 }
@@ -87,7 +101,34 @@ static bool wgrad_plan(int B, int cin, int cout, int H, int W, WgradPlan* p) {
 size_t conv3x3_wgrad_workspace_bytes(int B, int cin, int cout, int H, int W) {
     WgradPlan p;
     if (!wgrad_plan(B, cin, cout, H, W, &p)) return 0;
-    return static_cast<size_t>(p.per_group) * cin * cout * 9 * sizeof(float);
+    return static_cast<size_t>(p.per_group / p.cluster) * cin * cout * 9 * sizeof(float);
+}
+
+// ---- thread-block cluster helpers (distributed shared memory)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_saddr, uint32_t rank) {
+    uint32_t ra;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_dsmem_f32x4(uint32_t local_saddr, uint32_t rank) {
+    uint32_t ra;
+    float4 v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(rank));
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(ra)
+                 : "memory");
+    return v;
 }
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
@@ -134,6 +175,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
                                                             const __grid_constant__ CUtensorMap tmap_g,
                                                             const WgradArgs a) {
     extern __shared__ uint8_t smem_raw[];
+    WG_STAMP(0);
     pdl_trigger();        // the reduction that follows may be scheduled while this grid drains (it waits for all of it)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     // ring of n_stage {x tile, ga tile} slots followed by the mbarriers
@@ -161,6 +203,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
     }
     __syncthreads();
     pdl_wait();           // x / ga come from the kernels before this one in the stream
+    WG_STAMP(1);
 
     auto issue = [&](int tile, int stage) {
         const int tx = tile % a.tiles_x;
@@ -198,6 +241,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
         const int ahead = tile + (a.n_stage - 1) * gridDim.x;
         if (threadIdx.x == 0 && ahead < a.n_tiles) issue(ahead, stage == 0 ? a.n_stage - 1 : stage - 1);
         mbar_wait(bars + stage, phase);
+        if (tile == static_cast<int>(blockIdx.x)) WG_STAMP(2);
 
         const uint32_t xb = smem_u32(smem + stage * slot_bytes), gb = xb + a.x_stage_bytes;
         // per-lane ldmatrix row addresses (matrix = lane/8, row = lane%8)
@@ -218,36 +262,109 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const __grid_constan
         }
     }
 
-    // ---- flush: acc[tap][nb] = D[co = g (+8)][ci = nb*8 + 2t (+1)].  Every warp stores its accumulator block to its
-    // own slice of shared memory (the operand slots are drained by now), the CTA sums the slices of the warps that
-    // shared a block in warp order, and writes the block into this pixel CTA's partial image, which is laid out like
-    // the gradient tensor itself ([co][ci][tap]): 144 consecutive floats per (block, co) row.
-    float* s_red = reinterpret_cast<float*>(smem);   // [8 warps = rsplit x n_blk][16 co][16 ci][9 taps]
-    const int g = lane >> 2, t = lane & 3;
+    // ---- flush.  acc[tap][nb][k] = D[co = g + 8*(k>>1)][ci = nb*8 + 2t + (k&1)] with g = lane/4, t = lane%4.  The
+    // partial image of this pixel CTA (or cluster) keeps that REGISTER ORDER -- [group][block][tap*2+nb][lane][k] --
+    // so every store below is a conflict-free, fully coalesced float4 and nothing is transposed or divided here (the
+    // transposing flush of round 1 cost 4-16 us per launch, more than the main loop of the low-resolution layers);
+    // wgrad_reduce_kernel undoes the permutation once, when it writes the summed gradient.
+    WG_STAMP(3);
+    float4* s4 = reinterpret_cast<float4*>(smem);    // [8 warps = rsplit x n_blk][18][32 lanes] float4
     {
-        float* mine = s_red + warp * 2304;
+        float4* mine = s4 + warp * 576;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
             for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int co = g + (k >> 1) * 8;
-                    const int ci = nb * 8 + 2 * t + (k & 1);
-                    mine[(co * 16 + ci) * 9 + tap] = acc[tap][nb][k];
-                }
+                mine[(tap * 2 + nb) * 32 + lane] =
+                    make_float4(acc[tap][nb][0], acc[tap][nb][1], acc[tap][nb][2], acc[tap][nb][3]);
     }
     __syncthreads();
-    float* out = a.partial + static_cast<size_t>(blockIdx.x) * a.cout * a.cin * 9;
-    const int n_out = n_blk * 2304;
-    for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
-        const int b = i / 2304, rem = i - b * 2304;
-        float v = 0.f;
-        for (int r = 0; r < rsplit; ++r) v += s_red[(r * n_blk + b) * 2304 + rem];     // warp = rs * n_blk + blk
-        const int co = rem / 144, j = rem - co * 144;        // j = ci * 9 + tap
-        const int co_abs = co_group * a.co_g + (b / n_ci_blk) * 16 + co;
-        const int ci0 = ci_group * a.ci_g + (b % n_ci_blk) * 16;
-        out[(static_cast<size_t>(co_abs) * a.cin + ci0) * 9 + j] = v;
+    const int n4 = n_blk * 576;
+    float4* out4 = reinterpret_cast<float4*>(a.partial) +
+                   (static_cast<size_t>(blockIdx.x / a.cluster) * gridDim.y + group) * n4;
+    auto fold = [&](int i) {             // sum over the warps that shared block b, in warp order
+        const int b = i / 576, rem = i - b * 576;
+        float4 v = s4[b * 576 + rem];    // warp = rs * n_blk + blk
+        for (int r = 1; r < rsplit; ++r) {
+            const float4 w = s4[(r * n_blk + b) * 576 + rem];
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        return v;
+    };
+    if (a.cluster == 1) {
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) out4[i] = fold(i);
+        WG_STAMP(4);
+        return;
+    }
+    // Cluster of a.cluster CTAs along the pixel dimension (same channel group, same outputs): every CTA first folds
+    // its warps' slices into the compact array s4[0 .. n4), then CTA q of the cluster adds slice q of the outputs
+    // over all CTAs in rank order through distributed shared memory and stores it.
+    if (rsplit > 1) {
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) s4[i] = fold(i);   // element i is only touched by this thread
+    }
+    cluster_sync();
+    const int per = n4 / a.cluster;
+    const uint32_t q = cluster_ctarank();
+    const uint32_t base = smem_u32(s4);
+    for (int k = threadIdx.x; k < per; k += blockDim.x) {
+        const int i = static_cast<int>(q) * per + k;
+        float4 v = ld_dsmem_f32x4(base + i * 16, 0);
+        for (int rk = 1; rk < a.cluster; ++rk) {
+            const float4 w = ld_dsmem_f32x4(base + i * 16, rk);
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        out4[i] = v;
+    }
+    cluster_sync();               // nobody leaves while a neighbour may still read its shared memory
+    WG_STAMP(4);
+}
+
+// Second stage: dW (+)= scale * sum_p partial[p], rows added in index order; one thread per float4 of the register-
+// order image (coalesced reads), which it scatters to its four places in the torch-layout gradient [cout][cin][3][3].
+template <int OPB>
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restrict__ partials, int n_partials,
+                                                           int n4_total, int n_blk, int n_ci_blk, int n_ci_groups,
+                                                           int ci_g, int co_g, int cin, float scale,
+                                                           float* __restrict__ dw, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int S = 256 / OPB;
+    __shared__ float4 red[S][OPB];
+    const int o = threadIdx.x % OPB, s = threadIdx.x / OPB;
+    const int e = blockIdx.x * OPB + o;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e < n4_total) {
+        const float4* src = partials + e;
+        int p = s;
+        for (; p + 3 * S < n_partials; p += 4 * S) {      // four loads in flight, added in row order
+            float4 t[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = __ldg(src + static_cast<size_t>(p + k * S) * n4_total);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { v.x += t[k].x; v.y += t[k].y; v.z += t[k].z; v.w += t[k].w; }
+        }
+        for (; p < n_partials; p += S) {
+            const float4 t = __ldg(src + static_cast<size_t>(p) * n4_total);
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+    }
+    red[s][o] = v;
+    __syncthreads();
+    if (s != 0 || e >= n4_total) return;
+#pragma unroll
+    for (int k = 1; k < S; ++k) { v.x += red[k][o].x; v.y += red[k][o].y; v.z += red[k][o].z; v.w += red[k][o].w; }
+    const int per_group = n_blk * 576;
+    const int group = e / per_group, r1 = e - group * per_group;
+    const int blk = r1 / 576, r2 = r1 - blk * 576;
+    const int q = r2 >> 5, lane = r2 & 31;
+    const int tap = q >> 1, nb = q & 1, g = lane >> 2, t = lane & 3;
+    const int co0 = (group / n_ci_groups) * co_g + (blk / n_ci_blk) * 16 + g;
+    const int ci0 = (group % n_ci_groups) * ci_g + (blk % n_ci_blk) * 16 + nb * 8 + 2 * t;
+    const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float* dst = dw + (static_cast<size_t>(co0 + (k >> 1) * 8) * cin + ci0 + (k & 1)) * 9 + tap;
+        *dst = accumulate ? *dst + scale * vals[k] : scale * vals[k];
     }
 }
 
@@ -266,6 +383,8 @@ int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int acc
     a.x_stage_bytes = ((a.ci_g / 8) * x_plane + 127) & ~127u;
     a.g_stage_bytes = ((a.co_g / 8) * g_plane + 127) & ~127u;
     a.partial = workspace;
+    a.cluster = p.cluster;
+    a.dbg = g_wgrad_trace;
     int n_stage = static_cast<int>((112u * 1024) / (a.x_stage_bytes + a.g_stage_bytes));   // two CTAs per SM stay resident
     if (n_stage > kWgMaxStages) n_stage = kWgMaxStages;
     if (n_stage < 2) n_stage = 2;
@@ -289,15 +408,45 @@ int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int acc
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(wgrad)");
         configured = true;
     }
-    cudaError_t le = p.rb == 4 ? launch_pdl(conv3x3_wgrad_kernel<4>, dim3(p.per_group, p.n_groups), dim3(256),
-                                            smem_bytes, st, tmx, tmg, a)
-                               : launch_pdl(conv3x3_wgrad_kernel<8>, dim3(p.per_group, p.n_groups), dim3(256),
-                                            smem_bytes, st, tmx, tmg, a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.per_group, p.n_groups);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
+    if (pdl_enabled()) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
+    if (p.cluster > 1) {
+        attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+        attr[n_attr].val.clusterDim.x = p.cluster;
+        attr[n_attr].val.clusterDim.y = 1;
+        attr[n_attr].val.clusterDim.z = 1;
+        ++n_attr;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n_attr;
+    cudaError_t le = p.rb == 4 ? cudaLaunchKernelEx(&cfg, conv3x3_wgrad_kernel<4>, tmx, tmg, a)
+                               : cudaLaunchKernelEx(&cfg, conv3x3_wgrad_kernel<8>, tmx, tmg, a);
     if (le != cudaSuccess) return check_cuda(le, "cudaLaunchKernelEx(conv3x3_wgrad)");
     rc = check_launch("conv3x3_wgrad");
     if (rc) return rc;
-    const long long n = static_cast<long long>(cin) * cout * 9;
-    return reduce_partials(workspace, p.per_group, n, n, scale, dw, accumulate, st);
+    const int n4_total = cin * cout * 9 / 4, n_part = p.per_group / p.cluster;
+    const int n_ci_blk = p.ci_g / 16;
+    cudaError_t re;
+    if (n_part <= 32)
+        re = launch_pdl(wgrad_reduce_kernel<64>, dim3((n4_total + 63) / 64), dim3(256), 0, st,
+                        reinterpret_cast<const float4*>(workspace), n_part, n4_total, p.n_blk, n_ci_blk, p.n_ci_groups,
+                        p.ci_g, p.co_g, cin, scale, dw, accumulate);
+    else
+        re = launch_pdl(wgrad_reduce_kernel<16>, dim3((n4_total + 15) / 16), dim3(256), 0, st,
+                        reinterpret_cast<const float4*>(workspace), n_part, n4_total, p.n_blk, n_ci_blk, p.n_ci_groups,
+                        p.ci_g, p.co_g, cin, scale, dw, accumulate);
+    if (re != cudaSuccess) return check_cuda(re, "cudaLaunchKernelEx(wgrad_reduce)");
+    return check_launch("wgrad_reduce");
 }
 
 }  // namespace ngan
