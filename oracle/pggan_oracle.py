@@ -104,6 +104,46 @@ def _q(x):
 
 
 # ----------------------------------------------------------------------------------------------
+# optional frozen LeakyReLU masks (test aid, off by default)
+# ----------------------------------------------------------------------------------------------
+_FORCED_MASKS = None
+
+
+class forced_masks:
+    """Context manager: every LeakyReLU inside takes its mask (True = positive side) from `masks`, in call order,
+    instead of from the sign of its input.  LeakyReLU is the only non-smooth operation of the networks; at random
+    initialisation the outputs are random-sign sums over pixels, so the ~0.3 % of masks that two bf16 evaluations
+    decide differently move a gradient by ~sqrt(0.3 %) -- that conditioning, not kernel error, is what limits a
+    free-running comparison at 256x256 / 512x512.  With the CUDA path's own masks (recovered from the signs of its
+    saved activations) the oracle is a smooth function of everything else, and whole-network gradients agree to the
+    accumulated rounding error: a composition error in any layer shows at full size."""
+
+    def __init__(self, masks):
+        self.masks = list(masks)
+
+    def __enter__(self):
+        global _FORCED_MASKS
+        self.prev, _FORCED_MASKS = _FORCED_MASKS, iter(self.masks)
+        return self
+
+    def __exit__(self, *exc):
+        global _FORCED_MASKS
+        left = sum(1 for _ in _FORCED_MASKS)
+        _FORCED_MASKS = self.prev
+        if exc[0] is None and left:
+            raise AssertionError(f'forced_masks: {left} masks were not consumed')
+
+
+def lrelu(x, leak):
+    """nn.LeakyReLU (models.py:263, 267, 310, 315, 472)."""
+    if _FORCED_MASKS is None:
+        return F.leaky_relu(x, leak)
+    m = next(_FORCED_MASKS)
+    assert m.shape == x.shape, (m.shape, x.shape)
+    return x * torch.where(m, torch.ones((), dtype=x.dtype), torch.full((), leak, dtype=x.dtype))
+
+
+# ----------------------------------------------------------------------------------------------
 # building blocks
 # ----------------------------------------------------------------------------------------------
 
@@ -142,7 +182,7 @@ def down2_bilinear(x):
 
 def clp(x, w, b, leak):
     """conv -> LeakyReLU -> PixelNorm (models.py:261-268, 312-316, 469-473)."""
-    return _q(pixel_norm(F.leaky_relu(eq_conv(x, w, b, 1, leak), leak)))
+    return _q(pixel_norm(lrelu(eq_conv(x, w, b, 1, leak), leak)))
 
 
 def scale_block(x, w1, w2, up: bool, leak):
@@ -172,7 +212,7 @@ def g_forward(p: dict, z, n_layers: int, alpha: float, arch: Arch):
     alpha < 1: levels 0..n-2 are the stable trunk, level n-1 is being faded in."""
     leak, s0, f0 = arch.leak, arch.size_init, arch.gen_features[0]
     x = eq_linear(z, p['lin.w'], leak).unflatten(1, (f0, s0, s0))          # models.py:299-302
-    x = _q(pixel_norm(F.leaky_relu(x, leak)))                               # models.py:310-311
+    x = _q(pixel_norm(lrelu(x, leak)))                                      # models.py:310-311
     x = clp(x, p['conv0.w'], None, leak)                                    # models.py:312-316
     n_trunk = n_layers - 1 if alpha >= 1 else n_layers - 2
     for i in range(1, n_trunk + 1):

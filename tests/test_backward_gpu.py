@@ -1,14 +1,17 @@
-"""Whole-network backward passes on the B200 driven by WELL-CONDITIONED cotangents, against autograd through the
-oracle with the CUDA path's storage precision emulated (bf16 weights / feature maps), same weights, same inputs.
+"""Whole-network backward passes on the B200 against autograd through the oracle with the CUDA path's storage
+precision emulated (bf16 weights / feature maps), same weights, same inputs, WELL-CONDITIONED cotangents (fixed
+same-signed weights on the critic's scores, a fixed random image on the generator's output -- not the cancelling
+Wasserstein difference of tests/test_step_gpu.py).
 
-Why this file exists: at random initialisation the Wasserstein loss gradient is a difference of nearly equal
-real / fake sums, so end-to-end gradient comparisons at 256x256 / 512x512 are limited by conditioning, not by the
-kernels (tests/test_step_gpu.py::test_gradients_match_bf16_emulating_oracle carries loose bounds there for that
-reason).  Here the cotangents are fixed, same-signed per-sample weights on the critic's scores and a fixed random
-image on the generator's output, so nothing cancels and a composition error of a few percent in ONE layer of the
-hand-written D backward, G backward or gradient-penalty double backward fails the test.
-
-Tolerance: relative L2 per parameter <= 5e-2; measured values are printed."""
+Two comparisons per case:
+  * frozen masks (asserted, rel-L2 per parameter <= 3e-2; measured <= 2e-2 at every resolution): the oracle's LeakyReLUs use the masks the CUDA forward
+    pass decided (signs of its saved activations).  LeakyReLU is the only non-smooth operation; with the masks fixed
+    the oracle is smooth, so the difference is accumulated bf16 rounding only and a composition error of a few
+    percent in ONE layer of the hand-written D backward, G backward or gradient-penalty double backward fails.
+  * free-running masks (printed; asserted only loosely): two bf16 evaluations decide ~0.3 % of the masks differently,
+    and because a random-init network's output is a random-sign sum over pixels, that moves a gradient by
+    ~sqrt(0.3 %) ~ 5 % at 256x256 / 512x512 (measured here: 2-12 %).  That is conditioning, not kernel error -- the
+    frozen-mask numbers of the same run show it."""
 import pytest
 import torch
 
@@ -17,7 +20,8 @@ from oracle import pggan_oracle as O
 pytestmark = pytest.mark.gpu
 ARCH = O.Arch()
 DEV = 'cuda'
-TOL = 5e-2
+TOL = 3e-2          # frozen masks (measured: critic <= 0.9 %, generator <= 2.0 %, penalty <= 0.5 %)
+TOL_FREE = 0.30     # free-running masks (conditioning-limited, see the module docstring)
 
 
 def nets(res, alpha):
@@ -39,18 +43,37 @@ def grads_of(net, km, sink):
     return {name: sink[id(params[key])] for name, key in km.items() if id(params[key]) in sink}
 
 
-def report_and_check(tag, got, ref, names):
-    rep = {}
-    for k in names:
-        assert ref[k] is not None, k
-        rep[k] = rel(got[k].cpu(), ref[k])
+def mask_of(y_c8):
+    from neuron_gan_b200 import ops
+    return (ops.c8_to_nchw(y_c8) > 0).cpu()
+
+
+def d_masks(ctx):
+    """LeakyReLU masks of a critic forward pass in the oracle's call order (new block, trunk blocks, last conv)."""
+    out = []
+    for st in ctx.stages:
+        if st.kind == 'block':
+            out += [mask_of(st.y1), mask_of(st.y2)]
+    return out + [mask_of(ctx.yl)]
+
+
+def g_masks(ctx):
+    out = [mask_of(ctx.y0), mask_of(ctx.yc)]
+    for rec in ctx.recs + ([ctx.new] if ctx.new is not None else []):
+        out += [mask_of(rec.y1), mask_of(rec.y2)]
+    return out
+
+
+def report(tag, got, ref, names, tol):
+    rep = {k: rel(got[k].cpu(), ref[k]) for k in names if ref[k] is not None}
     vals = sorted(rep.values())
-    worst = max(rep, key=rep.get)
-    print(f'{tag}: rel-L2 per parameter median {vals[len(vals) // 2]:.4f} max {vals[-1]:.4f} ({worst})')
-    assert vals[-1] <= TOL, rep
+    print(f'{tag}: rel-L2 per parameter median {vals[len(vals) // 2]:.4f} max {vals[-1]:.4f} '
+          f'({max(rep, key=rep.get)})')
+    print('   ', {k: round(v, 4) for k, v in rep.items()})
+    assert vals[-1] <= tol, rep
 
 
-CASES = [(64, 0.5, 4), (256, 1.0, 2), (512, 0.5, 1), (512, 1.0, 2)]
+CASES = [(64, 0.5, 4), (256, 1.0, 2), (512, 0.5, 2), (512, 1.0, 2)]
 
 
 @pytest.mark.parametrize('res,alpha,batch', CASES)
@@ -64,16 +87,18 @@ def test_critic_backward(res, alpha, batch):
     names = O.active_d_names(n, alpha, ARCH)
     x = O.synthetic_images(batch, res, seed=21)
     gout = torch.tensor([1.0 - 0.2 * (i % 3) for i in range(batch)])
-    with O.emulate_bf16():
-        scores = O.d_forward(dp, x, n, alpha, ARCH)
-        ref = dict(zip(names, torch.autograd.grad((scores[:, 0] * gout).sum(), [dp[k] for k in names])))
     with torch.no_grad():
         s, ctx = engine.d_forward(D, x.to(DEV)[:, 0], save=True)
         sink = autograd_fns._zeros_sink(D.active_parameters())
         engine.d_backward(D, ctx, gout.to(DEV), sink)
         engine.side_join()
-    assert torch.allclose(s.cpu(), scores[:, 0].detach(), rtol=0, atol=2e-3)
-    report_and_check(f'critic backward r{res} a{alpha}', grads_of(D, km, sink), ref, names)
+    got = grads_of(D, km, sink)
+    for tag, masks, tol in (('frozen masks', d_masks(ctx), TOL), ('free masks', None, TOL_FREE)):
+        with O.emulate_bf16(), (O.forced_masks(masks) if masks is not None else O.emulate_bf16()):
+            scores = O.d_forward(dp, x, n, alpha, ARCH)
+            ref = dict(zip(names, torch.autograd.grad((scores[:, 0] * gout).sum(), [dp[k] for k in names])))
+        assert torch.allclose(s.cpu(), scores[:, 0].detach(), rtol=0, atol=2e-3)
+        report(f'critic backward r{res} a{alpha} [{tag}]', got, ref, names, tol)
 
 
 @pytest.mark.parametrize('res,alpha,batch', CASES)
@@ -88,43 +113,46 @@ def test_generator_backward(res, alpha, batch):
     gen = torch.Generator().manual_seed(5)
     z = O.sample_latent((batch, 512), gen)
     g_img = torch.randn(batch, res, res, generator=gen)
-    with O.emulate_bf16():
-        img = O.g_forward(gp, z, n, alpha, ARCH)
-        ref = dict(zip(names, torch.autograd.grad((img[:, 0] * g_img).sum(), [gp[k] for k in names])))
     with torch.no_grad():
         out, ctx = engine.g_forward(G, z.to(DEV), save=True)
         sink = autograd_fns._zeros_sink(G.active_parameters())
         engine.g_backward(G, ctx, g_img.to(DEV), sink)
         engine.side_join()
-    assert rel(out.cpu(), img[:, 0].detach()) < 2e-2
-    report_and_check(f'generator backward r{res} a{alpha}', grads_of(G, km, sink), ref, names)
+    got = grads_of(G, km, sink)
+    for tag, masks, tol in (('frozen masks', g_masks(ctx), TOL), ('free masks', None, TOL_FREE)):
+        with O.emulate_bf16(), (O.forced_masks(masks) if masks is not None else O.emulate_bf16()):
+            img = O.g_forward(gp, z, n, alpha, ARCH)
+            ref = dict(zip(names, torch.autograd.grad((img[:, 0] * g_img).sum(), [gp[k] for k in names])))
+        assert rel(out.cpu(), img[:, 0].detach()) < 2e-2
+        report(f'generator backward r{res} a{alpha} [{tag}]', got, ref, names, tol)
 
 
 @pytest.mark.parametrize('res,alpha,batch', CASES)
 def test_gradient_penalty_double_backward(res, alpha, batch):
     """The gradient penalty (loss_functions.py:173-176) on a fixed batch: penalty value and every critic parameter
-    gradient of it -- forward, first-order backward, both sweeps of the hand-written double backward.  All samples
-    have ||grad|| << 1 at initialisation, so the per-sample terms have one sign and nothing cancels."""
-    from neuron_gan_b200 import autograd_fns
+    gradient of it -- forward, first-order backward, both sweeps of the hand-written double backward."""
+    from neuron_gan_b200 import engine
     _, D = nets(res, alpha)
     n = O.n_layers_for(res, ARCH)
     km = O.d_key_map(n, alpha < 1, ARCH)
     dp = named(D, km)
     names = O.active_d_names(n, alpha, ARCH)          # (head.b gets no penalty gradient: autograd returns None)
     x_hat = O.synthetic_images(batch, res, seed=23)
-    with O.emulate_bf16():
-        xh = x_hat.clone().requires_grad_()
-        out = O.d_forward(dp, xh, n, alpha, ARCH)
-        g, = torch.autograd.grad(out.sum(), xh, create_graph=True)
-        pen = 10.0 * torch.mean((g.norm(2, dim=(1, 2, 3)) - 1) ** 2)
-        ref = dict(zip(names, torch.autograd.grad(pen, [dp[k] for k in names], allow_unused=True)))
-    D.zero_grad()
-    pen_f = autograd_fns.gradient_penalty(D, x_hat.to(DEV), 10.0)
-    pen_f.backward()
-    assert abs(pen_f.item() - pen.item()) <= 2e-3 * abs(pen.item()), (pen_f.item(), pen.item())
-    params = dict(D.named_parameters())
-    got = {k: params[km[k]].grad for k in names}
-    report_and_check(f'gradient penalty r{res} a{alpha}', got, ref, [k for k in names if ref[k] is not None])
+    from neuron_gan_b200 import autograd_fns
+    with torch.no_grad():
+        sink = autograd_fns._zeros_sink(D.active_parameters())
+        pen_f, _, (_, ctx) = engine.d_grad_penalty(D, x_hat.to(DEV)[:, 0], 10.0, sink)
+        engine.side_join()
+    got = grads_of(D, km, sink)
+    for tag, masks, tol in (('frozen masks', d_masks(ctx), TOL), ('free masks', None, TOL_FREE)):
+        with O.emulate_bf16(), (O.forced_masks(masks) if masks is not None else O.emulate_bf16()):
+            xh = x_hat.clone().requires_grad_()
+            out = O.d_forward(dp, xh, n, alpha, ARCH)
+            g, = torch.autograd.grad(out.sum(), xh, create_graph=True)
+            pen = 10.0 * torch.mean((g.norm(2, dim=(1, 2, 3)) - 1) ** 2)
+            ref = dict(zip(names, torch.autograd.grad(pen, [dp[k] for k in names], allow_unused=True)))
+        assert abs(pen_f.item() - pen.item()) <= 2e-3 * abs(pen.item()), (pen_f.item(), pen.item())
+        report(f'gradient penalty r{res} a{alpha} [{tag}]', got, ref, names, tol)
 
 
 def test_default_epsilon_is_the_device_draw_of_the_reference():
@@ -132,7 +160,6 @@ def test_default_epsilon_is_the_device_draw_of_the_reference():
     draw and the generator pass, exactly like loss_functions.py:166-170: under a fixed CUDA seed it reproduces the
     result of injecting that draw."""
     from neuron_gan_b200.loss_functions import D_grad_pen_loss
-    from neuron_gan_b200.utils import sample_latent_vec
     G, D = nets(32, 1.0)
     x = O.synthetic_images(4, 32, seed=9).to(DEV)
     gp_f = D_grad_pen_loss(G, D, Lambda=10)

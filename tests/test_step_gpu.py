@@ -87,8 +87,10 @@ def test_train_step_losses_match_reference(golden, key):
             seen.add(name)
             ratio = p.grad.double().norm().item() / max(refg[name]['norm'], 1e-30)
             worst = max(worst, abs(ratio - 1))
-            lo, hi = (0.4, 2.5) if res <= 128 else (0.1, 10.0)    # conditioning-limited at depth, see the
-            assert lo < ratio < hi, (name, ratio)                 # emulating-oracle test for the tight check
+            # free-running comparison against the fp32 reference: conditioning-limited at depth (mask flips of a
+            # random-sign sum); the tight, frozen-mask check of every gradient is tests/test_backward_gpu.py
+            lo, hi = (0.4, 2.5) if res <= 128 else (0.1, 10.0)
+            assert lo < ratio < hi, (name, ratio)
         assert seen == set(refg.keys())
     print(f'{key}: worst grad-norm deviation {worst:.3%}; stats {stats}')
     # after the two Adam steps the parameters moved like the reference's
@@ -235,6 +237,8 @@ def test_gradients_match_bf16_emulating_oracle(res, alpha, batch):
     vals = sorted(report.values())
     print(f'res={res} alpha={alpha}: grad rel-L2 median {vals[len(vals) // 2]:.4f} max {vals[-1]:.4f} '
           f'({max(report, key=report.get)})')
+    # (Free-running masks: the tight per-parameter check, <= 3 % at 512x512 with the CUDA path's own LeakyReLU masks
+    # imposed on the oracle, is tests/test_backward_gpu.py.)
     # Agreement is limited by the conditioning of the loss gradients at random init, not by the kernels: the
     # critic gradient is a difference of nearly equal real/fake sums, so two equally valid bf16 evaluations
     # (this one and the emulating oracle) differ by rounding noise amplified ~2x per resolution level
