@@ -62,11 +62,12 @@ int ngan_conv_weight_is_folded(int cin, int cout);
 int ngan_conv3x3_fwd(const void* x_c8, const void* w_fwd, const float* bias, float scale, float leak, void* y_c8,
                      float* r, int B, int cin, int cout, int H, int W, void* stream);
 /* The generator's last conv with ToImage fused (models.py:141-149, 344-353): additionally img[b,y,x] =
- * tanh(sum_c toim_w[c] * y[b,c,y,x]) (fp32 [B][H][W]).  y_c8 and r may be NULL when only the image is wanted (the
- * detached generator passes of the critic step).  Folded layers only (ngan_conv_weight_is_folded). */
+ * tanh(sum_c toim_w[c] * y[b,c,y,x]) ([B][H][W]; fp32, or bf16 when img_bf16 != 0 -- generator-only inference,
+ * utils.py:346-355).  y_c8 and r may be NULL when only the image is wanted (the detached generator passes of the
+ * critic step, eval.py).  Folded layers only (ngan_conv_weight_is_folded). */
 int ngan_conv3x3_fwd_toim(const void* x_c8, const void* w_fwd, const float* bias, float scale, float leak, void* y_c8,
-                          float* r, const float* toim_w, float* img, int B, int cin, int cout, int H, int W,
-                          void* stream);
+                          float* r, const float* toim_w, void* img, int img_bf16, int B, int cin, int cout, int H,
+                          int W, void* stream);
 /* gx = scale * convT(ga, W): autograd's convolution_backward (input gradient) of models.py:204.  cin/cout are the
  * LAYER's channel counts: ga has cout channels, gx has cin. */
 int ngan_conv3x3_dgrad(const void* ga_c8, const void* w_dgrad, float scale, void* gx_c8, int B, int cin, int cout,
@@ -144,6 +145,8 @@ int ngan_fromim_dbl(const float* ghat_xp, float in_scale, const void* g_c8, int 
                     void* ghat_out_c8, float* what, int grad_accumulate, float* workspace, int B, int C, int H, int W,
                     void* stream);
 int ngan_toim_fwd(const void* y_c8, const float* w, float* img, int B, int C, int H, int W, void* stream);
+/* fp32 -> bf16 (image output of the inference path when ToImage was not fused into the last conv) */
+int ngan_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 int ngan_toim_bwd(const float* g_img, float gscale, const float* dyn, const float* img, const void* y_c8, const float* r,
                   const float* w, void* ga_c8, float* gpre, float* gw, int grad_accumulate, float* workspace, float leak,
                   int B, int C, int H, int W, void* stream);
@@ -179,6 +182,14 @@ int ngan_gloss(const float* s_fake, float* out1, float* g_fake, float gscale, in
 long long ngan_gp_loss_workspace_bytes(int B);
 int ngan_gp_loss(const float* g, float norm_scale, float lambda, float* pen, float* coeff, float gscale,
                  float* workspace, int B, long long per_sample, void* stream);
+
+/* similarity_loss (loss_functions.py:185-205, called at train.py:379-381): out[0] = lambda / (B*(B-1)) *
+ * sum_ij (cos(z_i, z_j) - cos(x_i, x_j))^2 for images x [B][per_image] and latents z [B][latent], both fp32.  Two
+ * launches (per-chunk partial Gram matrices, then an ordered reduction): deterministic.  With data parallelism the
+ * caller all-gathers the rows of both tensors first (the Gram couples samples across ranks). */
+long long ngan_similarity_loss_workspace_bytes(int B, long long per_image);
+int ngan_similarity_loss(const float* images, const float* z, float lambda, float* workspace, float* out, int B,
+                         long long per_image, int latent, void* stream);
 
 /* stats[5] = {D_loss + pen, score_real, score_fake, G_loss, pen}: train.py:362 and the six .item() reads of
  * train.py:389-394 as one packed device tensor */

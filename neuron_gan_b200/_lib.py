@@ -66,10 +66,10 @@ def load():
 
 _QUERIES = {'ngan_linear_fwd_workspace_bytes', 'ngan_augment_workspace_bytes', 'ngan_conv_weight_is_folded', 'ngan_version',
             'ngan_conv3x3_wgrad_workspace_bytes', 'ngan_pixel_reduction_workspace_bytes',
-            'ngan_gp_loss_workspace_bytes'}   # no launch, value returned
+            'ngan_gp_loss_workspace_bytes', 'ngan_similarity_loss_workspace_bytes'}   # no launch, value returned
 # kernels launched per C-ABI call (everything not listed launches exactly one; callers pass `launches=` where the
 # count depends on the arguments, e.g. one reduction per requested parameter gradient)
-_LAUNCHES = {'ngan_gp_loss': 2, 'ngan_augment_batch': 3, 'ngan_conv3x3_wgrad': 2, 'ngan_bias_grad': 2,
+_LAUNCHES = {'ngan_gp_loss': 2, 'ngan_similarity_loss': 2, 'ngan_augment_batch': 3, 'ngan_conv3x3_wgrad': 2, 'ngan_bias_grad': 2,
              'ngan_memset': 0}
 launch_count = 0          # running count of kernels launched through this binding (bench.py reads it)
 _profile = None           # when a list: (name, int args, start event, end event) per call

@@ -82,10 +82,11 @@ int ngan_conv3x3_fwd(const void* x, const void* w_fwd, const float* bias, float 
                             nullptr, nullptr, nullptr, S(stream));
 }
 int ngan_conv3x3_fwd_toim(const void* x, const void* w_fwd, const float* bias, float scale, float leak, void* y, float* r,
-                          const float* toim_w, float* img, int B, int cin, int cout, int H, int W, void* stream) {
+                          const float* toim_w, void* img, int img_bf16, int B, int cin, int cout, int H, int W,
+                          void* stream) {
     NGAN_REQUIRE(x && w_fwd && toim_w && img && B > 0, "conv3x3_fwd_toim: null pointer or empty batch");
     return conv3x3_dispatch(EPI_FWD_PN, x, w_fwd, B, cin, cout, H, W, scale, leak, bias, y, nullptr, r, nullptr,
-                            nullptr, nullptr, nullptr, S(stream), toim_w, img);
+                            nullptr, nullptr, nullptr, S(stream), toim_w, static_cast<float*>(img), img_bf16);
 }
 int ngan_conv3x3_dgrad(const void* ga, const void* w_dgrad, float scale, void* gx, int B, int cin, int cout, int H,
                        int W, void* stream) {
@@ -223,6 +224,11 @@ int ngan_toim_fwd(const void* y, const float* w, float* img, int B, int C, int H
     NGAN_REQUIRE(y && w && img && !bad_c(C) && B > 0, "toim_fwd: bad arguments");
     return toim_fwd(y, w, img, B, C, H, W, S(stream));
 }
+int ngan_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+    NGAN_REQUIRE(src && dst && n >= 0, "f32_to_bf16: bad arguments");
+    if (n == 0) return NGAN_OK;
+    return f32_to_bf16(src, dst, static_cast<size_t>(n), S(stream));
+}
 int ngan_toim_bwd(const float* g_img, float gscale, const float* dyn, const float* img, const void* y, const float* r, const float* w,
                   void* ga, float* gpre, float* gw, int grad_accumulate, float* workspace, float leak, int B, int C,
                   int H, int W, void* stream) {
@@ -272,6 +278,14 @@ int ngan_wloss(const float* s_real, const float* s_fake, float drift, float* out
 int ngan_gloss(const float* s_fake, float* out1, float* g_fake, float gscale, int B, void* stream) {
     NGAN_REQUIRE(s_fake && out1 && B > 0, "gloss: bad arguments");
     return gloss_fwd(s_fake, out1, g_fake, gscale, B, S(stream));
+}
+long long ngan_similarity_loss_workspace_bytes(int B, long long per_image) {
+    return static_cast<long long>(similarity_workspace_bytes(B, per_image));
+}
+int ngan_similarity_loss(const float* images, const float* z, float lambda, float* workspace, float* out, int B,
+                         long long per_image, int latent, void* stream) {
+    NGAN_REQUIRE(images && z && workspace && out && B > 1 && per_image > 0 && latent > 0, "similarity_loss: bad arguments");
+    return similarity_loss(images, z, lambda, workspace, out, B, per_image, latent, S(stream));
 }
 int ngan_pack_stats(const float* out3, const float* out1, const float* pen, float* stats, void* stream) {
     NGAN_REQUIRE(out3 && out1 && pen && stats, "pack_stats: null pointer");

@@ -116,7 +116,9 @@ __device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool vali
                 float dot = 0.f;
 #pragma unroll
                 for (int c = 0; c < COUT; ++c) dot = fmaf(__ldg(a.toim_w + c), o[c], dot);
-                a.img_out[p0] = tanhf(k * dot);
+                const float im = tanhf(k * dot);
+                if (a.img_bf16) reinterpret_cast<__nv_bfloat16*>(a.img_out)[p0] = __float2bfloat16(im);
+                else a.img_out[p0] = im;
             }
             if (a.out0) {
                 uint4* out = reinterpret_cast<uint4*>(a.out0) + q0;

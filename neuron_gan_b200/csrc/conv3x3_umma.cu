@@ -451,7 +451,7 @@ static int launch_conv(const CUtensorMap& tmap, const ConvArgs& a, const TilePla
 int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, int cout, int H, int W, float scale,
                      float leak, const float* bias, void* out0, void* out1, float* rout, const void* y,
                      const float* r, const void* gy, const void* addin, cudaStream_t st, const float* toim_w,
-                     float* img_out) {
+                     float* img_out, int img_bf16) {
     ConvArgs a;
     a.B = B; a.H = H; a.W = W;
     a.scale = scale; a.leak = leak;
@@ -464,6 +464,7 @@ int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, 
     a.rout = rout;
     a.toim_w = toim_w;
     a.img_out = img_out;
+    a.img_bf16 = img_bf16;
     a.y = static_cast<const __nv_bfloat16*>(y);
     a.r = r;
     a.gy = static_cast<const __nv_bfloat16*>(gy);

@@ -28,6 +28,7 @@ struct ConvArgs {
     float* rout;
     const float* toim_w;         // FWD (folded kernel): fused ToImage, img = tanh(sum_c toim_w[c] * y[c]) ...
     float* img_out;              // ... written here ([B][H][W] fp32); out0 may then be null (y not stored)
+    int img_bf16;                // img_out holds bf16 instead of fp32 (generator-only inference, BASELINE config 5)
     const __nv_bfloat16* y;
     const float* r;
     const __nv_bfloat16* gy;

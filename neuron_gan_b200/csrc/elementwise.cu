@@ -807,6 +807,14 @@ __global__ void toim_fwd_kernel(const uint4* __restrict__ y, const float* __rest
     }
     img[i] = tanhf(acc);
 }
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16(src[i]);
+}
+int f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t st) {
+    f32_to_bf16_kernel<<<nblocks(n, 256), 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+    return check_launch("f32_to_bf16");
+}
 int toim_fwd(const void* y, const float* w, float* img, int B, int C, int H, int W, cudaStream_t st) {
     const size_t HW = static_cast<size_t>(H) * W, total = B * HW;
     toim_fwd_kernel<<<nblocks(total, 256), 256, 0, st>>>(static_cast<const uint4*>(y), w, img, C, HW, total);
@@ -1174,6 +1182,85 @@ int gp_loss(const float* g, float norm_scale, float lambda, float* pen_out, floa
     gp_sumsq_kernel<<<dim3(bx, B), 256, 0, st>>>(g, workspace, per_sample);
     gp_finish_kernel<<<1, 256, 0, st>>>(workspace, bx, coeff_out, norm_scale, lambda, pen_out, gscale, B);
     return check_launch("gp_loss");
+}
+
+// ------------------------------------------------------------------------------- similarity_loss (loss_functions.py:185-205)
+// Lambda / (B*(B-1)) * sum_ij (cos(z_i, z_j) - cos(x_i, x_j))^2 over a batch of images x [B][P] and latents z [B][L].
+// Stage 1: every block takes one chunk of pixels of ALL images into shared memory and writes its partial B x B Gram
+// matrix of the images as one row of the workspace (no atomics).  Stage 2 (one block): adds the rows in order, forms
+// the latent Gram directly, normalises both with their diagonals and reduces the squared difference.
+constexpr int kSimChunk = 512;      // pixels per block and image
+__global__ void __launch_bounds__(256) sim_gram_kernel(const float* __restrict__ x, int B, long long P,
+                                                       float* __restrict__ partial /* [gridDim.x][B*B] */) {
+    extern __shared__ float tile[];                   // [B][kSimChunk + 1]
+    const long long p0 = static_cast<long long>(blockIdx.x) * kSimChunk;
+    const int n = static_cast<int>(P - p0 < kSimChunk ? P - p0 : kSimChunk);
+    for (int i = threadIdx.x; i < B * kSimChunk; i += blockDim.x) {
+        const int b = i / kSimChunk, k = i - b * kSimChunk;
+        tile[b * (kSimChunk + 1) + k] = k < n ? __ldg(x + static_cast<long long>(b) * P + p0 + k) : 0.f;
+    }
+    __syncthreads();
+    for (int pr = threadIdx.x; pr < B * B; pr += blockDim.x) {
+        const int i = pr / B, j = pr - i * B;
+        float acc = 0.f;
+        if (j >= i) {                                 // symmetric: the lower triangle is mirrored by stage 2
+            const float* a = tile + i * (kSimChunk + 1);
+            const float* c = tile + j * (kSimChunk + 1);
+#pragma unroll 8
+            for (int k = 0; k < kSimChunk; ++k) acc = fmaf(a[k], c[k], acc);
+        }
+        partial[static_cast<size_t>(blockIdx.x) * B * B + pr] = acc;
+    }
+}
+__global__ void __launch_bounds__(256) sim_finish_kernel(const float* __restrict__ partial, int n_chunks,
+                                                         const float* __restrict__ z, int B, int L, float lambda,
+                                                         float* __restrict__ gram /* scratch [2][B*B] */,
+                                                         float* __restrict__ out) {
+    __shared__ float red[32];
+    for (int pr = threadIdx.x; pr < B * B; pr += blockDim.x) {
+        const int i = pr / B, j = pr - i * B;
+        const int lo = i < j ? i : j, hi = i < j ? j : i;
+        float gx = 0.f;
+        for (int c = 0; c < n_chunks; ++c) gx += partial[static_cast<size_t>(c) * B * B + lo * B + hi];
+        float gz = 0.f;
+        for (int k = 0; k < L; ++k) gz = fmaf(__ldg(z + lo * L + k), __ldg(z + hi * L + k), gz);
+        gram[pr] = gx;
+        gram[B * B + pr] = gz;
+    }
+    __syncthreads();
+    float acc = 0.f;
+    for (int pr = threadIdx.x; pr < B * B; pr += blockDim.x) {
+        const int i = pr / B, j = pr - i * B;
+        const float cx = gram[pr] / (sqrtf(gram[i * B + i]) * sqrtf(gram[j * B + j]));
+        const float cz = gram[B * B + pr] / (sqrtf(gram[B * B + i * B + i]) * sqrtf(gram[B * B + j * B + j]));
+        acc += (cz - cx) * (cz - cx);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[0] = lambda * acc / (static_cast<float>(B) * (B - 1));
+}
+size_t similarity_workspace_bytes(int B, long long P) {
+    const long long n_chunks = (P + kSimChunk - 1) / kSimChunk;
+    return static_cast<size_t>(n_chunks + 2) * B * B * sizeof(float);
+}
+int similarity_loss(const float* x, const float* z, float lambda, float* workspace, float* out, int B, long long P,
+                    int L, cudaStream_t st) {
+    const int n_chunks = static_cast<int>((P + kSimChunk - 1) / kSimChunk);
+    const size_t smem = static_cast<size_t>(B) * (kSimChunk + 1) * sizeof(float);
+    if (smem > 200u * 1024) {
+        set_error("similarity_loss: batch %d too large for one shared-memory tile (max %d)", B,
+                  static_cast<int>(200u * 1024 / ((kSimChunk + 1) * sizeof(float))));
+        return NGAN_ERR_UNSUPPORTED;
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(sim_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(sim_gram)");
+        configured = true;
+    }
+    sim_gram_kernel<<<n_chunks, 256, smem, st>>>(x, B, P, workspace);
+    float* gram = workspace + static_cast<size_t>(n_chunks) * B * B;
+    sim_finish_kernel<<<1, 256, 0, st>>>(workspace, n_chunks, z, B, L, lambda, gram, out);
+    return check_launch("similarity_loss");
 }
 
 }  // namespace ngan

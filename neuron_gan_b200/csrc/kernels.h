@@ -11,7 +11,7 @@ enum ConvEpilogue { EPI_FWD_PN = 0, EPI_LINEAR = 1, EPI_BWD_PN = 2, EPI_DBL = 3 
 int conv3x3_dispatch(int epi, const void* x, const void* wprep, int B, int cin, int cout, int H, int W, float scale,
                      float leak, const float* bias, void* out0, void* out1, float* rout, const void* y,
                      const float* r, const void* gy, const void* addin, cudaStream_t st, const float* toim_w = nullptr,
-                     float* img_out = nullptr);
+                     float* img_out = nullptr, int img_bf16 = 0);
 int prep_conv_weight(const float* w, void* fwd, void* dgrad, int cin, int cout, cudaStream_t st);
 
 // wgrad.cu
@@ -52,6 +52,7 @@ int fromim_dbl(const float* ghat_xp, float in_scale, const void* g, int unpool, 
                void* ghat_out, float* what, int grad_accumulate, float* workspace, int B, int C, int H, int W,
                cudaStream_t st);
 int toim_fwd(const void* y, const float* w, float* img, int B, int C, int H, int W, cudaStream_t st);
+int f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t st);
 int toim_bwd(const float* g_img, float gscale, const float* dyn, const float* img, const void* y, const float* r, const float* w,
              void* ga, float* gpre, float* gw, int grad_accumulate, float* workspace, float leak, int B, int C, int H,
              int W, cudaStream_t st);
@@ -68,6 +69,9 @@ int wloss_fwd(const float* s_real, const float* s_fake, float drift, float* out3
 int gloss_fwd(const float* s_fake, float* out1, float* g_fake, float gscale, int B, cudaStream_t st);
 int gp_loss(const float* g, float norm_scale, float lambda, float* pen_out, float* coeff_out, float gscale,
             float* workspace, int B, size_t per_sample, cudaStream_t st);
+size_t similarity_workspace_bytes(int B, long long P);
+int similarity_loss(const float* x, const float* z, float lambda, float* workspace, float* out, int B, long long P,
+                    int L, cudaStream_t st);
 int pack_stats(const float* out3, const float* out1, const float* pen, float* stats, cudaStream_t st);
 int scale_rows_f32(const float* x, const float* coeff, float scale, float* out, int B, size_t per_sample,
                    cudaStream_t st);

@@ -49,7 +49,7 @@ def _cache_set(w, ent):
 
 
 def _wkey(w):
-    return (w._version, getattr(w, '_ngan_epoch', 0), w.data_ptr())
+    return (w._version, getattr(w, '_ngan_epoch', 0), getattr(w, '_ngan_ext', 0), w.data_ptr())
 
 
 def conv_images(conv):
@@ -98,6 +98,18 @@ def linear_shadow(lin, allocate_only=False):
         ops.prep_linear_weight(w.detach(), C, S, ent['shadow'])
         ent['key'] = key
     return ent['shadow']
+
+
+def invalidate(net_or_params):
+    """Declare the fp32 master weights of a network (or an iterable of parameters) changed from outside the fused
+    optimiser.  The bf16 operand images (conv_images / linear_shadow) and TrainStep's decision to replay a captured
+    graph key on `p._version`, which in-place writes through `p.data` (EMA weight swaps, weight clipping,
+    re-initialisation after a first forward: `p.data.copy_()`, `p.data.clamp_()` ...) do NOT bump -- such writes must
+    be followed by engine.invalidate(net), otherwise the kernels keep computing with the old images.  Writes through
+    the parameter itself under no_grad (`p.copy_()`, load_state_dict, optimizer.step) need nothing."""
+    params = net_or_params.parameters() if hasattr(net_or_params, 'parameters') else net_or_params
+    for p in params:
+        p._ngan_ext = getattr(p, '_ngan_ext', 0) + 1      # (not _ngan_epoch: that one counts the fused optimiser's steps)
 
 
 def mark_updated(param, shadow_is_fresh=False):
@@ -236,10 +248,17 @@ def _times(scale, term):
 
 def g_forward(net, z, save, img_out=None):
     """Generator_PG.forward (reference models.py:344-353). z: [B, latent] fp32 -> (img [B, R, R] fp32, ctx).
-    img_out: optional preallocated [B, R, R] fp32 tensor that receives the image."""
+    img_out: optional preallocated [B, R, R] tensor that receives the image: fp32, or bf16 (generator-only
+    inference, BASELINE config 5: written straight from the fused ToImage epilogue when the last conv has one)."""
     leak = net.LeakyReLU_neg_slope
     alpha = net.alpha_value()
     lin, conv0 = net.layers[0], net.layers[4]
+    bf16_out = None
+    if img_out is not None and img_out.dtype == torch.bfloat16:
+        last_conv = net.trunk_blocks()[-1].conv2 if net.trunk_blocks() else conv0
+        fused = FUSE_TOIMAGE and ops.conv_weight_is_folded(last_conv.in_channels, last_conv.out_channels)
+        if save or alpha < 1 or not fused:        # the image passes through fp32 kernels first: convert at the end
+            bf16_out, img_out = img_out, None
     S, C0 = net.image_size_init, net.N_features_per_layer[0]
     lin._ngan_dims = (lin.in_features, C0, S)
     z = z.detach().to(F32).contiguous()
@@ -267,6 +286,8 @@ def g_forward(net, z, save, img_out=None):
     if not fade:
         if save:
             ctx.img = img_trunk
+        if bf16_out is not None:
+            return ops.f32_to_bf16(img_trunk, bf16_out), ctx
         return img_trunk, ctx
     # fade-in: im_start = up(ToIm_old(x)), im_end = ToIm_new(block_new(x))      (models.py:347-350)
     new = _g_block_fwd(net.conv_block_list[0], y, leak, save, toim=net.ToIm_list[0], need_y=False)
@@ -274,6 +295,8 @@ def g_forward(net, z, save, img_out=None):
     img = ops.lerp(ops.up2_image(img_trunk), new.img, a_dev, out=img_out)
     if save:
         ctx.new, ctx.img_old, ctx.img_end, ctx.toim_new = new, img_trunk, new.img, net.ToIm_list[0]
+    if bf16_out is not None:
+        return ops.f32_to_bf16(img, bf16_out), ctx
     return img, ctx
 
 

@@ -43,7 +43,7 @@ class TrainConfig:
     """The options of configs/config.py that the PGGAN loop reads, with its defaults."""
     n_critic: int = 1
     adapt_critic: bool = False
-    grad_pen_lambda: float = 10
+    grad_pen_lambda: float = 10.0
     transit_sch: list = field(default_factory=lambda: [25000, 50000, 75000, 100000, 125000])
     alpha_step: float = 0.0001
     learning_rate: float = 0.0001
@@ -203,6 +203,30 @@ def open_checkpoint(cfg, Generator_net, Discriminator_net, weights_dir, resume, 
     return checkpoint, 1
 
 
+SUPPORTED_WIDTHS = (16, 32, 64, 128)
+
+
+def validate_features(gen_features, dis_features, image_size):
+    """The conv kernels are built for the widths 16 / 32 / 64 / 128 with neighbouring levels equal or a factor of two
+    apart (csrc/conv3x3_*.cu dispatch tables; the shipped configuration, configs/config.py:62-63, is inside).  Other
+    reference `N_gen_features` / `N_dis_features` lists would only fail at the first forward pass with
+    NGAN_ERR_UNSUPPORTED, so they are rejected here, before anything is built."""
+    for name, f in (('N_gen_features', gen_features), ('N_dis_features', dis_features)):
+        bad = [c for c in f if c not in SUPPORTED_WIDTHS]
+        if bad:
+            raise SystemExit(f'{name}={list(f)}: widths {bad} are not built (supported: {SUPPORTED_WIDTHS})')
+        for a, b in zip(f[:-1], f[1:]):
+            if b not in (a, 2 * a, a // 2):
+                raise SystemExit(f'{name}={list(f)}: {a} -> {b} is not built (neighbouring levels must be equal or a '
+                                 f'factor of two apart)')
+    if len(gen_features) != len(dis_features):
+        raise SystemExit('N_gen_features and N_dis_features must have the same number of levels (train.py:162-165)')
+    if dis_features[-1] != 128 or gen_features[0] != 128:
+        raise SystemExit('the lowest-resolution level must be 128 wide (generator stem / critic head kernels)')
+    if image_size % 2 ** (len(gen_features) - 1):
+        raise SystemExit(f'image_size {image_size} is not divisible by 2^{len(gen_features) - 1}')
+
+
 def synthetic_images(n, image_size, seed=0):
     """Stand-in canvases (no dataset ships with the repository): smooth random fields in [0, 1], padded like
     NeuronDataset pads (image_size // 4 per side)."""
@@ -224,9 +248,12 @@ def main(argv=None):
         elif isinstance(default, bool):
             ap.add_argument('--' + name, action='store_true')
         else:
-            ap.add_argument('--' + name, type=type(default) if default is not None else int, default=default)
+            # the declared field type, not type(default): `grad_pen_lambda: float = 10` must accept 0.5
+            ftype = f.type if isinstance(f.type, type) else {'int': int, 'float': float, 'str': str}.get(str(f.type), int)
+            ap.add_argument('--' + name, type=ftype, default=default)
     args = ap.parse_args(argv)
     cfg = TrainConfig(**{k: getattr(args, k) for k in TrainConfig.__dataclass_fields__})
+    validate_features(cfg.N_gen_features, cfg.N_dis_features, cfg.image_size)
     rank, world, local = dp.init_from_env()
     device = torch.device('cuda', local)
     torch.cuda.set_device(device)

@@ -94,15 +94,34 @@ class D_grad_pen_loss(nn.Module):
         return Gradient_penalty_loss
 
 
-def similarity_loss(images_batch: torch.Tensor, Z_batch: torch.Tensor, Lambda: float = 1.0):
-    """Optional anti-mode-collapse term (reference loss_functions.py:185-205); default weight 0, off the hot
-    path, kept as plain tensor algebra for API completeness."""
-    batch_size = images_batch.size(0)
-    images_mat = images_batch.view(batch_size, -1)
-    Z_mat = Z_batch.view(batch_size, -1)
-    images_mat = images_mat / images_mat.norm(2, dim=1, keepdim=True)
-    Z_mat = Z_mat / Z_mat.norm(2, dim=1, keepdim=True)
-    Z_cos_sim = torch.matmul(Z_mat, Z_mat.t())
-    images_cos_sim = torch.matmul(images_mat, images_mat.t())
-    N_pairs = batch_size * (batch_size - 1)
-    return Lambda * torch.pow((Z_cos_sim - images_cos_sim), 2).sum() / N_pairs
+def similarity_loss(images_batch: torch.Tensor, Z_batch: torch.Tensor, Lambda: float = 1.0, data_parallel=None):
+    """Optional anti-mode-collapse term (reference loss_functions.py:185-205; train.py:379-381 adds it to the generator
+    loss when sim_loss_lambda > 0): Lambda / (B*(B-1)) * sum_ij (cos(z_i, z_j) - cos(x_i, x_j))^2.
+
+    Runs in two kernels of libngan_b200.so (per-chunk Gram matrices, ordered reduction).  The Gram matrices couple the
+    samples of a batch, so with data parallelism (torch.distributed initialised; `data_parallel` overrides) the rows of
+    both tensors are all-gathered first and every rank returns the loss of the GLOBAL batch -- what a single process
+    would compute.  As train.py calls it -- on the REAL images and a fresh latent draw -- nothing requires grad and the
+    term only shifts the reported generator loss; inputs that do require grad take the differentiable tensor-algebra
+    route below (same arithmetic as the reference, off the training path)."""
+    import torch.distributed as dist
+    if images_batch.requires_grad or Z_batch.requires_grad:
+        batch_size = images_batch.size(0)
+        images_mat = images_batch.view(batch_size, -1)
+        Z_mat = Z_batch.view(batch_size, -1)
+        images_mat = images_mat / images_mat.norm(2, dim=1, keepdim=True)
+        Z_mat = Z_mat / Z_mat.norm(2, dim=1, keepdim=True)
+        diff = torch.matmul(Z_mat, Z_mat.t()) - torch.matmul(images_mat, images_mat.t())
+        return Lambda * torch.pow(diff, 2).sum() / (batch_size * (batch_size - 1))
+    x = images_batch.detach().to(torch.float32).reshape(images_batch.size(0), -1).contiguous()
+    z = Z_batch.detach().to(device=x.device, dtype=torch.float32).reshape(Z_batch.size(0), -1).contiguous()
+    if data_parallel is None:
+        data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if data_parallel:
+        world = dist.get_world_size()
+        xg = torch.empty((world * x.shape[0], x.shape[1]), dtype=x.dtype, device=x.device)
+        zg = torch.empty((world * z.shape[0], z.shape[1]), dtype=z.dtype, device=z.device)
+        dist.all_gather_into_tensor(xg, x)
+        dist.all_gather_into_tensor(zg, z)
+        x, z = xg, zg
+    return ops.similarity_loss(x, z, float(Lambda))[0]

@@ -33,7 +33,17 @@ except Exception:  # noqa: BLE001 - standalone use: configs/config.py:58-61 defa
     N_colors_default = 1
     LeakyReLU_neg_slope_default = 0.2
 
-__all__ = ['Generator_PG', 'Discriminator_PG']
+from .legacy import Discriminator_dcgan, Discriminator_wgan, Generator_dcgan, Generator_wgan  # noqa: E402,F401
+
+# the reference's `from models import *` surface (models.py:10-12)
+__all__ = ['Generator_dcgan', 'Discriminator_dcgan', 'Generator_wgan', 'Discriminator_wgan', 'Generator_PG',
+           'Discriminator_PG']
+
+
+def _default_device():
+    """Where from_state_dict(filename) puts a network when no device is given (eval.py:23): the current CUDA device;
+    the CPU only when there is none (checkpoint surgery still works there, forward passes do not)."""
+    return torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
 
 
 def kaiming_init(model: nn.Module, neg_slope=LeakyReLU_neg_slope_default):
@@ -228,6 +238,12 @@ class _ProgressiveNet(nn.Module):
             self.increase_resolution()
             self.advance_transition(alpha if self.image_size == res else 1.0)
 
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        from . import engine
+        engine.invalidate(self)         # copy_() bumps the versions already; explicit so that .data writes are covered
+        return out
+
     def _check_input(self, x, what):
         if not x.is_cuda:
             raise RuntimeError(f'neuron_gan_b200.{type(self).__name__} runs on CUDA (sm_100a) only; got a {x.device} '
@@ -336,8 +352,11 @@ class Generator_PG(_ProgressiveNet):
         return autograd_fns.generator_forward(self, x)
 
     @classmethod
-    def from_state_dict(cls, filename, device=torch.device('cpu'), verbose=True):
-        """Rebuild a generator from a reference-format .pth (reference models.py:394-444)."""
+    def from_state_dict(cls, filename, device=None, verbose=True):
+        """Rebuild a generator from a reference-format .pth (reference models.py:394-444).  device=None (the way
+        eval.py:23 calls it): the current CUDA device -- the reference defaults to the CPU, where these networks
+        cannot run."""
+        device = _default_device() if device is None else torch.device(device)
         saved = torch.load(filename, map_location=device, weights_only=False)
         attrs = saved['Generator_attrs']
         ctor = {k: v for k, v in attrs.items() if k in ('N_features_per_layer', 'image_size_init',
@@ -355,7 +374,8 @@ class Generator_PG(_ProgressiveNet):
                                                [len(obj.ToIm_list), len(obj.conv_block_list)],
                                                ['ToIm_prev', 'last_conv_block'], from_start=True)
         obj.load_state_dict(state)
-        if verbose:
+        obj.to(device)                  # the reference builds on the CPU and leaves it there (eval.py runs on CPU);
+        if verbose:                     # these networks only run on CUDA, so `device` is where the result lives
             print('Loaded training state from {}'.format(filename))
         return obj
 
@@ -429,8 +449,9 @@ class Discriminator_PG(_ProgressiveNet):
         return autograd_fns.discriminator_forward(self, x)
 
     @classmethod
-    def from_state_dict(cls, filename, device=torch.device('cpu'), verbose=True):
-        """Rebuild a critic from a reference-format .pth (reference models.py:566-616)."""
+    def from_state_dict(cls, filename, device=None, verbose=True):
+        """Rebuild a critic from a reference-format .pth (reference models.py:566-616); device=None: current CUDA device."""
+        device = _default_device() if device is None else torch.device(device)
         saved = torch.load(filename, map_location=device, weights_only=False)
         attrs = saved['Discriminator_attrs']
         ctor = {k: v for k, v in attrs.items() if k in ('N_features_per_layer', 'image_size_init',
@@ -448,6 +469,7 @@ class Discriminator_PG(_ProgressiveNet):
                                                [len(obj.FromIm_list), len(obj.conv_block_list)],
                                                ['FromIm_prev', 'first_conv_block'], from_start=False)
         obj.load_state_dict(state)
+        obj.to(device)
         if verbose:
             print('Loaded training state from {}'.format(filename))
         return obj

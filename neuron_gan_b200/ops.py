@@ -107,10 +107,16 @@ def conv3x3_fwd_toim(x, w_fwd, bias, scale, leak, cout, toim_w, want_y=True, wan
     y = c8_empty(B, cout, H, W, x.device) if want_y else None
     r = torch.empty((B, H, W), dtype=F32, device=x.device) if want_r else None
     img = torch.empty((B, H, W), dtype=F32, device=x.device) if img_out is None else img_out
-    assert img.shape == (B, H, W) and img.dtype == F32
+    assert img.shape == (B, H, W) and img.dtype in (F32, BF16)       # bf16 images: generator-only inference
     _lib.call('ngan_conv3x3_fwd_toim', _p(x, BF16), _p(w_fwd, BF16), _p(bias, F32), scale, leak, _p(y), _p(r),
-              _p(toim_w, F32), _p(img), B, cin, cout, H, W, _stream())
+              _p(toim_w, F32), _p(img), int(img.dtype == BF16), B, cin, cout, H, W, _stream())
     return y, r, img
+
+
+def f32_to_bf16(src, out):
+    assert src.dtype == F32 and out.dtype == BF16 and src.numel() == out.numel()
+    _lib.call('ngan_f32_to_bf16', _p(src, F32), _p(out, BF16), src.numel(), _stream())
+    return out
 
 
 def conv3x3_dgrad(ga, w_dgrad, scale, cin):
@@ -429,6 +435,17 @@ def gp_loss(g, norm_scale, lam, gscale=1.0):
     _lib.call('ngan_gp_loss', _p(g, F32), norm_scale, lam, _p(pen), _p(coeff), gscale, _p(ws, F32), B, g.numel() // B,
               _stream())
     return pen, coeff
+
+
+def similarity_loss(images, z, lam):
+    """images [B, ...] fp32, z [B, L] fp32 -> [1] fp32 (reference loss_functions.py:185-205)"""
+    B = images.shape[0]
+    per = images.numel() // B
+    out = torch.empty(1, dtype=F32, device=images.device)
+    ws = _workspace(_lib.call('ngan_similarity_loss_workspace_bytes', B, per), images.device)
+    _lib.call('ngan_similarity_loss', _p(images, F32), _p(z, F32), float(lam), _p(ws, F32), _p(out), B, per,
+              z.numel() // B, _stream())
+    return out
 
 
 def pack_stats(out3, out1, pen, stats):

@@ -44,6 +44,7 @@ class TrainStep:
         self.n_critic = int(n_critic)   # critic steps per generator step (train.py:356; > 1 runs kernel by kernel)
         self.segment_graphs = False     # capture three graphs even on one GPU (lets a caller time the three parts)
         self.segment_events = None      # when a list: 4 CUDA events per replayed iteration are appended (start, D, G, end)
+        self.global_draws = True        # data parallel: draw the global batch on every rank and keep this rank's rows
         self.fork_chains = True         # run the two independent halves of the critic step on two streams
         self._chain_stream = None
         self._bound = {}
@@ -93,6 +94,12 @@ class TrainStep:
 
     # -- RNG draws in the reference's order: z (D_W_loss) -> z (grad pen) -> eps -> z (G_W_loss) --------------
     def draw_host(self, batch):
+        """This rank's rows of the four draws.  With data parallelism every rank draws the GLOBAL batch on its
+        (identically seeded) CPU generator in the reference's order and keeps rows [rank*b, (rank+1)*b), so any GPU
+        count consumes the single-process random stream bit-exactly (dp.global_draws)."""
+        if self.dp and dist.is_initialized() and self.global_draws:
+            from .dp import global_draws
+            return global_draws(sample_latent_vec, batch * dist.get_world_size(), self.G.latent_dim)
         z1 = sample_latent_vec((batch, self.G.latent_dim))
         z2 = sample_latent_vec((batch, self.G.latent_dim))
         eps = torch.rand((batch, 1, 1, 1))          # CPU generator (SURVEY.md section 8d) for reproducibility
@@ -252,7 +259,8 @@ class TrainStep:
 
     # -- CUDA-graph capture ----------------------------------------------------------------------------------
     def _versions(self):
-        return tuple(p._version for net in (self.G, self.D) for p in net.parameters())
+        # (_ngan_ext: engine.invalidate(), for writes through p.data that do not bump p._version)
+        return tuple((p._version, getattr(p, '_ngan_ext', 0)) for net in (self.G, self.D) for p in net.parameters())
 
     def _config_key(self, B, R):
         # alpha itself is NOT part of the key: the kernels read it from device memory (_sync_alpha), so one graph

@@ -113,14 +113,108 @@ class Checkpointer:
                     attrs['alpha'] = attrs['alpha'].to(dev_g)
             set_saved_attrs(self.Generator_net, gen_attrs)
             set_saved_attrs(self.Discriminator_net, dis_attrs)
-        gen = self.Generator_net.from_state_dict(source, verbose=False)
-        dis = self.Discriminator_net.from_state_dict(source, verbose=False)
+        gen = self.Generator_net.from_state_dict(source, device=torch.device('cpu'), verbose=False)
+        dis = self.Discriminator_net.from_state_dict(source, device=torch.device('cpu'), verbose=False)
         self.Generator_net.load_state_dict(gen.state_dict(), strict=False)
         self.Discriminator_net.load_state_dict(dis.state_dict(), strict=False)
         if self.verbose and filename is None:
             print('Loaded training state from {}'.format(self.filename))
         elif self.verbose:
             print('Loaded weights from {}'.format(filename))
+
+
+def init_weights(m: nn.Module):
+    """DCGAN initialisation (reference utils.py:96-101); train.py:208-209 applies it to the legacy nets only."""
+    if type(m) in [nn.Conv2d, nn.ConvTranspose2d]:
+        m.weight.data.normal_(0.0, 0.02)
+    elif type(m) == nn.BatchNorm2d:
+        m.weight.data.normal_(1.0, 0.02)
+        m.bias.data.fill_(0.0)
+
+
+def ValidatedInput(prompt: str, validate_func, invalid_ans_msg='Invalid answer.'):
+    """Interactive prompt of the reference (utils.py:234-246; train.py:117-125, configs/config.py:138-144)."""
+    if not prompt.endswith('\n'):
+        prompt += '\n'
+    while True:
+        Ans = input(prompt)
+        if validate_func(Ans):
+            break
+        print(invalid_ans_msg)
+    return Ans
+
+
+def N_params(model: nn.Module):
+    return sum(p.numel() for p in model.parameters())
+
+
+def calculate_grad_norm_hist(model: nn.Module, grad_min=-30, log_scale=True):
+    """|grad| of every parameter element that has one, log10-scaled (reference utils.py:249-275)."""
+    parts = [p.grad.detach().abs().flatten() for p in model.parameters() if p.grad is not None and p.requires_grad]
+    vals = torch.cat(parts).cpu().numpy() if parts else np.array([])
+    if log_scale:
+        vals = np.log10(np.maximum(vals, 10.0 ** grad_min))
+    else:
+        vals = np.maximum(vals, grad_min)
+    if vals.size:
+        return vals, float(np.mean(vals)), float(np.std(vals))
+    return vals, float('nan'), float('nan')
+
+
+def _pyplot():
+    try:
+        import matplotlib
+        matplotlib.use('Agg')
+        import matplotlib.pyplot as plt
+        return plt if hasattr(plt, 'subplots') and callable(getattr(plt, 'subplots')) else None
+    except Exception:  # noqa: BLE001 - matplotlib is optional: the plots are observability only (SURVEY.md section 2)
+        return None
+
+
+def plot_grad_norm(generator_model, discriminator_model, filename: str = None):
+    """Histogram of the parameter-gradient magnitudes of both networks (reference utils.py:619-645).  Needs real fp32
+    `.grad` tensors on the parameters, which both the autograd path and TrainStep provide.  Without matplotlib the
+    statistics are still computed (and returned); no figure is written."""
+    g_vals, g_mean, g_std = calculate_grad_norm_hist(generator_model)
+    d_vals, d_mean, d_std = calculate_grad_norm_hist(discriminator_model)
+    plt = _pyplot()
+    if plt is not None and filename is not None:
+        try:
+            fig, (ax1, ax2) = plt.subplots(1, 2, figsize=(8, 5))
+            ax1.hist(g_vals, alpha=0.75)
+            ax1.set_title('Generator, mean={:.2}, std={:.2}'.format(g_mean, g_std))
+            ax2.hist(d_vals, alpha=0.75)
+            ax2.set_title('Discriminator, mean={:.2}, std={:.2}'.format(d_mean, d_std))
+            for ax in (ax1, ax2):
+                ax.set_xlabel('Parameter gradient norm (Logged)')
+                ax.set_ylabel('Counts')
+            fig.tight_layout()
+            fig.savefig(filename)
+            plt.close(fig)
+        except Exception:  # noqa: BLE001 - a stubbed matplotlib draws nothing
+            pass
+    return (g_mean, g_std), (d_mean, d_std)
+
+
+def plot_scores(loss_real, loss_fake, filename, G_loss=None, D_loss=None):
+    """Training summary plot (reference utils.py:649-665); a no-op without matplotlib."""
+    plt = _pyplot()
+    if plt is None:
+        return
+    try:
+        fig = plt.figure()
+        plt.plot(loss_real, label='Real images (<D(x)>_x)')
+        plt.plot(loss_fake, label='Fake images (<D(G(z))>_z)')
+        if G_loss:
+            plt.plot(G_loss, label='Generator')
+        if D_loss:
+            plt.plot(D_loss, label='Discriminator')
+        plt.legend(loc='upper left')
+        plt.xlabel('Epoch')
+        plt.savefig(filename)
+        plt.close(fig)
+    except Exception:  # noqa: BLE001
+        pass
 
 
 def save_vars(variables: dict, directory='./saved_vars', verbose=True):
@@ -155,29 +249,88 @@ def Calculate_D_steps(Loss_real, Loss_fake, N_min, N_max, Period):
 
 
 # ----------------------------------------------------------------------------------------------- testing
-def gen_samples(Generator: nn.Module, N_images=16, seed=None, chunk=256):
-    """Generator-only inference (reference utils.py:346-355), chunked so 4096 samples at 512x512 fit."""
+def gen_samples(Generator: nn.Module, N_images=16, seed=None, chunk=128, dtype=torch.float32):
+    """Generator-only inference (reference utils.py:346-355): returns (images [N, 1, R, R] on the generator's device,
+    z).  Chunked so that 4096 samples at 512x512 fit; every chunk writes straight into its slice of the result (no
+    concatenation, no per-chunk allocation of the result).  dtype: torch.float32 (reference) or torch.bfloat16."""
+    from . import engine
     dev = next(Generator.parameters()).device
+    if dev.type != 'cuda':
+        raise RuntimeError('neuron_gan_b200 generators run on CUDA only: move the network to the GPU first')
     z_latent = sample_latent_vec((N_images, Generator.latent_dim), seed=seed, device=dev)
+    R = Generator.image_size
+    images = torch.empty((N_images, 1, R, R), dtype=dtype, device=dev)
     with torch.no_grad():
-        images = torch.cat([Generator(z_latent[i:i + chunk]) for i in range(0, N_images, chunk)]).detach()
+        for i in range(0, N_images, chunk):
+            engine.g_forward(Generator, z_latent[i:i + chunk], save=False, img_out=images[i:i + chunk, 0])
     return images, z_latent
+
+
+_host_pool = {}
+
+
+def gen_samples_host(Generator: nn.Module, N_images=16, seed=None, dtype=torch.float32, chunk=128, to_host=True):
+    """eval.py's data path end to end: seeded latents -> generator -> images in (pinned) HOST memory, which is where
+    the reference has them before it writes the PNG grid (utils.py:583 `.cpu()`).  Chunks are double-buffered on
+    the device and their device-to-host copies run on a copy stream beside the next chunk's kernels; the pinned
+    result buffer is kept per (N, R, dtype).  Returns the host tensor [N, 1, R, R] (valid until the next call with
+    the same shape), or -- with to_host=False -- the last device chunk (timing without the copy)."""
+    from . import engine
+    dev = next(Generator.parameters()).device
+    R = Generator.image_size
+    z_latent = sample_latent_vec((N_images, Generator.latent_dim), seed=seed, device=dev)
+    key = (N_images, R, dtype, dev)
+    pool = _host_pool.get(key)
+    if pool is None:
+        if len(_host_pool) >= 4:
+            _host_pool.clear()
+        c = min(chunk, N_images)
+        pool = _host_pool[key] = {
+            'host': torch.empty((N_images, 1, R, R), dtype=dtype).pin_memory(),
+            'dev': [torch.empty((c, R, R), dtype=dtype, device=dev) for _ in range(2)],
+            'free': [None, None], 'stream': torch.cuda.Stream(dev)}
+    host, bufs, free, copy_stream = pool['host'], pool['dev'], pool['free'], pool['stream']
+    cur = torch.cuda.current_stream(dev)
+    with torch.no_grad():
+        for k, i in enumerate(range(0, N_images, chunk)):
+            n = min(chunk, N_images - i)
+            buf = bufs[k % 2][:n]
+            if free[k % 2] is not None:
+                cur.wait_event(free[k % 2])              # the copy that last read this buffer has finished
+            engine.g_forward(Generator, z_latent[i:i + n], save=False, img_out=buf)
+            if to_host:
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ready)
+                    host[i:i + n, 0].copy_(buf, non_blocking=True)
+                    free[k % 2] = torch.cuda.Event()
+                    free[k % 2].record(copy_stream)
+    if not to_host:
+        return buf
+    cur.wait_stream(copy_stream)                         # stream-ordered: callers synchronise before reading `host`
+    return host
 
 
 def plot_gen_samples(Generator: nn.Module, eval_noise=None, N_images=16, seed=None, filename=None):
     """Sample grid PNG (reference utils.py:568-610): nearest-upsample to image_size_max, nrow=round(sqrt(N)),
     normalize=True.  Needs `filename` (the reference's matplotlib display path is out of scope)."""
+    if isinstance(eval_noise, int):
+        # eval.py:26 passes `n` positionally, i.e. into this slot (SURVEY.md section 0 row 11: as shipped the reference
+        # then calls Generator(20) and raises); the intended call is plot_gen_samples(G, N_images=n, filename=...)
+        N_images, eval_noise = eval_noise, None
     was_training = Generator.training
     Generator.train(False)
     if eval_noise is None:
-        images, _ = gen_samples(Generator, N_images, seed=seed)
+        images = gen_samples_host(Generator, N_images, seed=seed)
+        torch.cuda.synchronize()
+        images = images.clone()
     else:
         with torch.no_grad():
-            images = Generator(eval_noise).detach()
+            images = Generator(eval_noise).detach().cpu()
         N_images = images.size(0)
     Generator.train(was_training)
     n_rows = int(np.round(np.sqrt(N_images)))
-    images = images.cpu()
     if images.size(-1) != Generator.image_size_max:
         size = (Generator.image_size_max, Generator.image_size_max)
         images = nn.functional.interpolate(images, size=size)
