@@ -215,6 +215,19 @@ typedef struct {
 int ngan_adam_multi(const ngan_adam_tensor* tensors, int n_tensors, float beta1, float beta2, float eps,
                     void* stream);
 
+/* Adam on the generator's Linear weight [C*S*S][K] with the gradient taken from its FACTORS instead of a materialised
+ * tensor (models.py:240-241 backward + train.py:385):  g[f][k] = gscale * sum_b ga[b][f] * z[b][k] over Btot samples,
+ * ga = gradient at the stem's pre-activation (c8, what ngan_linear_wgrad takes), z = the latent batch.  Bit-identical
+ * to ngan_linear_wgrad + ngan_adam_multi, without the 67 MB gradient round trip; with data parallelism the ranks
+ * all-gather the factors (1 MB + 32 KB per rank) instead of all-reducing the product.  Sample b is row b % b_per_seg
+ * of segment b / b_per_seg (segments *_seg_stride BYTES apart: the layout of an all-gathered buffer; one segment:
+ * b_per_seg = Btot).  shadow_img (optional): the operand image of ngan_prep_linear_weight, refreshed in the same pass;
+ * g_out (optional): also write the gradient.  step_size / inv_bc2_sqrt / dyn as in ngan_adam_tensor. */
+int ngan_adam_linear_factored(float* p, float* m, float* v, void* shadow_img, float* g_out, const void* ga_c8,
+                              const float* z, int Btot, int b_per_seg, long long ga_seg_stride, long long z_seg_stride,
+                              int K, int C, int S, float gscale, float step_size, float inv_bc2_sqrt,
+                              const float* dyn, float beta1, float beta2, float eps, void* stream);
+
 /* ---- on-device image pipeline: DatasetIterator.__next__ (data/NeuronDataset.py:170-205) applying the transform
  * list of NeuronDataset.__init__ / set_image_size (data/NeuronDataset.py:112-126, 149-164) to a whole batch:
  * RandomAffine(nearest, fill 0) -> RandomVerticalFlip -> ColorJitter(brightness, contrast) -> CenterCrop(crop) ->

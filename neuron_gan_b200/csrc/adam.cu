@@ -130,6 +130,115 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
 #undef NGAN_ADAM1
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Adam on the generator's Linear weight with the gradient taken from its FACTORS (reference models.py:240-241 backward +
+// train.py:385):  g[f][k] = gscale * sum_b ga[b][f] * z[b][k]  over the Btot samples of the (global) batch, where ga is
+// the gradient at the stem's pre-activation (C8 bf16 [b][C/8][SS][8], f = c*SS + px) and z the latent batch.
+// The 16.8 M-element gradient (98 % of the generator) is a rank-Btot product: it is never written to HBM nor read back
+// (-134 MB per step), and with data parallelism the ranks exchange the factors (1 MB + 32 KB per rank, all-gather)
+// instead of all-reducing the 67 MB product.  One thread owns 8 channels (one C8 granule) x 8 k of one pixel: per
+// sample one broadcast 16-byte load of ga and 32 bytes of z feed 64 FMAs, so the kernel stays bound by the 28 B/element
+// of Adam traffic up to a global batch of ~128.  Samples are added in index order: deterministic, and bit-identical
+// to ngan_linear_wgrad followed by ngan_adam_multi.
+// Samples may live in per-rank segments of an all-gathered buffer: sample b is row (b % b_per_seg) of segment
+// b / b_per_seg, segments ga_seg_stride / z_seg_stride BYTES apart.
+struct AdamLinearArgs {
+    float* p;
+    float* m;
+    float* v;
+    __nv_bfloat16* shadow;     // operand image [SS][K/8][C][8] or null
+    float* g_out;              // optional: materialise the gradient here ([C*SS][K] fp32)
+    const uint4* ga;
+    const float* z;
+    int Btot, b_per_seg;
+    long long ga_seg_stride, z_seg_stride;
+    int K, C, SS;
+    float gscale, step_size, inv_bc2_sqrt;
+    const float* dyn;
+    float beta1, beta2, eps;
+};
+__global__ void __launch_bounds__(256) adam_linear_factored_kernel(const AdamLinearArgs a) {
+    const float step_size = a.dyn ? __ldg(a.dyn) : a.step_size;
+    const float inv_bc2_sqrt = a.dyn ? __ldg(a.dyn + 1) : a.inv_bc2_sqrt;
+    const int KG = a.K >> 3, NCH = a.C >> 3;
+    const long long items = static_cast<long long>(NCH) * a.SS * KG;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long it = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; it < items; it += stride) {
+        const int kg = static_cast<int>(it % KG);
+        const long long rest = it / KG;
+        const int px = static_cast<int>(rest % a.SS), j = static_cast<int>(rest / a.SS);
+        float acc[8][8];                       // [channel of the granule][k]
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[e][q] = 0.f;
+        for (int b = 0; b < a.Btot; ++b) {
+            const int seg = b / a.b_per_seg, row = b - seg * a.b_per_seg;
+            const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(a.ga) + seg * a.ga_seg_stride) +
+                              (static_cast<size_t>(row) * NCH + j) * a.SS + px;
+            const float4* zp = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(a.z) + seg * a.z_seg_stride +
+                                                               static_cast<size_t>(row) * a.K * sizeof(float)) + kg * 2;
+            float gv[8];
+            unpack8(__ldg(gp), gv);
+            const float4 z0 = __ldg(zp), z1 = __ldg(zp + 1);
+            const float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[e][q] += gv[e] * zv[q];
+        }
+        uint4 img[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const long long i = ((static_cast<long long>(j * 8 + e) * a.SS + px) * a.K + kg * 8) >> 2;   // float4 index
+            uint32_t packed[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float4 p = reinterpret_cast<float4*>(a.p)[i + h];
+                float4 m = reinterpret_cast<float4*>(a.m)[i + h];
+                float4 v = reinterpret_cast<float4*>(a.v)[i + h];
+                const float4 g = make_float4(a.gscale * acc[e][4 * h], a.gscale * acc[e][4 * h + 1],
+                                             a.gscale * acc[e][4 * h + 2], a.gscale * acc[e][4 * h + 3]);
+#define NGAN_ADAM1(c)                                                      \
+    m.c = m.c + (1.f - a.beta1) * (g.c - m.c);                             \
+    v.c = a.beta2 * v.c + (1.f - a.beta2) * g.c * g.c;                     \
+    p.c = p.c - step_size * (m.c / (sqrtf(v.c) * inv_bc2_sqrt + a.eps));
+                NGAN_ADAM1(x) NGAN_ADAM1(y) NGAN_ADAM1(z) NGAN_ADAM1(w)
+#undef NGAN_ADAM1
+                reinterpret_cast<float4*>(a.p)[i + h] = p;
+                reinterpret_cast<float4*>(a.m)[i + h] = m;
+                reinterpret_cast<float4*>(a.v)[i + h] = v;
+                if (a.g_out) reinterpret_cast<float4*>(a.g_out)[i + h] = g;
+                packed[2 * h] = pack_bf16(p.x, p.y);
+                packed[2 * h + 1] = pack_bf16(p.z, p.w);
+            }
+            img[e] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        if (a.shadow) {
+            uint4* dst = reinterpret_cast<uint4*>(a.shadow) + (static_cast<long long>(px) * KG + kg) * a.C + j * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dst[e] = img[e];
+        }
+    }
+}
+int adam_linear_factored(float* p, float* m, float* v, void* shadow, float* g_out, const void* ga, const float* z,
+                         int Btot, int b_per_seg, long long ga_seg_stride, long long z_seg_stride, int K, int C, int SS,
+                         float gscale, float step_size, float inv_bc2_sqrt, const float* dyn, float beta1, float beta2,
+                         float eps, cudaStream_t st) {
+    if (K % 8 || C % 8 || Btot <= 0 || b_per_seg <= 0) {
+        set_error("adam_linear_factored: bad shape K=%d C=%d Btot=%d", K, C, Btot);
+        return NGAN_ERR_INVALID;
+    }
+    AdamLinearArgs a{p, m, v, static_cast<__nv_bfloat16*>(shadow), g_out, static_cast<const uint4*>(ga), z, Btot,
+                     b_per_seg, ga_seg_stride, z_seg_stride, K, C, SS, gscale, step_size, inv_bc2_sqrt, dyn, beta1,
+                     beta2, eps};
+    const long long items = static_cast<long long>(C / 8) * SS * (K / 8);
+    long long bx = (items + 255) / 256;
+    if (bx > 148 * 8) bx = 148 * 8;
+    adam_linear_factored_kernel<<<static_cast<unsigned>(bx), 256, 0, st>>>(a);
+    return check_launch("adam_linear_factored");
+}
+
 int adam_multi_launch(const AdamEntry* entries, int n_tensors, float beta1, float beta2, float eps,
                       cudaStream_t st) {
     if (n_tensors <= 0) return NGAN_OK;

@@ -303,6 +303,15 @@ int ngan_adam_multi(const ngan_adam_tensor* tensors, int n_tensors, float beta1,
     return adam_multi_launch(reinterpret_cast<const AdamEntry*>(tensors), n_tensors, beta1, beta2, eps, S(stream));
 }
 
+int ngan_adam_linear_factored(float* p, float* m, float* v, void* shadow_img, float* g_out, const void* ga_c8,
+                              const float* z, int Btot, int b_per_seg, long long ga_seg_stride, long long z_seg_stride,
+                              int K, int C, int Sz, float gscale, float step_size, float inv_bc2_sqrt,
+                              const float* dyn, float beta1, float beta2, float eps, void* stream) {
+    NGAN_REQUIRE(p && m && v && ga_c8 && z, "adam_linear_factored: null pointer");
+    return adam_linear_factored(p, m, v, shadow_img, g_out, ga_c8, z, Btot, b_per_seg, ga_seg_stride, z_seg_stride, K,
+                                C, Sz * Sz, gscale, step_size, inv_bc2_sqrt, dyn, beta1, beta2, eps, S(stream));
+}
+
 /* ---- on-device image pipeline (data/NeuronDataset.py:170-205) ---- */
 long long ngan_augment_workspace_bytes(int batch, int canvas, int crop) {
     return static_cast<long long>(augment_workspace_bytes(batch, canvas, crop));

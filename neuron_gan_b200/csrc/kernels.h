@@ -85,6 +85,10 @@ int linear_wgrad(const void* ga, const float* z, float scale, float* dw, int acc
 
 // adam.cu (AdamEntry has the layout of ngan_adam_tensor in include/ngan_b200.h)
 struct AdamEntry;
+int adam_linear_factored(float* p, float* m, float* v, void* shadow, float* g_out, const void* ga, const float* z,
+                         int Btot, int b_per_seg, long long ga_seg_stride, long long z_seg_stride, int K, int C, int SS,
+                         float gscale, float step_size, float inv_bc2_sqrt, const float* dyn, float beta1, float beta2,
+                         float eps, cudaStream_t st);
 int adam_multi_launch(const AdamEntry* entries, int n_tensors, float beta1, float beta2, float eps, cudaStream_t st);
 
 // augment.cu

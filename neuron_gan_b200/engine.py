@@ -312,9 +312,11 @@ def _g_block_bwd(rec, ga2, y_prev, r_prev, leak, sink, extra_pre=None, extra_w=N
     return ops.up2_bwd_pn_bwd(g_up, y_prev, r_prev, extra_pre, extra_w, leak)
 
 
-def g_backward(net, ctx, g_img, sink, linear_overwrite=False):
+def g_backward(net, ctx, g_img, sink, linear_overwrite=False, linear_factors=None):
     """Gradient of the generator parameters given d loss / d image ([B, R, R] fp32).  linear_overwrite: the Linear
-    weight's gradient (98 % of the parameters) is stored, not accumulated -- its part of the sink need not be zeroed."""
+    weight's gradient (98 % of the parameters) is stored, not accumulated -- its part of the sink need not be zeroed.
+    linear_factors: a SimpleNamespace; when given, the Linear weight's gradient is NOT formed: its two factors (the
+    gradient at the stem's pre-activation `ga0`, and the latents `z`) are left on it for ops.adam_linear_factored."""
     leak = net.LeakyReLU_neg_slope
     alpha = ctx.alpha
     acc = _acc(sink)
@@ -339,6 +341,9 @@ def g_backward(net, ctx, g_img, sink, linear_overwrite=False):
     lin, conv0 = net.layers[0], net.layers[4]
     _wgrad(ctx.y0, ga, conv0.scale_value, _sink_get(sink, conv0.weight), acc)
     ga0, _ = ops.conv3x3_dgrad_pn(ga, conv_images(conv0)[1], conv0.scale_value, leak, ctx.y0, ctx.r0)
+    if linear_factors is not None:
+        linear_factors.ga0, linear_factors.z, linear_factors.scale = ga0, ctx.z, lin.scale_value
+        return
     ops.linear_wgrad(ga0, ctx.z, lin.scale_value, _sink_get(sink, lin.weight), accumulate=acc and not linear_overwrite)
 
 

@@ -475,6 +475,18 @@ def adam_multi(entries, beta1, beta2, eps):
     _lib.call('ngan_adam_multi', ctypes.cast(arr, ctypes.c_void_p), n, beta1, beta2, eps, _stream())
 
 
+def adam_linear_factored(p, m, v, shadow, ga, z, K, C, S, gscale, step_size, inv_bc2_sqrt, dyn, beta1, beta2, eps,
+                         b_per_seg=None, ga_seg_stride=0, z_seg_stride=0, n_seg=1, g_out=None):
+    """Adam on the Linear weight with the gradient formed from its factors (see ngan_adam_linear_factored).
+    ga: c8 gradient at the stem's pre-activation, z: latents [B, K]; with n_seg > 1 both are all-gathered buffers of
+    n_seg per-rank segments of b_per_seg samples, *_seg_stride bytes apart."""
+    b_per_seg = b_per_seg if b_per_seg is not None else z.shape[0]
+    _lib.call('ngan_adam_linear_factored', _p(p, F32), _p(m, F32), _p(v, F32), _p(shadow, BF16), _p(g_out, F32),
+              ctypes.c_void_p(ga.data_ptr()), ctypes.c_void_p(z.data_ptr()), b_per_seg * n_seg, b_per_seg,
+              int(ga_seg_stride), int(z_seg_stride), K, C, S, float(gscale), float(step_size), float(inv_bc2_sqrt),
+              _p(dyn, F32), beta1, beta2, eps, _stream())
+
+
 # ------------------------------------------------------------------------------------------ image pipeline
 def augment_batch(canvases, src_index, params, tap_first, tap_count, tap_weight, out, crop, workspace=None):
     """canvases [N, P, P] f32, src_index [b] i32, params [b, 16] f32, taps for crop -> R, out [b, 1, R, R] f32

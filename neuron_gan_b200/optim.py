@@ -83,8 +83,12 @@ class FusedAdam(torch.optim.Optimizer):
             self._ring.release(k)
 
     @torch.no_grad()
-    def launch(self):
-        """Device half: one multi-tensor kernel per <= 48 tensors, on the current stream (capturable)."""
+    def launch(self, factored=None):
+        """Device half: one multi-tensor kernel per <= 48 tensors, on the current stream (capturable).
+        factored: optional {id(param): dict(ga, z, gscale, K, C, S, b_per_seg, n_seg, ga_seg_stride, z_seg_stride,
+        g_out)} -- the generator's Linear weight, whose gradient is handed over as its two factors and formed inside
+        the Adam pass (ops.adam_linear_factored) instead of being read from p.grad."""
+        factored = factored or {}
         for group in self.param_groups:
             beta1, beta2 = group['betas']
             entries, touched = [], []
@@ -92,6 +96,22 @@ class FusedAdam(torch.optim.Optimizer):
                 if p.grad is None:
                     continue
                 st = self._state(p)
+                if id(p) in factored:
+                    f = factored[id(p)]
+                    ent = engine._cache_get(p)
+                    shadow = ent['shadow'] if ent is not None and 'shadow' in ent and ent['shadow'].device == p.device else None
+                    if self.capturable:
+                        self._ensure_dyn(p.device)
+                        a, b, dyn = 0.0, 0.0, self._dyn[self._slot[id(p)]]
+                    else:
+                        (a, b), dyn = self._scalars(group, max(st['step'], 1)), None
+                    ops.adam_linear_factored(p, st['exp_avg'], st['exp_avg_sq'], shadow, f['ga'], f['z'], f['K'], f['C'],
+                                             f['S'], f['gscale'], a, b, dyn, beta1, beta2, group['eps'],
+                                             b_per_seg=f.get('b_per_seg'), ga_seg_stride=f.get('ga_seg_stride', 0),
+                                             z_seg_stride=f.get('z_seg_stride', 0), n_seg=f.get('n_seg', 1),
+                                             g_out=f.get('g_out'))
+                    touched.append((p, shadow is not None))
+                    continue
                 # bf16 operand images of the GEMM weights (linear stem, 3x3 convs) are rewritten in the same pass
                 shadow, shadow_dims, shadow_kind = None, None, 0
                 ent = engine._cache_get(p) if p.dim() in (2, 4) else None

@@ -45,6 +45,10 @@ class TrainStep:
         self.segment_graphs = False     # capture three graphs even on one GPU (lets a caller time the three parts)
         self.segment_events = None      # when a list: 4 CUDA events per replayed iteration are appended (start, D, G, end)
         self.global_draws = True        # data parallel: draw the global batch on every rank and keep this rank's rows
+        self.factor_linear = True       # hand the Linear weight's gradient to Adam as its two factors (never materialised;
+                                        # with data parallelism the ranks all-gather 1 MB of factors instead of
+                                        # all-reducing the 67 MB product)
+        self.materialize_linear_grad = False   # with factor_linear: also write lin.weight.grad (plot_grad_norm wants it)
         self.fork_chains = True         # run the two independent halves of the critic step on two streams
         self._chain_stream = None
         self._bound = {}
@@ -84,13 +88,28 @@ class TrainStep:
                 for k in range(n_slots):
                     sinks[k][id(p)] = slots[k, off:off + p.numel()].view(p.shape)
                 off += p.numel()
-            ent = {'key': key, 'flat': flat, 'sinks': sinks, 'slots': slots if n_slots > 1 else None}
+            big = sum(p.numel() for p in active if p.numel() > (1 << 22))
+            ent = {'key': key, 'flat': flat, 'sinks': sinks, 'slots': slots if n_slots > 1 else None,
+                   'small': flat[:n - big] if big else flat}
             self._bound[id(net)] = ent
         return ent['flat'], ent['sinks']
 
     def _allreduce(self, flat):
         if self.dp:
             dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+
+    def _exchange_g(self, buf):
+        """Data-parallel exchange after the generator's backward pass: all-reduce (mean) of the small gradients and --
+        with factor_linear -- all-gather of the Linear gradient's factors into the step buffers (rank-major, what
+        ops.adam_linear_factored reads as segments)."""
+        if not self.dp:
+            return
+        if not self.factor_linear:
+            dist.all_reduce(self._bound[id(self.G)]['flat'], op=dist.ReduceOp.AVG)
+            return
+        dist.all_reduce(self._bound[id(self.G)]['small'], op=dist.ReduceOp.AVG)
+        dist.all_gather_into_tensor(buf.gather_ga.view(-1), buf.out.lin.ga0.reshape(-1))
+        dist.all_gather_into_tensor(buf.gather_z.view(-1), buf.out.lin.z.reshape(-1))
 
     # -- RNG draws in the reference's order: z (D_W_loss) -> z (grad pen) -> eps -> z (G_W_loss) --------------
     def draw_host(self, batch):
@@ -115,10 +134,16 @@ class TrainStep:
         """Step inputs: imgs = [x | G(z1) | G(z2)] (the critic batch [real; fake] and x_tilde are views of it),
         z12 = [z1; z2] (both detached generator passes of the critic step run as one batch)."""
         L = self.G.latent_dim
-        return SimpleNamespace(imgs=torch.empty((3 * B, R, R), dtype=F32, device=dev),
-                               z12=torch.empty((2 * B, L), dtype=F32, device=dev),
-                               z3=torch.empty((B, L), dtype=F32, device=dev),
-                               eps=torch.empty((B,), dtype=F32, device=dev), B=B, out=SimpleNamespace())
+        buf = SimpleNamespace(imgs=torch.empty((3 * B, R, R), dtype=F32, device=dev),
+                              z12=torch.empty((2 * B, L), dtype=F32, device=dev),
+                              z3=torch.empty((B, L), dtype=F32, device=dev),
+                              eps=torch.empty((B,), dtype=F32, device=dev), B=B, out=SimpleNamespace())
+        if self.dp and self.factor_linear:
+            world = dist.get_world_size()
+            n_ga = B * self.G.N_features_per_layer[0] * self.G.image_size_init ** 2
+            buf.gather_ga = torch.empty((world, n_ga), dtype=torch.bfloat16, device=dev)
+            buf.gather_z = torch.empty((world, B, L), dtype=F32, device=dev)
+        return buf
 
     def _load(self, buf, x, z1, z2, eps, z3):
         """Copy the iteration's inputs into the step buffers.  Device and pinned-host sources are copied directly
@@ -182,14 +207,28 @@ class TrainStep:
         g_xp = engine.d_backward(D, dctx, g_fake, None, want_gxp=True)
         gx = ops.unpool_image(g_xp, 0.25) if dctx.pooled else g_xp
         del dctx
-        engine.g_backward(G, gctx, gx, sink_g, linear_overwrite=True)
+        buf.out.lin = SimpleNamespace() if self.factor_linear else None
+        engine.g_backward(G, gctx, gx, sink_g, linear_overwrite=True, linear_factors=buf.out.lin)
         del gctx
         engine.side_join()
         return flat_g
 
     def _seg_end(self, buf):
         """Adam(G) (train.py:385) and the packed statistics (train.py:362, 389-394)"""
-        self.opt_g.launch()
+        factored = None
+        if self.factor_linear:
+            lin, f = self.G.layers[0], buf.out.lin
+            K, C, S = lin._ngan_dims
+            world = dist.get_world_size() if self.dp else 1
+            d = dict(K=K, C=C, S=S, gscale=f.scale / world, b_per_seg=buf.B, n_seg=world,
+                     g_out=self._bound[id(self.G)]['sinks'][0][id(lin.weight)] if self.materialize_linear_grad else None)
+            if self.dp:
+                d.update(ga=buf.gather_ga, z=buf.gather_z, ga_seg_stride=buf.gather_ga.stride(0) * 2,
+                         z_seg_stride=buf.gather_z.stride(0) * 4)
+            else:
+                d.update(ga=f.ga0, z=f.z)
+            factored = {id(lin.weight): d}
+        self.opt_g.launch(factored=factored)
         stats = torch.empty(5, dtype=F32, device=buf.z3.device)
         ops.pack_stats(buf.out.out3, buf.out.out1, buf.out.pen, stats)
         self._last_critic_out = (buf.out.out3, buf.out.pen)
@@ -207,7 +246,8 @@ class TrainStep:
         self.opt_d.advance()
         self.opt_g.advance()
         self._allreduce(self._seg_d(buf))
-        self._allreduce(self._seg_g(buf))
+        self._seg_g(buf)
+        self._exchange_g(buf)
         return self._seg_end(buf)
 
     def _run_multi_critic(self, images, draws, dev):
@@ -239,7 +279,8 @@ class TrainStep:
         z3 = sample_latent_vec((B, self.G.latent_dim)) if draws is None else draws[self.n_critic]
         buf.z3.copy_(z3.to(dev) if not z3.is_cuda else z3)
         self.opt_g.advance()
-        self._allreduce(self._seg_g(buf, adam_d=False))
+        self._seg_g(buf, adam_d=False)
+        self._exchange_g(buf)
         self._versions_seen = None
         return self._seg_end(buf)
 
@@ -266,7 +307,7 @@ class TrainStep:
         # alpha itself is NOT part of the key: the kernels read it from device memory (_sync_alpha), so one graph
         # serves every epoch of a fade-in; only whether a fade is in progress changes the kernel sequence
         return (B, R, self.G.alpha_value() < 1, self.D.alpha_value() < 1, self.G.N_layers, self.D.N_layers, self.dp,
-                self.lam, self.drift,
+                self.lam, self.drift, self.factor_linear, self.materialize_linear_grad,
                 tuple(id(p) for p in self.G.active_parameters()), tuple(id(p) for p in self.D.active_parameters()))
 
     def _capture(self, key, B, R, dev):
@@ -351,7 +392,7 @@ class TrainStep:
             if ev:
                 ev[1].record()
             ent.graphs[1].replay()
-            self._allreduce(ent.flats[1])
+            self._exchange_g(ent.buf)
             if ev:
                 ev[2].record()
             ent.graphs[2].replay()

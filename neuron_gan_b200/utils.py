@@ -279,7 +279,7 @@ def gen_samples_host(Generator: nn.Module, N_images=16, seed=None, dtype=torch.f
     dev = next(Generator.parameters()).device
     R = Generator.image_size
     z_latent = sample_latent_vec((N_images, Generator.latent_dim), seed=seed, device=dev)
-    key = (N_images, R, dtype, dev)
+    key = (N_images, R, dtype, dev, min(chunk, N_images))
     pool = _host_pool.get(key)
     if pool is None:
         if len(_host_pool) >= 4:
