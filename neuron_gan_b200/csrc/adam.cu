@@ -32,6 +32,16 @@ struct AdamTable {
     AdamEntry e[kAdamMaxTensors];
 };
 
+// One element of the update, with every rounding spelled out: the multi-tensor kernel and the factored Linear kernel
+// must produce the same bits from the same gradient (no compiler-chosen FMA contraction).
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, float beta1, float beta2, float eps,
+                                      float step_size, float inv_bc2_sqrt) {
+    m = __fmaf_rn(1.f - beta1, __fsub_rn(g, m), m);
+    v = __fmaf_rn(1.f - beta2, __fmul_rn(g, g), __fmul_rn(beta2, v));
+    const float denom = __fmaf_rn(sqrtf(v), inv_bc2_sqrt, eps);
+    p = __fmaf_rn(-step_size, __fdividef(m, denom), p);
+}
+
 __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ AdamTable tab, float beta1,
                                                          float beta2, float eps) {
     const AdamEntry& t = tab.e[blockIdx.y];
@@ -39,10 +49,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
     const float inv_bc2_sqrt = t.dyn ? __ldg(t.dyn + 1) : t.inv_bc2_sqrt;
     const long long n4 = t.n >> 2;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-#define NGAN_ADAM1(c)                                                      \
-    m.c = m.c + (1.f - beta1) * (g.c - m.c);                               \
-    v.c = beta2 * v.c + (1.f - beta2) * g.c * g.c;                         \
-    p.c = p.c - step_size * (m.c / (sqrtf(v.c) * inv_bc2_sqrt + eps));
+#define NGAN_ADAM1(c) adam1(p.c, g.c, m.c, v.c, beta1, beta2, eps, step_size, inv_bc2_sqrt);
     if (t.shadow && t.shadow_kind == 1 && (t.shadow_c & 1) == 0) {
         // The linear weight [C*SS][K] with its operand image [SS][K/8][C][8]: one thread updates the 8 k's of two
         // channels c, c+1 of one pixel -- rows f and f + SS of the master, 32 contiguous bytes each -- and writes
@@ -120,9 +127,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
         if (i < t.n) {
             const float g = t.g[i];
             float m = t.m[i], v = t.v[i], p = t.p[i];
-            m = m + (1.f - beta1) * (g - m);
-            v = beta2 * v + (1.f - beta2) * g * g;
-            p = p - step_size * (m / (sqrtf(v) * inv_bc2_sqrt + eps));
+            adam1(p, g, m, v, beta1, beta2, eps, step_size, inv_bc2_sqrt);
             t.p[i] = p; t.m[i] = m; t.v[i] = v;
             if (t.shadow && !t.shadow_kind) t.shadow[i] = __float2bfloat16(p);   // (image layouts have n % 4 == 0)
         }
@@ -197,12 +202,11 @@ __global__ void __launch_bounds__(256) adam_linear_factored_kernel(const AdamLin
                 float4 p = reinterpret_cast<float4*>(a.p)[i + h];
                 float4 m = reinterpret_cast<float4*>(a.m)[i + h];
                 float4 v = reinterpret_cast<float4*>(a.v)[i + h];
-                const float4 g = make_float4(a.gscale * acc[e][4 * h], a.gscale * acc[e][4 * h + 1],
-                                             a.gscale * acc[e][4 * h + 2], a.gscale * acc[e][4 * h + 3]);
-#define NGAN_ADAM1(c)                                                      \
-    m.c = m.c + (1.f - a.beta1) * (g.c - m.c);                             \
-    v.c = a.beta2 * v.c + (1.f - a.beta2) * g.c * g.c;                     \
-    p.c = p.c - step_size * (m.c / (sqrtf(v.c) * inv_bc2_sqrt + a.eps));
+                // __fmul_rn: the gradient is rounded to fp32 exactly as if it had been stored (no FMA contraction with
+                // the moment updates below), so this pass is bit-identical to ngan_linear_wgrad + ngan_adam_multi
+                const float4 g = make_float4(__fmul_rn(a.gscale, acc[e][4 * h]), __fmul_rn(a.gscale, acc[e][4 * h + 1]),
+                                             __fmul_rn(a.gscale, acc[e][4 * h + 2]), __fmul_rn(a.gscale, acc[e][4 * h + 3]));
+#define NGAN_ADAM1(c) adam1(p.c, g.c, m.c, v.c, a.beta1, a.beta2, a.eps, step_size, inv_bc2_sqrt);
                 NGAN_ADAM1(x) NGAN_ADAM1(y) NGAN_ADAM1(z) NGAN_ADAM1(w)
 #undef NGAN_ADAM1
                 reinterpret_cast<float4*>(a.p)[i + h] = p;

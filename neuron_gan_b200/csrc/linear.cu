@@ -250,10 +250,10 @@ __global__ void __launch_bounds__(K / 4) linear_wgrad_kernel(const uint4* __rest
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const float gv = sg[bb][e];
-                acc[e][0] += gv * zv.x;
-                acc[e][1] += gv * zv.y;
-                acc[e][2] += gv * zv.z;
-                acc[e][3] += gv * zv.w;
+                acc[e][0] = __fmaf_rn(gv, zv.x, acc[e][0]);
+                acc[e][1] = __fmaf_rn(gv, zv.y, acc[e][1]);
+                acc[e][2] = __fmaf_rn(gv, zv.z, acc[e][2]);
+                acc[e][3] = __fmaf_rn(gv, zv.w, acc[e][3]);
             }
         }
     }
@@ -261,10 +261,11 @@ __global__ void __launch_bounds__(K / 4) linear_wgrad_kernel(const uint4* __rest
     for (int e = 0; e < 8; ++e) {
         float4* d = reinterpret_cast<float4*>(dw + (static_cast<size_t>(j * 8 + e) * SS + p) * K) + threadIdx.x;
         float4 o = accumulate ? *d : make_float4(0.f, 0.f, 0.f, 0.f);
-        o.x += scale * acc[e][0];
-        o.y += scale * acc[e][1];
-        o.z += scale * acc[e][2];
-        o.w += scale * acc[e][3];
+        // (explicit roundings: ngan_adam_linear_factored forms the same gradient in registers, bit for bit)
+        o.x = __fadd_rn(o.x, __fmul_rn(scale, acc[e][0]));
+        o.y = __fadd_rn(o.y, __fmul_rn(scale, acc[e][1]));
+        o.z = __fadd_rn(o.z, __fmul_rn(scale, acc[e][2]));
+        o.w = __fadd_rn(o.w, __fmul_rn(scale, acc[e][3]));
         *d = o;
     }
 }

@@ -33,12 +33,19 @@ gen = torch.Generator().manual_seed(11)
 images = [torch.rand(GB, 1, res, res, generator=gen) * 2 - 1 for _ in range(steps)]
 
 
+def params_of(G, D):
+    return [v.detach().clone() for net in (G, D) for v in net.state_dict().values()]
+
+
 def run(data_parallel):
     G, D = build_networks(res, alpha, seed=1, device=dev)
     step = TrainStep(G, D, data_parallel=data_parallel)
     torch.manual_seed(77)                     # the CPU draw stream, identical on every rank
     out = []
+    first = None
     for x in images:
+        if len(out) == 1:
+            first = params_of(G, D)           # the parameters after ONE iteration
         if data_parallel:
             xs = dp.shard_rows(x, rank, world).contiguous().to(dev)
             out.append(step(xs).cpu())        # TrainStep draws the global batch and keeps this rank's rows
@@ -46,10 +53,18 @@ def run(data_parallel):
             draws = tuple(t.to(dev) for t in dp.global_draws(sample_latent_vec, GB, G.latent_dim, 0, 1))
             out.append(step(x.to(dev), draws).cpu())
     torch.cuda.synchronize()
-    return G, D, torch.stack(out), step
+    return G, D, torch.stack(out), step, first
 
 
-G, D, stats_dp, step_dp = run(True)
+def diff(pa, pb):
+    worst, total, n = 0.0, 0.0, 0
+    for a, b in zip(pa, pb):
+        d = (a.float() - b.float()).abs()
+        worst, total, n = max(worst, d.max().item()), total + d.sum().item(), n + d.numel()
+    return worst, total / n
+
+
+G, D, stats_dp, step_dp, first_dp = run(True)
 # statistics: mean over ranks of the shard statistics
 s = stats_dp.to(dev)
 dist.all_reduce(s, op=dist.ReduceOp.AVG)
@@ -61,23 +76,22 @@ dist.all_gather(digests, digest)
 identical = all(torch.equal(d, digests[0]) for d in digests)
 dist.barrier()
 if rank == 0:
-    G1, D1, stats_1, _ = run(False)
+    G1, D1, stats_1, _, first_1 = run(False)
     print(f'world={world} res={res} alpha={alpha} global batch={GB} steps={steps} last_run={step_dp.last_run}')
     print('replicas bit-identical after the DP run:', identical)
     print('stats DP     :', [round(v, 6) for v in stats_dp[-1].tolist()])
     print('stats 1 GPU  :', [round(v, 6) for v in stats_1[-1].tolist()])
     dmax = (stats_dp - stats_1).abs().max().item()
     print(f'max |stat difference| over {steps} iterations: {dmax:.3e}')
-    worst, mean = 0.0, 0.0
-    n = 0
-    for (k, a), (_, b) in list(zip(G.state_dict().items(), G1.state_dict().items())) + \
-            list(zip(D.state_dict().items(), D1.state_dict().items())):
-        d = (a.float() - b.float()).abs()
-        worst = max(worst, d.max().item())
-        mean += d.sum().item()
-        n += d.numel()
-    print(f'parameters after {steps} iterations: max |diff| {worst:.3e}, mean |diff| {mean / n:.3e} (lr = 1e-4)')
-    ok = identical and dmax < 5e-3 and worst <= steps * 2.1e-4 and mean / n < 1e-5
+    w1, m1 = diff(first_dp, first_1)
+    wn, mn = diff(params_of(G, D), params_of(G1, D1))
+    print(f'parameters after 1 iteration : max |diff| {w1:.3e}, mean |diff| {m1:.3e} (lr = 1e-4)')
+    print(f'parameters after {steps} iterations: max |diff| {wn:.3e}, mean |diff| {mn:.3e}')
+    # One iteration: the two runs see identical weights, so they differ only by the order in which fp32 gradient sums
+    # are added (shards vs one batch); Adam turns a sign change of a ~0 gradient element into 2*lr, hence the bound on
+    # the maximum.  Later iterations: bf16 rounding of the activations amplifies those last-bit differences (rounding
+    # boundaries), Adam normalises the resulting gradient noise -- bounded by steps * 2 * lr, small in the mean.
+    ok = identical and dmax < 5e-3 and w1 <= 2.1e-4 and m1 < 5e-6 and wn <= steps * 2.1e-4 and mn < 1e-4
     print('DP_EQUIVALENCE_OK' if ok else 'DP_EQUIVALENCE_FAILED')
 dist.barrier()
 dist.destroy_process_group()

@@ -68,6 +68,7 @@ def test_train_step_losses_match_reference(golden, key):
     res, alpha, batch = ref['res'], ref['alpha'], ref['batch']
     G, D = nets(res, alpha)
     step = TrainStep(G, D)
+    step.materialize_linear_grad = True     # (by default the Linear weight's gradient only exists as its two factors)
     x = O.synthetic_images(batch, res).to(DEV)
     stats = TrainStep.stats_dict(step(x).cpu())          # draws z, z, eps, z from the global CPU stream
     for k, v in ref['stats'].items():
@@ -222,6 +223,7 @@ def test_gradients_match_bf16_emulating_oracle(res, alpha, batch):
     with O.emulate_bf16():
         ref = tr.iteration(x, draws=draws)
     step = TrainStep(G, D)
+    step.materialize_linear_grad = True
     stats = TrainStep.stats_dict(step(x.to(DEV), tuple(t.to(DEV) for t in draws)).cpu())
     for k, v in ref.items():
         assert abs(stats[k] - v) <= 2e-3 * max(1.0, abs(v)), (k, stats[k], v)
@@ -247,6 +249,32 @@ def test_gradients_match_bf16_emulating_oracle(res, alpha, batch):
     med_tol, max_tol = {16: (0.02, 0.04), 32: (0.06, 0.10), 64: (0.08, 0.30), 128: (0.12, 0.35)}.get(res, (0.20, 0.90))
     assert vals[len(vals) // 2] < med_tol, report
     assert vals[-1] < max_tol, report
+
+
+def test_factored_linear_adam_equals_materialised_gradient():
+    """The generator's Linear weight (98 % of its parameters) is updated from the two factors of its gradient inside
+    the Adam pass (ops.adam_linear_factored); with factor_linear = False the 67 MB gradient is written by
+    linear_wgrad and read by adam_multi as in round 1.  Same bits either way; materialize_linear_grad additionally
+    writes the gradient, equal to linear_wgrad's."""
+    from neuron_gan_b200.train_step import TrainStep
+    res, alpha, B = 32, 0.5, 8
+    x = O.synthetic_images(B, res, seed=31).to(DEV)
+    draws = tuple(t.to(DEV) for t in draws_like_reference(B))
+    out = {}
+    for mode in ('factored', 'factored+grad', 'materialised'):
+        G, D = nets(res, alpha)
+        step = TrainStep(G, D)
+        step.factor_linear = mode != 'materialised'
+        step.materialize_linear_grad = mode == 'factored+grad'
+        for _ in range(3):                                   # eager, eager + capture, replay
+            stats = step(x, draws)
+        out[mode] = (stats.cpu(), {k: v.clone() for k, v in G.state_dict().items()}, G.layers[0].weight.grad.clone())
+    for mode in ('factored+grad', 'materialised'):
+        assert torch.equal(out['factored'][0], out[mode][0])
+        for k, v in out['factored'][1].items():
+            assert torch.equal(v, out[mode][1][k]), (mode, k)
+    assert torch.equal(out['factored+grad'][2], out['materialised'][2])
+    assert out['factored'][2].abs().max().item() == 0.0      # not materialised by default
 
 
 def _snapshot(nets_, opts):
