@@ -101,8 +101,8 @@ int ngan_bias_grad(const void* ga_c8, float* gb, int accumulate, float* workspac
  * parameter-gradient reduction; exported for hosts that want to place it on another stream) */
 int ngan_reduce_partials(const float* partials, int n_partials, long long n, long long ld, float scale, float* out,
                          int accumulate, void* stream);
-/* out[i] = slots[i] + slots[ld + i] + ... (n_slots terms, in slot order) */
-int ngan_sum_slots(const float* slots, int n_slots, long long n, long long ld, float* out, void* stream);
+/* out[i] = scale * (slots[i] + slots[ld + i] + ...) (n_slots terms, in slot order; ld in floats) */
+int ngan_sum_slots(const float* slots, int n_slots, long long n, long long ld, float scale, float* out, void* stream);
 /* cudaMemsetAsync through the C ABI (gradient-slot zeroing inside a captured iteration; D.zero_grad(), train.py:357) */
 int ngan_memset(void* dst, int value, long long bytes, void* stream);
 

@@ -128,9 +128,9 @@ int ngan_reduce_partials(const float* partials, int n_partials, long long n, lon
     NGAN_REQUIRE(partials && out && n_partials > 0 && n > 0 && ld >= n, "reduce_partials: bad arguments");
     return reduce_partials(partials, n_partials, n, ld, scale, out, accumulate, S(stream));
 }
-int ngan_sum_slots(const float* slots, int n_slots, long long n, long long ld, float* out, void* stream) {
+int ngan_sum_slots(const float* slots, int n_slots, long long n, long long ld, float scale, float* out, void* stream) {
     NGAN_REQUIRE(slots && out && n_slots > 0 && n > 0 && ld >= n, "sum_slots: bad arguments");
-    return sum_slots(slots, n_slots, n, ld, out, S(stream));
+    return sum_slots(slots, n_slots, n, ld, scale, out, S(stream));
 }
 int ngan_memset(void* dst, int value, long long bytes, void* stream) {
     NGAN_REQUIRE(dst && bytes >= 0, "memset: bad arguments");

@@ -98,17 +98,18 @@ int reduce_partials(const float* partials, int n_partials, long long n, long lon
     if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(reduce_partials)");
     return check_launch("reduce_partials");
 }
-// out[i] = sum_k slots[k * ld + i] in slot order (the critic's three gradient contributions, train_step.py)
-__global__ void sum_slots_kernel(const float* __restrict__ slots, int n_slots, long long n, long long ld,
+// out[i] = scale * sum_k slots[k * ld + i] in slot order (the critic's three gradient contributions; the ranks'
+// all-gathered small gradients of the generator: train_step.py)
+__global__ void sum_slots_kernel(const float* __restrict__ slots, int n_slots, long long n, long long ld, float scale,
                                  float* __restrict__ out) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float v = slots[i];
     for (int k = 1; k < n_slots; ++k) v += slots[k * ld + i];
-    out[i] = v;
+    out[i] = scale == 1.f ? v : scale * v;
 }
-int sum_slots(const float* slots, int n_slots, long long n, long long ld, float* out, cudaStream_t st) {
-    sum_slots_kernel<<<nblocks(static_cast<size_t>(n), 256), 256, 0, st>>>(slots, n_slots, n, ld, out);
+int sum_slots(const float* slots, int n_slots, long long n, long long ld, float scale, float* out, cudaStream_t st) {
+    sum_slots_kernel<<<nblocks(static_cast<size_t>(n), 256), 256, 0, st>>>(slots, n_slots, n, ld, scale, out);
     return check_launch("sum_slots");
 }
 size_t pixel_reduction_workspace_bytes(int B, int C, int H, int W) {

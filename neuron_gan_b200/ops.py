@@ -178,10 +178,13 @@ def reduce_partials(partials, n_partials, n, ld, out, scale=1.0, accumulate=Fals
               _stream())
 
 
-def sum_slots(slots, out):
-    """out = slots[0] + slots[1] + ... in slot order; slots: [n_slots, n] fp32"""
+def sum_slots(slots, out, scale=1.0):
+    """out = scale * (slots[0] + slots[1] + ...) in slot order; slots: [n_slots, n] fp32, rows `slots.stride(0)` apart"""
     n_slots, n = slots.shape
-    _lib.call('ngan_sum_slots', _p(slots, F32), n_slots, n, n, _p(out, F32), _stream())
+    if slots.stride(1) != 1 or not slots.is_cuda or slots.dtype != F32:
+        raise _lib.NganError('sum_slots needs fp32 CUDA rows with unit inner stride')
+    _lib.call('ngan_sum_slots', ctypes.c_void_p(slots.data_ptr()), n_slots, n, slots.stride(0), float(scale),
+              _p(out, F32), _stream())
     return out
 
 

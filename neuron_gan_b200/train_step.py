@@ -51,6 +51,7 @@ class TrainStep:
         self.materialize_linear_grad = False   # with factor_linear: also write lin.weight.grad (plot_grad_norm wants it)
         self.fork_chains = True         # run the two independent halves of the critic step on two streams
         self._chain_stream = None
+        self._comm_stream = None        # data parallel: the critic's gradient all-reduce overlaps the generator forward
         self._bound = {}
         self._graphs = {}               # configuration key -> captured iteration, least recently used first
         self.max_graphs = 4             # during a fade-in alpha (part of the key) changes every epoch: old graphs go
@@ -99,17 +100,43 @@ class TrainStep:
             dist.all_reduce(flat, op=dist.ReduceOp.AVG)
 
     def _exchange_g(self, buf):
-        """Data-parallel exchange after the generator's backward pass: all-reduce (mean) of the small gradients and --
-        with factor_linear -- all-gather of the Linear gradient's factors into the step buffers (rank-major, what
-        ops.adam_linear_factored reads as segments)."""
+        """Data-parallel exchange after the generator's backward pass, as ONE collective: every rank packs
+        [small gradients | latents z | Linear-gradient factor ga0] into one buffer, the buffers are all-gathered, and
+        each rank (a) adds the ranks' small gradients in rank order (ops.sum_slots: every replica computes the same
+        bits, whatever algorithm NCCL picks) and (b) hands the gathered factors to ops.adam_linear_factored as
+        per-rank segments.  1.2 MB + 32 KB + 1 MB per rank instead of an all-reduce of 68 MB."""
         if not self.dp:
             return
+        ent = self._bound[id(self.G)]
         if not self.factor_linear:
-            dist.all_reduce(self._bound[id(self.G)]['flat'], op=dist.ReduceOp.AVG)
+            dist.all_reduce(ent['flat'], op=dist.ReduceOp.AVG)
             return
-        dist.all_reduce(self._bound[id(self.G)]['small'], op=dist.ReduceOp.AVG)
-        dist.all_gather_into_tensor(buf.gather_ga.view(-1), buf.out.lin.ga0.reshape(-1))
-        dist.all_gather_into_tensor(buf.gather_z.view(-1), buf.out.lin.z.reshape(-1))
+        pk = buf.pack
+        pk.send_small.copy_(ent['small'], non_blocking=True)
+        pk.send_z.copy_(buf.out.lin.z.reshape(-1), non_blocking=True)
+        pk.send_ga.copy_(buf.out.lin.ga0.reshape(-1), non_blocking=True)
+        dist.all_gather_into_tensor(pk.recv.view(-1), pk.send)
+        ops.sum_slots(pk.recv_small, ent['small'], scale=1.0 / pk.world)
+
+    def _make_pack(self, B, dev):
+        """Send / receive buffers of _exchange_g (per step-buffer set: the factor sizes depend on the batch)."""
+        world = dist.get_world_size()
+        n_small = self._bind(self.G)[0].numel() - sum(p.numel() for p in self.G.active_parameters()
+                                                      if p.numel() > (1 << 22))
+        L = self.G.latent_dim
+        n_ga = B * self.G.N_features_per_layer[0] * self.G.image_size_init ** 2
+        pad = lambda nbytes: (nbytes + 15) // 16 * 16
+        o_z = pad(n_small * 4)
+        o_ga = o_z + pad(B * L * 4)
+        per = o_ga + pad(n_ga * 2)
+        send = torch.empty(per, dtype=torch.uint8, device=dev)
+        recv = torch.empty((world, per), dtype=torch.uint8, device=dev)
+        view = lambda t, o, n, dt: t[..., o:o + n * (4 if dt is F32 else 2)].view(dt)
+        return SimpleNamespace(world=world, per=per, send=send, recv=recv, n_small=n_small,
+                               send_small=view(send, 0, n_small, F32), send_z=view(send, o_z, B * L, F32),
+                               send_ga=view(send, o_ga, n_ga, torch.bfloat16),
+                               recv_small=view(recv, 0, n_small, F32),              # [world, n_small], row stride per / 4
+                               recv_z=view(recv, o_z, B * L, F32), recv_ga=view(recv, o_ga, n_ga, torch.bfloat16))
 
     # -- RNG draws in the reference's order: z (D_W_loss) -> z (grad pen) -> eps -> z (G_W_loss) --------------
     def draw_host(self, batch):
@@ -139,10 +166,7 @@ class TrainStep:
                               z3=torch.empty((B, L), dtype=F32, device=dev),
                               eps=torch.empty((B,), dtype=F32, device=dev), B=B, out=SimpleNamespace())
         if self.dp and self.factor_linear:
-            world = dist.get_world_size()
-            n_ga = B * self.G.N_features_per_layer[0] * self.G.image_size_init ** 2
-            buf.gather_ga = torch.empty((world, n_ga), dtype=torch.bfloat16, device=dev)
-            buf.gather_z = torch.empty((world, B, L), dtype=F32, device=dev)
+            buf.pack = self._make_pack(B, dev)
         return buf
 
     def _load(self, buf, x, z1, z2, eps, z3):
@@ -195,13 +219,23 @@ class TrainStep:
         ops.sum_slots(self._bound[id(D)]['slots'], flat_d)
         return flat_d
 
+    def _seg_g1(self, buf):
+        """The generator's forward pass of the generator step (train.py:376).  It depends on neither the critic's
+        gradients nor its update, so with data parallelism it runs while the critic's gradients are all-reduced."""
+        buf.out.fake, buf.out.gctx = engine.g_forward(self.G, buf.z3, save=True)
+
     def _seg_g(self, buf, adam_d=True):
-        """Adam(D) (train.py:366), then the generator step up to complete gradients (train.py:375-384)"""
+        self._seg_g1(buf)
+        return self._seg_g2(buf, adam_d)
+
+    def _seg_g2(self, buf, adam_d=True):
+        """Adam(D) (train.py:366), then the rest of the generator step up to complete gradients (train.py:375-384)"""
         G, D = self.G, self.D
         if adam_d:
             self.opt_d.launch()
         flat_g, (sink_g,) = self._bind(G)
-        fake, gctx = engine.g_forward(G, buf.z3, save=True)
+        fake, gctx = buf.out.fake, buf.out.gctx
+        buf.out.fake = buf.out.gctx = None
         s_fake, dctx = engine.d_forward(D, fake, save=True)
         buf.out.out1, g_fake = ops.gloss(s_fake)
         g_xp = engine.d_backward(D, dctx, g_fake, None, want_gxp=True)
@@ -223,8 +257,7 @@ class TrainStep:
             d = dict(K=K, C=C, S=S, gscale=f.scale / world, b_per_seg=buf.B, n_seg=world,
                      g_out=self._bound[id(self.G)]['sinks'][0][id(lin.weight)] if self.materialize_linear_grad else None)
             if self.dp:
-                d.update(ga=buf.gather_ga, z=buf.gather_z, ga_seg_stride=buf.gather_ga.stride(0) * 2,
-                         z_seg_stride=buf.gather_z.stride(0) * 4)
+                d.update(ga=buf.pack.recv_ga, z=buf.pack.recv_z, ga_seg_stride=buf.pack.per, z_seg_stride=buf.pack.per)
             else:
                 d.update(ga=f.ga0, z=f.z)
             factored = {id(lin.weight): d}
@@ -330,12 +363,12 @@ class TrainStep:
                 graphs.append(g)
             return graphs, outs
 
-        # With data parallelism: three graphs, the two all-reduces issued by the host in between.  (Capturing the NCCL
+        # With data parallelism: four graphs, the collectives issued by the host in between.  (Capturing the NCCL
         # calls into one graph was measured: same iteration time at 2 GPUs, and the process then hung in
         # destroy_process_group -- not worth it.)
-        three = [self._seg_d, self._seg_g, self._seg_end]
+        parts = [self._seg_d, self._seg_g1, self._seg_g2, self._seg_end]
         if self.dp or self.segment_graphs:
-            ent.graphs, ent.flats = capture(three)
+            ent.graphs, ent.flats = capture(parts)
         else:
             ent.graphs, ent.flats = capture([whole])
         ent.stats = ent.flats[-1]
@@ -387,15 +420,25 @@ class TrainStep:
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
                 self.segment_events.append(ev)
                 ev[0].record()
+            cur = torch.cuda.current_stream()
             ent.graphs[0].replay()
-            self._allreduce(ent.flats[0])
+            if self.dp:
+                # the critic's 2 MB all-reduce runs on the communication stream beside the generator's forward pass
+                if self._comm_stream is None:
+                    self._comm_stream = torch.cuda.Stream()
+                self._comm_stream.wait_stream(cur)
+                with torch.cuda.stream(self._comm_stream):
+                    self._allreduce(ent.flats[0])
+            ent.graphs[1].replay()
+            if self.dp:
+                cur.wait_stream(self._comm_stream)
             if ev:
                 ev[1].record()
-            ent.graphs[1].replay()
+            ent.graphs[2].replay()
             self._exchange_g(ent.buf)
             if ev:
                 ev[2].record()
-            ent.graphs[2].replay()
+            ent.graphs[3].replay()
             if ev:
                 ev[3].record()
         self._last_key = key
