@@ -222,7 +222,9 @@ int ngan_adam_multi(const ngan_adam_tensor* tensors, int n_tensors, float beta1,
  * all-gather the factors (1 MB + 32 KB per rank) instead of all-reducing the product.  Sample b is row b % b_per_seg
  * of segment b / b_per_seg (segments *_seg_stride BYTES apart: the layout of an all-gathered buffer; one segment:
  * b_per_seg = Btot).  shadow_img (optional): the operand image of ngan_prep_linear_weight, refreshed in the same pass;
- * g_out (optional): also write the gradient.  step_size / inv_bc2_sqrt / dyn as in ngan_adam_tensor. */
+ * g_out (optional): also write the gradient.  p == NULL (then m, v are ignored and g_out is required): only form the
+ * gradient -- the tensor-core replacement of ngan_linear_wgrad for an all-gathered global batch.  step_size /
+ * inv_bc2_sqrt / dyn as in ngan_adam_tensor. */
 int ngan_adam_linear_factored(float* p, float* m, float* v, void* shadow_img, float* g_out, const void* ga_c8,
                               const float* z, int Btot, int b_per_seg, long long ga_seg_stride, long long z_seg_stride,
                               int K, int C, int S, float gscale, float step_size, float inv_bc2_sqrt,

@@ -6,6 +6,8 @@
 // computed on the host in double precision, like torch does, and travel in the descriptor table, which is
 // passed by value in kernel-parameter space (no device-side table to maintain).
 // Optionally refreshes a bf16 shadow copy of the parameter in the same pass (the generator's linear weight).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "conv_args.cuh"
 #include "kernels.h"
@@ -225,6 +227,143 @@ __global__ void __launch_bounds__(256) adam_linear_factored_kernel(const AdamLin
         }
     }
 }
+// ---- tensor-core version (C % 128 == 0, K % 128 == 0): the rank-Btot product runs on mma.sync m16n8k16, so the pass
+// stays bound by Adam's 28 B / element for ANY global batch (the FMA version above needs 64 FMAs per sample and 8x8
+// tile: 119 us at 64 samples, 240 us at 128 -- more than the 73 us of memory traffic).  ga is bf16 already; z is split
+// into two bf16 terms z = hi + lo (|error| <= 2^-17 |z|), two MMAs per tile, fp32 accumulation: the gradient agrees
+// with the fp32-z product to ~1e-5 relative.
+// One block = one pixel px x 128 channels x 128 k.  Shared memory: the ga tile [b][128 ch] and the two z tiles
+// [b][128 k], rows padded to 272 B (conflict-free ldmatrix).  A C8 granule row [b][8 ch] is the transpose of the mma
+// A fragment and a z row [b][8 k] the transpose of the B fragment: ldmatrix.trans delivers both (as in wgrad.cu).
+// Warp w owns channels 16w..16w+15 x all 128 k: 64 fp32 accumulators per thread, then the Adam update straight from
+// the accumulator fragments (each quad of lanes covers one full 32-byte sector of p / m / v per row).
+constexpr int kLinPitch = 272;     // bytes per shared-memory row: 128 bf16 + 16 B pad
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, "
+        "%2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool ADAM>
+__global__ void __launch_bounds__(256, 2) adam_linear_mma_kernel(const AdamLinearArgs a, int Bpad) {
+    extern __shared__ __align__(16) uint8_t lin_smem[];
+    uint8_t* s_ga = lin_smem;                                   // [Bpad][kLinPitch]
+    uint8_t* s_zh = s_ga + static_cast<size_t>(Bpad) * kLinPitch;
+    uint8_t* s_zl = s_zh + static_cast<size_t>(Bpad) * kLinPitch;
+    const int px = blockIdx.x, k0 = blockIdx.y * 128, c0 = blockIdx.z * 128;
+    const int NCH = a.C >> 3, KG = a.K >> 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- stage the factors: 16 granules of ga and 128 latents (as hi / lo bf16) per sample; pad rows are zero
+    for (int i = threadIdx.x; i < Bpad * 16; i += blockDim.x) {
+        const int b = i >> 4, jj = i & 15;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (b < a.Btot) {
+            const int seg = b / a.b_per_seg, row = b - seg * a.b_per_seg;
+            v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(a.ga) + seg * a.ga_seg_stride) +
+                      (static_cast<size_t>(row) * NCH + (c0 >> 3) + jj) * a.SS + px);
+        }
+        *reinterpret_cast<uint4*>(s_ga + b * kLinPitch + jj * 16) = v;
+    }
+    for (int i = threadIdx.x; i < Bpad * 32; i += blockDim.x) {
+        const int b = i >> 5, q = i & 31;                       // q: float4 index inside the 128-k slice
+        float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < a.Btot) {
+            const int seg = b / a.b_per_seg, row = b - seg * a.b_per_seg;
+            zv = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(a.z) + seg * a.z_seg_stride +
+                                                       static_cast<size_t>(row) * a.K * sizeof(float)) + (k0 >> 2) + q);
+        }
+        const float f[4] = {zv.x, zv.y, zv.z, zv.w};
+        uint32_t hi[2], lo[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const __nv_bfloat16 h0 = __float2bfloat16(f[2 * h]), h1 = __float2bfloat16(f[2 * h + 1]);
+            hi[h] = pack_bf16(__bfloat162float(h0), __bfloat162float(h1));
+            lo[h] = pack_bf16(f[2 * h] - __bfloat162float(h0), f[2 * h + 1] - __bfloat162float(h1));
+        }
+        *reinterpret_cast<uint2*>(s_zh + b * kLinPitch + q * 8) = make_uint2(hi[0], hi[1]);
+        *reinterpret_cast<uint2*>(s_zl + b * kLinPitch + q * 8) = make_uint2(lo[0], lo[1]);
+    }
+    __syncthreads();
+    // ---- g tile = ga^T z: M = 16 channels of this warp, N = 128 k (16 n-tiles), K = samples
+    float acc[16][4];
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[nt][q] = 0.f;
+    const int mi = lane >> 3, ri = lane & 7;
+    const uint32_t a_lane = smem_u32(s_ga) + ((mi >> 1) * 8 + ri) * kLinPitch + (warp * 2 + (mi & 1)) * 16;
+    const uint32_t bh_lane = smem_u32(s_zh) + ((mi & 1) * 8 + ri) * kLinPitch + (mi >> 1) * 16;
+    const uint32_t bl_lane = smem_u32(s_zl) + ((mi & 1) * 8 + ri) * kLinPitch + (mi >> 1) * 16;
+    for (int b0 = 0; b0 < Bpad; b0 += 16) {
+        uint32_t af[4];
+        ldsm_x4_trans(a_lane + b0 * kLinPitch, af);
+#pragma unroll
+        for (int np = 0; np < 8; ++np) {                        // pairs of n-tiles
+            uint32_t bh[4], bl[4];
+            ldsm_x4_trans(bh_lane + b0 * kLinPitch + np * 32, bh);
+            ldsm_x4_trans(bl_lane + b0 * kLinPitch + np * 32, bl);
+            mma16816(acc[2 * np], af, bh[0], bh[1]);
+            mma16816(acc[2 * np + 1], af, bh[2], bh[3]);
+            mma16816(acc[2 * np], af, bl[0], bl[1]);
+            mma16816(acc[2 * np + 1], af, bl[2], bl[3]);
+        }
+    }
+    // ---- Adam straight from the accumulator fragments: c[0..1] = (channel g, k 2t..2t+1), c[2..3] = (channel g + 8, same k)
+    const float step_size = a.dyn ? __ldg(a.dyn) : a.step_size;
+    const float inv_bc2_sqrt = a.dyn ? __ldg(a.dyn + 1) : a.inv_bc2_sqrt;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = c0 + warp * 16 + g + 8 * h;
+        const size_t row = (static_cast<size_t>(c) * a.SS + px) * a.K;
+        // four n-tiles at a time: 12 independent 8-byte loads in flight per thread before the first use (with one
+        // n-tile per iteration the pass ran at the latency of its loads, not at HBM bandwidth)
+        if constexpr (!ADAM) {                      // gradient only: dW = gscale * ga^T z, written once
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt) {
+                const size_t i2 = (row + k0 + nt * 8 + 2 * t) >> 1;
+                reinterpret_cast<float2*>(a.g_out)[i2] =
+                    make_float2(__fmul_rn(a.gscale, acc[nt][2 * h]), __fmul_rn(a.gscale, acc[nt][2 * h + 1]));
+            }
+            continue;
+        }
+#pragma unroll
+        for (int n0 = 0; n0 < 16; n0 += 4) {
+            float2 p[4], m[4], v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const size_t i2 = (row + k0 + (n0 + q) * 8 + 2 * t) >> 1;       // float2 index
+                p[q] = reinterpret_cast<const float2*>(a.p)[i2];
+                m[q] = reinterpret_cast<const float2*>(a.m)[i2];
+                v[q] = reinterpret_cast<const float2*>(a.v)[i2];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int nt = n0 + q, k = k0 + nt * 8 + 2 * t;
+                const size_t i2 = (row + k) >> 1;
+                const float gx = __fmul_rn(a.gscale, acc[nt][2 * h]), gy = __fmul_rn(a.gscale, acc[nt][2 * h + 1]);
+                adam1(p[q].x, gx, m[q].x, v[q].x, a.beta1, a.beta2, a.eps, step_size, inv_bc2_sqrt);
+                adam1(p[q].y, gy, m[q].y, v[q].y, a.beta1, a.beta2, a.eps, step_size, inv_bc2_sqrt);
+                reinterpret_cast<float2*>(a.p)[i2] = p[q];
+                reinterpret_cast<float2*>(a.m)[i2] = m[q];
+                reinterpret_cast<float2*>(a.v)[i2] = v[q];
+                if (a.g_out) reinterpret_cast<float2*>(a.g_out)[i2] = make_float2(gx, gy);
+                if (a.shadow) {
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(a.shadow) +
+                                    (((static_cast<size_t>(px) * KG + (k >> 3)) * a.C + c) * 8 + (k & 7)) / 2;
+                    *dst = pack_bf16(p[q].x, p[q].y);
+                }
+            }
+        }
+    }
+}
+
 int adam_linear_factored(float* p, float* m, float* v, void* shadow, float* g_out, const void* ga, const float* z,
                          int Btot, int b_per_seg, long long ga_seg_stride, long long z_seg_stride, int K, int C, int SS,
                          float gscale, float step_size, float inv_bc2_sqrt, const float* dyn, float beta1, float beta2,
@@ -236,6 +375,30 @@ int adam_linear_factored(float* p, float* m, float* v, void* shadow, float* g_ou
     AdamLinearArgs a{p, m, v, static_cast<__nv_bfloat16*>(shadow), g_out, static_cast<const uint4*>(ga), z, Btot,
                      b_per_seg, ga_seg_stride, z_seg_stride, K, C, SS, gscale, step_size, inv_bc2_sqrt, dyn, beta1,
                      beta2, eps};
+    static const bool force_fma = getenv("NGAN_LINEAR_ADAM_FMA") != nullptr;
+    const int Bpad = (Btot + 15) / 16 * 16;
+    const size_t smem = static_cast<size_t>(3) * Bpad * kLinPitch;
+    if (!force_fma && C % 128 == 0 && K % 128 == 0 && smem <= 200u * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(adam_linear_mma_kernel<true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(adam_linear_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+            if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(adam_linear_mma)");
+            configured = true;
+        }
+        if (p)
+            adam_linear_mma_kernel<true><<<dim3(SS, K / 128, C / 128), 256, smem, st>>>(a, Bpad);
+        else
+            adam_linear_mma_kernel<false><<<dim3(SS, K / 128, C / 128), 256, smem, st>>>(a, Bpad);
+        return check_launch("adam_linear_mma");
+    }
+    if (!p) {
+        set_error("adam_linear_factored: the gradient-only mode needs C %% 128 == 0, K %% 128 == 0 (got C=%d K=%d)", C, K);
+        return NGAN_ERR_UNSUPPORTED;
+    }
     const long long items = static_cast<long long>(C / 8) * SS * (K / 8);
     long long bx = (items + 255) / 256;
     if (bx > 148 * 8) bx = 148 * 8;

@@ -307,7 +307,7 @@ int ngan_adam_linear_factored(float* p, float* m, float* v, void* shadow_img, fl
                               const float* z, int Btot, int b_per_seg, long long ga_seg_stride, long long z_seg_stride,
                               int K, int C, int Sz, float gscale, float step_size, float inv_bc2_sqrt,
                               const float* dyn, float beta1, float beta2, float eps, void* stream) {
-    NGAN_REQUIRE(p && m && v && ga_c8 && z, "adam_linear_factored: null pointer");
+    NGAN_REQUIRE(ga_c8 && z && ((p && m && v) || (!p && g_out)), "adam_linear_factored: null pointer");
     return adam_linear_factored(p, m, v, shadow_img, g_out, ga_c8, z, Btot, b_per_seg, ga_seg_stride, z_seg_stride, K,
                                 C, Sz * Sz, gscale, step_size, inv_bc2_sqrt, dyn, beta1, beta2, eps, S(stream));
 }

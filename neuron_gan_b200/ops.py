@@ -490,6 +490,14 @@ def adam_linear_factored(p, m, v, shadow, ga, z, K, C, S, gscale, step_size, inv
               _p(dyn, F32), beta1, beta2, eps, _stream())
 
 
+def linear_wgrad_factored(ga, z, K, C, S, gscale, dw, b_per_seg, n_seg=1, ga_seg_stride=0, z_seg_stride=0):
+    """dW = gscale * ga^T z over all samples of an (all-gathered) global batch, on tensor cores (z = hi + lo in bf16):
+    the gradient-only mode of ngan_adam_linear_factored.  Overwrites dw."""
+    _lib.call('ngan_adam_linear_factored', None, None, None, None, _p(dw, F32), ctypes.c_void_p(ga.data_ptr()),
+              ctypes.c_void_p(z.data_ptr()), b_per_seg * n_seg, b_per_seg, int(ga_seg_stride), int(z_seg_stride), K, C,
+              S, float(gscale), 0.0, 0.0, None, 0.0, 0.0, 0.0, _stream())
+
+
 # ------------------------------------------------------------------------------------------ image pipeline
 def augment_batch(canvases, src_index, params, tap_first, tap_count, tap_weight, out, crop, workspace=None):
     """canvases [N, P, P] f32, src_index [b] i32, params [b, 16] f32, taps for crop -> R, out [b, 1, R, R] f32

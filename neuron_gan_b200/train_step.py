@@ -45,10 +45,15 @@ class TrainStep:
         self.segment_graphs = False     # capture three graphs even on one GPU (lets a caller time the three parts)
         self.segment_events = None      # when a list: 4 CUDA events per replayed iteration are appended (start, D, G, end)
         self.global_draws = True        # data parallel: draw the global batch on every rank and keep this rank's rows
-        self.factor_linear = True       # hand the Linear weight's gradient to Adam as its two factors (never materialised;
-                                        # with data parallelism the ranks all-gather 1 MB of factors instead of
-                                        # all-reducing the 67 MB product)
-        self.materialize_linear_grad = False   # with factor_linear: also write lin.weight.grad (plot_grad_norm wants it)
+        # The generator's Linear weight is 98 % of its parameters and its gradient a rank-B product ga0^T z.
+        # factor_linear: keep the gradient as its two factors after the backward pass.  With data parallelism the
+        # ranks then all-gather 1 MB of factors instead of all-reducing the 67 MB product, and form the global
+        # gradient locally on tensor cores (ops.linear_wgrad_factored).  fuse_linear_adam: form it inside the Adam pass
+        # and never write it (ops.adam_linear_factored; lin.weight.grad then stays unmaterialised unless
+        # materialize_linear_grad) -- measured 2 % slower than the separate kernels on one GPU, so off by default.
+        self.factor_linear = True
+        self.fuse_linear_adam = False
+        self.materialize_linear_grad = False
         self.fork_chains = True         # run the two independent halves of the critic step on two streams
         self._chain_stream = None
         self._comm_stream = None        # data parallel: the critic's gradient all-reduce overlaps the generator forward
@@ -254,13 +259,18 @@ class TrainStep:
             lin, f = self.G.layers[0], buf.out.lin
             K, C, S = lin._ngan_dims
             world = dist.get_world_size() if self.dp else 1
-            d = dict(K=K, C=C, S=S, gscale=f.scale / world, b_per_seg=buf.B, n_seg=world,
-                     g_out=self._bound[id(self.G)]['sinks'][0][id(lin.weight)] if self.materialize_linear_grad else None)
+            dw = self._bound[id(self.G)]['sinks'][0][id(lin.weight)]
+            d = dict(K=K, C=C, S=S, gscale=f.scale / world, b_per_seg=buf.B, n_seg=world)
             if self.dp:
                 d.update(ga=buf.pack.recv_ga, z=buf.pack.recv_z, ga_seg_stride=buf.pack.per, z_seg_stride=buf.pack.per)
             else:
                 d.update(ga=f.ga0, z=f.z)
-            factored = {id(lin.weight): d}
+            if self.fuse_linear_adam:
+                d['g_out'] = dw if self.materialize_linear_grad else None
+                factored = {id(lin.weight): d}
+            else:
+                ops.linear_wgrad_factored(d['ga'], d['z'], K, C, S, d['gscale'], dw, buf.B, world,
+                                          d.get('ga_seg_stride', 0), d.get('z_seg_stride', 0))
         self.opt_g.launch(factored=factored)
         stats = torch.empty(5, dtype=F32, device=buf.z3.device)
         ops.pack_stats(buf.out.out3, buf.out.out1, buf.out.pen, stats)
@@ -340,7 +350,7 @@ class TrainStep:
         # alpha itself is NOT part of the key: the kernels read it from device memory (_sync_alpha), so one graph
         # serves every epoch of a fade-in; only whether a fade is in progress changes the kernel sequence
         return (B, R, self.G.alpha_value() < 1, self.D.alpha_value() < 1, self.G.N_layers, self.D.N_layers, self.dp,
-                self.lam, self.drift, self.factor_linear, self.materialize_linear_grad,
+                self.lam, self.drift, self.factor_linear, self.fuse_linear_adam, self.materialize_linear_grad,
                 tuple(id(p) for p in self.G.active_parameters()), tuple(id(p) for p in self.D.active_parameters()))
 
     def _capture(self, key, B, R, dev):

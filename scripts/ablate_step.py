@@ -55,6 +55,15 @@ def noop(name, ret=None):
 
 
 base = measure('baseline')
+measure('four graphs (segment_graphs)', segment_graphs=True)
+for ns in (2, 4, 6):
+    def setn(n=ns):
+        engine._Side.n_streams = n; engine._Side.streams = []
+    def unsetn():
+        engine._Side.n_streams = 3; engine._Side.streams = []
+    measure(f'{ns} wgrad side streams', setn, unsetn)
+measure('factored linear grad + plain Adam', factor_linear=True)
+measure('factored linear grad fused into Adam', factor_linear=True, fuse_linear_adam=True)
 p, u = noop('conv3x3_wgrad')
 measure('no conv3x3_wgrad', p, u)
 side = engine._Side.enabled

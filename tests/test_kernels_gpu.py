@@ -305,6 +305,58 @@ def test_linear(B):
     assert rel(dw, s * ga.flatten(1).t() @ z) < 1e-4
 
 
+@pytest.mark.parametrize('B,n_seg', [(3, 1), (16, 1), (64, 1), (16, 8), (5, 2)])
+def test_adam_linear_factored(B, n_seg):
+    """ops.adam_linear_factored (gradient of the Linear weight formed from its factors inside the Adam pass, tensor
+    cores, z = hi + lo) against linear_wgrad + torch.optim.Adam on the materialised gradient; samples in per-rank
+    segments of an all-gathered buffer (n_seg > 1) give the same result as one contiguous batch."""
+    o = ops()
+    C, S, K = 128, 16, 512
+    torch.manual_seed(B * 10 + n_seg)
+    p0 = torch.randn(C * S * S, K, device='cuda') * 0.05
+    Bt = B * n_seg
+    ga = rnd(Bt, C, S, S, seed=27, scale=0.01)
+    z = torch.randn(Bt, K, device='cuda')
+    z = z / z.norm(dim=1, keepdim=True)
+    s = GAIN / math.sqrt(K) / n_seg
+    g_ref = torch.zeros_like(p0)
+    o.linear_wgrad(o.nchw_to_c8(ga), z, s, g_ref, accumulate=False)
+    assert rel(g_ref, s * ga.flatten(1).t() @ z) < 1e-4
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.5, 0.999))
+    own = torch.nn.Parameter(p0.clone())
+    opt_own = torch.optim.Adam([own], lr=1e-3, betas=(0.5, 0.999))
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    img = torch.zeros(p.numel(), dtype=torch.bfloat16, device='cuda')
+    g_out = torch.empty_like(p0)
+    # the factors as an all-gathered buffer: n_seg segments [ga rows | z rows], with padding between the segments
+    ga_c8 = o.nchw_to_c8(ga)
+    n_ga, n_z = B * C * S * S, B * K
+    per = n_ga * 2 + n_z * 4 + 64
+    buf = torch.zeros((n_seg, per), dtype=torch.uint8, device='cuda')
+    buf_ga = buf[:, :n_ga * 2].view(torch.bfloat16)
+    buf_z = buf[:, n_ga * 2:n_ga * 2 + n_z * 4].view(torch.float32)
+    for r in range(n_seg):
+        buf_ga[r].copy_(ga_c8[r * B:(r + 1) * B].reshape(-1))
+        buf_z[r].copy_(z[r * B:(r + 1) * B].reshape(-1))
+    for step in range(1, 3):
+        ref.grad = g_ref.clone()
+        opt.step()
+        o.adam_linear_factored(p, m, v, img, buf_ga, buf_z, K, C, S, s, 1e-3 / (1 - 0.5 ** step),
+                               1 / math.sqrt(1 - 0.999 ** step), None, 0.5, 0.999, 1e-8, b_per_seg=B,
+                               ga_seg_stride=per, z_seg_stride=per, n_seg=n_seg, g_out=g_out)
+        assert rel(g_out, g_ref) < 1e-4
+        # the moments are linear / quadratic in g: close to torch's; the parameter itself is sign-like in g at the first
+        # steps (a ~0 gradient element may move by 2*lr either way), so it is checked against torch.optim.Adam fed
+        # with the gradient this kernel formed
+        st = opt.state[ref]
+        assert rel(m, st['exp_avg']) < 1e-4 and rel(v, st['exp_avg_sq']) < 2e-4
+        own.grad = g_out.clone()
+        opt_own.step()
+        assert torch.allclose(p, own.data, rtol=1e-5, atol=1e-6)
+        assert torch.equal(img, o.prep_linear_weight(p, C, S))
+
+
 def test_losses():
     o = ops()
     B = 16
