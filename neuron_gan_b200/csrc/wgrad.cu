@@ -71,8 +71,10 @@ static bool wgrad_plan(int B, int cin, int cout, int H, int W, WgradPlan* p) {
     if (8 % p->n_blk) return false;
     p->n_ci_groups = cin / p->ci_g;
     p->n_groups = p->n_ci_groups * (cout / p->co_g);
+    static const int tw_env = getenv("NGAN_WGRAD_TW") ? atoi(getenv("NGAN_WGRAD_TW")) : 0;    // tuning experiments
     p->TW = W < 64 ? W : 64;
     if (p->ci_g >= 64 && p->TW > 32) p->TW = 32;
+    if (tw_env && p->TW > tw_env) p->TW = tw_env;
     p->tiles_x = W / p->TW;
     p->tiles_y = H / kWgTH;
     p->n_tiles = p->tiles_x * p->tiles_y * B;
@@ -80,8 +82,8 @@ static bool wgrad_plan(int B, int cin, int cout, int H, int W, WgradPlan* p) {
     p->rb = p->n_blk == 1 ? 4 : 8;
     // CTAs along the pixel dimension: one resident wave (148 CTAs over all channel groups) up to a few tiles per
     // CTA, two CTAs per SM beyond that (measured in round 1, graph-timed).  Every pixel CTA (or cluster) ends with one
-    // partial image of its group's blocks, so low-resolution launches -- few pixels, up to 590 KB of gradient --
-    // first add the partials of 4 neighbouring CTAs through distributed shared memory (in rank order).
+    // partial image of its group's blocks.  NGAN_WGRAD_CLUSTER=2|4|8 first adds the partials of neighbouring CTAs
+    // through distributed shared memory (in rank order); measured slower than plain partial images, off by default.
     static const int target_env = getenv("NGAN_WGRAD_CTAS") ? atoi(getenv("NGAN_WGRAD_CTAS")) : 0;
     const long long work = static_cast<long long>(p->n_tiles) * p->n_groups;
     const int target = target_env ? target_env : (work >= 4LL * 148 ? 2 * 148 : 148);
@@ -89,7 +91,9 @@ static bool wgrad_plan(int B, int cin, int cout, int H, int W, WgradPlan* p) {
     if (per_group > p->n_tiles) per_group = p->n_tiles;
     if (per_group < 1) per_group = 1;
     static const int cluster_env = getenv("NGAN_WGRAD_CLUSTER") ? atoi(getenv("NGAN_WGRAD_CLUSTER")) : -1;
-    const int cluster_max = cluster_env >= 0 ? cluster_env : (H <= 32 ? 4 : 1);
+    // (round 1 clustered the 16x16 / 32x32 layers to save global atomics; with partial images and plain stores the
+    // cluster's co-scheduling constraint only costs: 128->64 @32x32 24.7 us alone vs 31.6 us in clusters of 4)
+    const int cluster_max = cluster_env >= 0 ? cluster_env : 1;
     int cs = 1;
     while (cs * 2 <= cluster_max && cs * 2 <= 8 && cs * 2 <= per_group) cs *= 2;
     per_group = per_group / cs * cs;
