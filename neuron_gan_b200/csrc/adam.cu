@@ -259,38 +259,8 @@ __global__ void __launch_bounds__(256, 2) adam_linear_mma_kernel(const AdamLinea
     const int px = blockIdx.x, k0 = blockIdx.y * 128, c0 = blockIdx.z * 128;
     const int NCH = a.C >> 3, KG = a.K >> 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // ---- stage the factors: 16 granules of ga and 128 latents (as hi / lo bf16) per sample; pad rows are zero
-    for (int i = threadIdx.x; i < Bpad * 16; i += blockDim.x) {
-        const int b = i >> 4, jj = i & 15;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (b < a.Btot) {
-            const int seg = b / a.b_per_seg, row = b - seg * a.b_per_seg;
-            v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(a.ga) + seg * a.ga_seg_stride) +
-                      (static_cast<size_t>(row) * NCH + (c0 >> 3) + jj) * a.SS + px);
-        }
-        *reinterpret_cast<uint4*>(s_ga + b * kLinPitch + jj * 16) = v;
-    }
-    for (int i = threadIdx.x; i < Bpad * 32; i += blockDim.x) {
-        const int b = i >> 5, q = i & 31;                       // q: float4 index inside the 128-k slice
-        float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b < a.Btot) {
-            const int seg = b / a.b_per_seg, row = b - seg * a.b_per_seg;
-            zv = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(a.z) + seg * a.z_seg_stride +
-                                                       static_cast<size_t>(row) * a.K * sizeof(float)) + (k0 >> 2) + q);
-        }
-        const float f[4] = {zv.x, zv.y, zv.z, zv.w};
-        uint32_t hi[2], lo[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const __nv_bfloat16 h0 = __float2bfloat16(f[2 * h]), h1 = __float2bfloat16(f[2 * h + 1]);
-            hi[h] = pack_bf16(__bfloat162float(h0), __bfloat162float(h1));
-            lo[h] = pack_bf16(f[2 * h] - __bfloat162float(h0), f[2 * h + 1] - __bfloat162float(h1));
-        }
-        *reinterpret_cast<uint2*>(s_zh + b * kLinPitch + q * 8) = make_uint2(hi[0], hi[1]);
-        *reinterpret_cast<uint2*>(s_zl + b * kLinPitch + q * 8) = make_uint2(lo[0], lo[1]);
-    }
-    __syncthreads();
-    // ---- g tile = ga^T z: M = 16 channels of this warp, N = 128 k (16 n-tiles), K = samples
+    // ---- g tile = ga^T z: M = 16 channels of this warp, N = 128 k (16 n-tiles), K = samples, in chunks of Bpad <= 64
+    // samples staged at a time (bounded shared memory for any global batch)
     float acc[16][4];
 #pragma unroll
     for (int nt = 0; nt < 16; ++nt)
@@ -300,18 +270,52 @@ __global__ void __launch_bounds__(256, 2) adam_linear_mma_kernel(const AdamLinea
     const uint32_t a_lane = smem_u32(s_ga) + ((mi >> 1) * 8 + ri) * kLinPitch + (warp * 2 + (mi & 1)) * 16;
     const uint32_t bh_lane = smem_u32(s_zh) + ((mi & 1) * 8 + ri) * kLinPitch + (mi >> 1) * 16;
     const uint32_t bl_lane = smem_u32(s_zl) + ((mi & 1) * 8 + ri) * kLinPitch + (mi >> 1) * 16;
-    for (int b0 = 0; b0 < Bpad; b0 += 16) {
-        uint32_t af[4];
-        ldsm_x4_trans(a_lane + b0 * kLinPitch, af);
+    for (int base = 0; base < a.Btot; base += Bpad) {
+        if (base) __syncthreads();                              // everyone is done reading the previous chunk
+        // stage the factors: 16 granules of ga and 128 latents (as hi / lo bf16) per sample; rows past Btot are zero
+        for (int i = threadIdx.x; i < Bpad * 16; i += blockDim.x) {
+            const int r = i >> 4, jj = i & 15, b = base + r;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (b < a.Btot) {
+                const int seg = b / a.b_per_seg, row = b - seg * a.b_per_seg;
+                v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(a.ga) + seg * a.ga_seg_stride) +
+                          (static_cast<size_t>(row) * NCH + (c0 >> 3) + jj) * a.SS + px);
+            }
+            *reinterpret_cast<uint4*>(s_ga + r * kLinPitch + jj * 16) = v;
+        }
+        for (int i = threadIdx.x; i < Bpad * 32; i += blockDim.x) {
+            const int r = i >> 5, q = i & 31, b = base + r;     // q: float4 index inside the 128-k slice
+            float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b < a.Btot) {
+                const int seg = b / a.b_per_seg, row = b - seg * a.b_per_seg;
+                zv = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(a.z) + seg * a.z_seg_stride +
+                                                           static_cast<size_t>(row) * a.K * sizeof(float)) + (k0 >> 2) + q);
+            }
+            const float f[4] = {zv.x, zv.y, zv.z, zv.w};
+            uint32_t hi[2], lo[2];
 #pragma unroll
-        for (int np = 0; np < 8; ++np) {                        // pairs of n-tiles
-            uint32_t bh[4], bl[4];
-            ldsm_x4_trans(bh_lane + b0 * kLinPitch + np * 32, bh);
-            ldsm_x4_trans(bl_lane + b0 * kLinPitch + np * 32, bl);
-            mma16816(acc[2 * np], af, bh[0], bh[1]);
-            mma16816(acc[2 * np + 1], af, bh[2], bh[3]);
-            mma16816(acc[2 * np], af, bl[0], bl[1]);
-            mma16816(acc[2 * np + 1], af, bl[2], bl[3]);
+            for (int h = 0; h < 2; ++h) {
+                const __nv_bfloat16 h0 = __float2bfloat16(f[2 * h]), h1 = __float2bfloat16(f[2 * h + 1]);
+                hi[h] = pack_bf16(__bfloat162float(h0), __bfloat162float(h1));
+                lo[h] = pack_bf16(f[2 * h] - __bfloat162float(h0), f[2 * h + 1] - __bfloat162float(h1));
+            }
+            *reinterpret_cast<uint2*>(s_zh + r * kLinPitch + q * 8) = make_uint2(hi[0], hi[1]);
+            *reinterpret_cast<uint2*>(s_zl + r * kLinPitch + q * 8) = make_uint2(lo[0], lo[1]);
+        }
+        __syncthreads();
+        for (int b0 = 0; b0 < Bpad; b0 += 16) {
+            uint32_t af[4];
+            ldsm_x4_trans(a_lane + b0 * kLinPitch, af);
+#pragma unroll
+            for (int np = 0; np < 8; ++np) {                    // pairs of n-tiles
+                uint32_t bh[4], bl[4];
+                ldsm_x4_trans(bh_lane + b0 * kLinPitch + np * 32, bh);
+                ldsm_x4_trans(bl_lane + b0 * kLinPitch + np * 32, bl);
+                mma16816(acc[2 * np], af, bh[0], bh[1]);
+                mma16816(acc[2 * np + 1], af, bh[2], bh[3]);
+                mma16816(acc[2 * np], af, bl[0], bl[1]);
+                mma16816(acc[2 * np + 1], af, bl[2], bl[3]);
+            }
         }
     }
     // ---- Adam straight from the accumulator fragments: c[0..1] = (channel g, k 2t..2t+1), c[2..3] = (channel g + 8, same k)
@@ -376,9 +380,10 @@ int adam_linear_factored(float* p, float* m, float* v, void* shadow, float* g_ou
                      b_per_seg, ga_seg_stride, z_seg_stride, K, C, SS, gscale, step_size, inv_bc2_sqrt, dyn, beta1,
                      beta2, eps};
     static const bool force_fma = getenv("NGAN_LINEAR_ADAM_FMA") != nullptr;
-    const int Bpad = (Btot + 15) / 16 * 16;
+    int Bpad = (Btot + 15) / 16 * 16;          // samples staged per pass: the whole batch up to 64, else chunks of 64
+    if (Bpad > 64) Bpad = 64;
     const size_t smem = static_cast<size_t>(3) * Bpad * kLinPitch;
-    if (!force_fma && C % 128 == 0 && K % 128 == 0 && smem <= 200u * 1024) {
+    if (!force_fma && C % 128 == 0 && K % 128 == 0) {
         static bool configured = false;
         if (!configured) {
             cudaError_t e = cudaFuncSetAttribute(adam_linear_mma_kernel<true>,

@@ -305,7 +305,7 @@ def test_linear(B):
     assert rel(dw, s * ga.flatten(1).t() @ z) < 1e-4
 
 
-@pytest.mark.parametrize('B,n_seg', [(3, 1), (16, 1), (64, 1), (16, 8), (5, 2)])
+@pytest.mark.parametrize('B,n_seg', [(3, 1), (16, 1), (64, 1), (16, 8), (5, 2), (64, 4), (70, 1)])
 def test_adam_linear_factored(B, n_seg):
     """ops.adam_linear_factored (gradient of the Linear weight formed from its factors inside the Adam pass, tensor
     cores, z = hi + lo) against linear_wgrad + torch.optim.Adam on the materialised gradient; samples in per-rank
