@@ -511,11 +511,12 @@ def run_b200(args):
         if big:
             b = max(big, key=lambda r: r['frac'])
             traffic = None
-            try:
-                tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
-                traffic = tr.get(f'{b["kernel"]}|{"x".join(map(str, b["dims"]))}')
-            except Exception:  # noqa: BLE001
-                pass
+            for f in ('r02_traffic.json', 'r01_traffic.json'):      # ncu --set full captures, per launch
+                try:
+                    tr = json.load(open(os.path.join(ROOT, 'profiles', f)))
+                    traffic = traffic or tr.get(f'{b["kernel"]}|{"x".join(map(str, b["dims"]))}')
+                except Exception:  # noqa: BLE001
+                    pass
             fl = conv_flops(b['kernel'], b['dims'])
             roofline['best_launch'] = {'kernel': b['kernel'], 'dims': b['dims'], 'avg_launch_us': b['us'],
                                        'achieved': b['GBps'], 'frac': b['frac'], 'traffic': traffic,

@@ -31,6 +31,7 @@ import torch.distributed as dist
 
 from . import dp
 from .data import DatasetIterator, NeuronImages
+from .loss_functions import similarity_loss
 from .train_step import TrainStep, build_networks
 from .utils import Calculate_D_steps, Checkpointer, plot_gen_samples
 
@@ -52,6 +53,8 @@ class TrainConfig:
     N_epochs_session: int = None
     beta1: float = 0.5
     drift_epsilon: float = 0.001
+    sim_loss_lambda: float = 0.0
+    sim_loss_lambda_decay_rate: float = 0.0
     seed: int = 1
     checkpointing_period: int = 100
     translation: float = 0.05
@@ -131,6 +134,7 @@ def pggan_train(cfg: TrainConfig, images: NeuronImages, Generator_net, Discrimin
     series = {k: [] for k in names}
     history = []
     start = time.time()
+    sim_lambda = cfg.sim_loss_lambda                                                                # train.py:300
     for epoch in range(epoch_init, epoch_final):
         lr = step.opt_g.param_groups[0]['lr']
         if Generator_net.alpha < 1 and Discriminator_net.alpha < 1:                                 # train.py:318-325
@@ -148,16 +152,30 @@ def pggan_train(cfg: TrainConfig, images: NeuronImages, Generator_net, Discrimin
                                               Period=DISC_ADAPT_UPDATE_PERIOD)
         else:
             step.n_critic = cfg.n_critic
+        if cfg.sim_loss_lambda_decay_rate > 0 and sim_lambda > 0:                                   # train.py:343-348
+            sim_lambda = cfg.sim_loss_lambda * (1 - cfg.sim_loss_lambda_decay_rate) ** (epoch - 1) \
+                if sim_lambda > 1e-5 else 0
         # one device tensor accumulates batch * statistics (train.py:388-394): no host sync inside the epoch
-        acc = torch.zeros(5, dtype=torch.float64, device=device)
+        acc = torch.zeros(6, dtype=torch.float64, device=device)
         for real_images in dataloader:
             b = real_images.shape[0]
             if b == 0:
                 continue
             draws = _global_draws(step, b * world, rank, world) if world > 1 else None
-            acc += b * step(real_images, draws).double()
+            if sim_lambda > 0 and draws is None:
+                draws = step.draw_host(b)          # the similarity term needs the generator step's latents (z3)
+            acc[:5] += b * step(real_images, draws).double()
+            if sim_lambda > 0:
+                # train.py:379-381: similarity_loss(images, Z_latent, lambda) on the REAL images and the generator step's
+                # latents -- no gradient path into either network, it shifts the reported generator loss.  With data
+                # parallelism the rows are all-gathered: every rank gets the loss of the global batch.
+                z3 = draws[-1].to(device, non_blocking=True)
+                sim = similarity_loss(real_images, z3, sim_lambda).double()
+                acc[3] += b * sim
+                acc[5] += b * sim
         totals = _sum_over_ranks(acc.tolist())
         stats = {k: v / len(images) for k, v in zip(names, totals)}                                 # train.py:397-399
+        g_sim_loss = totals[5] / len(images)
         TrainStep.check_nan([stats[k] for k in names])
         if rank == 0 and epoch % 10 == 0:                                                           # train.py:402-425
             done = epoch - epoch_init
@@ -168,12 +186,13 @@ def pggan_train(cfg: TrainConfig, images: NeuronImages, Generator_net, Discrimin
                            'Loss_real (<D(x)>_x):{: >#7.4g}'.format(stats['score_real']),
                            'Loss_fake (<D(G(z))>):{: >#7.4g}'.format(stats['score_fake']),
                            'G_loss:{: >#7.4g}'.format(stats['G_loss']), 'D_loss:{: >#7.4g}'.format(stats['D_loss']),
-                           'D_grad_pen:{: >#7.4g}'.format(stats['D_grad_pen'])]))
+                           'D_grad_pen:{: >#7.4g}'.format(stats['D_grad_pen'])] +
+                          (['G_sim_loss:{: >#7.4g}'.format(g_sim_loss)] if g_sim_loss != 0 else [])))
         schedule.apply(step.opt_d, epoch)                                                           # train.py:428-429
         schedule.apply(step.opt_g, epoch)
         for k in names:
             series[k].append(stats[k])
-        history.append(dict(stats, epoch=epoch, lr=lr, alpha=float(Generator_net.alpha),
+        history.append(dict(stats, epoch=epoch, lr=lr, alpha=float(Generator_net.alpha), G_sim_loss=g_sim_loss,
                             image_size=Generator_net.image_size, n_critic=step.n_critic))
         if checkpoint is not None and rank == 0:
             checkpoint.Loss_real[epoch - 1], checkpoint.Loss_fake[epoch - 1] = stats['score_real'], stats['score_fake']

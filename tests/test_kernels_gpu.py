@@ -389,6 +389,30 @@ def test_losses():
     assert torch.isfinite(out).all() and torch.allclose(out, gz_ref, rtol=1e-4, atol=1e-8)
 
 
+@pytest.mark.parametrize('B,shape,L', [(16, (1, 64, 64), 512), (5, (1, 24, 40), 512), (64, (1, 16, 16), 512), (2, (1, 512, 512), 512)])
+def test_similarity_loss(B, shape, L):
+    """similarity_loss (reference loss_functions.py:185-205, verbatim formula below) as two kernels: per-chunk Gram
+    matrices of the images, ordered reduction + cosine matrices + squared difference."""
+    from neuron_gan_b200.loss_functions import similarity_loss
+    g = torch.Generator(device='cuda').manual_seed(B)
+    images = torch.rand(B, *shape, device='cuda', generator=g) * 2 - 1
+    Z = torch.randn(B, L, device='cuda', generator=g)
+    lam = 0.7
+    im = images.view(B, -1).double()
+    zz = Z.view(B, -1).double()
+    im = im / im.norm(2, dim=1, keepdim=True)
+    zz = zz / zz.norm(2, dim=1, keepdim=True)
+    ref = lam * torch.pow(zz @ zz.t() - im @ im.t(), 2).sum() / (B * (B - 1))
+    got = similarity_loss(images, Z, lam)
+    assert got.dim() == 0 and abs(got.item() - ref.item()) <= 1e-4 * abs(ref.item()) + 1e-7, (got.item(), ref.item())
+    assert similarity_loss(images, Z, lam).item() == got.item()                 # deterministic
+    # inputs that require grad take the differentiable route (same value)
+    zg = Z.clone().requires_grad_()
+    d = similarity_loss(images, zg, lam)
+    d.backward()
+    assert abs(d.item() - ref.item()) <= 1e-4 * abs(ref.item()) + 1e-7 and zg.grad is not None
+
+
 def test_adam_multi():
     o = ops()
     torch.manual_seed(0)

@@ -74,3 +74,28 @@ def test_command_line_entry_point():
                          cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert 'done: epoch 4, 32x32, alpha 1.000' in out.stdout, out.stdout[-500:]
+
+
+def test_similarity_loss_in_the_loop():
+    """sim_loss_lambda > 0 (train.py:300, 343-348, 379-381): the term is added to the reported generator loss, decays
+    with sim_loss_lambda_decay_rate, and -- having no gradient path into either network -- leaves the weights alone."""
+    from neuron_gan_b200 import launch
+    from neuron_gan_b200.data import NeuronImages
+    from neuron_gan_b200.train_step import build_networks
+    out = {}
+    for lam in (0.0, 2.0):
+        cfg = _small_cfg(N_epochs=3, transit_sch=[], checkpointing_period=100, sim_loss_lambda=lam,
+                         sim_loss_lambda_decay_rate=0.5 if lam else 0.0)
+        G, D = build_networks(16, 1.0, seed=1, device='cuda', gen_features=cfg.N_gen_features,
+                              dis_features=cfg.N_dis_features, image_size=cfg.image_size)
+        images = NeuronImages(launch.synthetic_images(8, cfg.image_size), cfg.image_size, True, cfg.translation)
+        torch.manual_seed(5)
+        out[lam] = (launch.pggan_train(cfg, images, G, D, log=lambda s: None), G.state_dict())
+    h0, h1 = out[0.0][0], out[2.0][0]
+    assert all(h['G_sim_loss'] == 0 for h in h0) and all(h['G_sim_loss'] > 0 for h in h1)
+    for a, b in zip(h0, h1):
+        assert b['G_loss'] == pytest.approx(a['G_loss'] + b['G_sim_loss'], abs=1e-6)
+    # lambda halves every epoch: 2, 1, 0.5 -- the term is lambda times a slowly varying quantity
+    assert h1[1]['G_sim_loss'] < 0.75 * h1[0]['G_sim_loss'] and h1[2]['G_sim_loss'] < 0.75 * h1[1]['G_sim_loss']
+    for k, v in out[0.0][1].items():
+        assert torch.equal(v, out[2.0][1][k]), k
