@@ -83,19 +83,19 @@ def test_similarity_loss_in_the_loop():
     from neuron_gan_b200.data import NeuronImages
     from neuron_gan_b200.train_step import build_networks
     out = {}
-    for lam in (0.0, 2.0):
+    for key, lam, decay in (('off', 0.0, 0.0), ('on', 2.0, 0.0), ('decay', 2.0, 0.5)):
         cfg = _small_cfg(N_epochs=3, transit_sch=[], checkpointing_period=100, sim_loss_lambda=lam,
-                         sim_loss_lambda_decay_rate=0.5 if lam else 0.0)
+                         sim_loss_lambda_decay_rate=decay)
         G, D = build_networks(16, 1.0, seed=1, device='cuda', gen_features=cfg.N_gen_features,
                               dis_features=cfg.N_dis_features, image_size=cfg.image_size)
         images = NeuronImages(launch.synthetic_images(8, cfg.image_size), cfg.image_size, True, cfg.translation)
         torch.manual_seed(5)
-        out[lam] = (launch.pggan_train(cfg, images, G, D, log=lambda s: None), G.state_dict())
-    h0, h1 = out[0.0][0], out[2.0][0]
+        out[key] = (launch.pggan_train(cfg, images, G, D, log=lambda s: None), G.state_dict())
+    h0, h1, h2 = out['off'][0], out['on'][0], out['decay'][0]
     assert all(h['G_sim_loss'] == 0 for h in h0) and all(h['G_sim_loss'] > 0 for h in h1)
-    for a, b in zip(h0, h1):
+    for e, (a, b, c) in enumerate(zip(h0, h1, h2)):
         assert b['G_loss'] == pytest.approx(a['G_loss'] + b['G_sim_loss'], abs=1e-6)
-    # lambda halves every epoch: 2, 1, 0.5 -- the term is lambda times a slowly varying quantity
-    assert h1[1]['G_sim_loss'] < 0.75 * h1[0]['G_sim_loss'] and h1[2]['G_sim_loss'] < 0.75 * h1[1]['G_sim_loss']
-    for k, v in out[0.0][1].items():
-        assert torch.equal(v, out[2.0][1][k]), k
+        # lambda = 2 * (1 - 0.5)^(epoch - 1): the same images and latents, so the term scales exactly with lambda
+        assert c['G_sim_loss'] == pytest.approx(b['G_sim_loss'] * 0.5 ** e, rel=1e-5)
+    for k, v in out['off'][1].items():      # no gradient path: the weights do not notice the term
+        assert torch.equal(v, out['on'][1][k]), k
