@@ -62,7 +62,7 @@ constexpr bool kDebug = false;
 #endif
 constexpr int kFoldMaxStages = 12;
 constexpr int kFoldMaxAcc = 8;            // accumulator buffers in TMEM (ring between MMA issuers and epilogue)
-constexpr uint32_t kFoldBarBytes = (1 + 2 * kFoldMaxStages + 2 * kFoldMaxAcc) * 8 + 16;
+constexpr uint32_t kFoldBarBytes = (1 + 2 * kFoldMaxStages + 2 * kFoldMaxAcc) * 8 + 16 + 16 + 64 * 4;   // + ToImage weights
 
 // tile -> (sample, tile row, tile column) without integer division: (n + 0.5) * (1/d) truncated is exact for
 // n*d < ~4e6, far above any tile count here (a 512x512 batch of 128 has 73728 tiles)
@@ -75,7 +75,8 @@ __device__ __forceinline__ void tile_coords(const ConvArgs& a, int tile, int& b,
 
 // Fused pointwise tail on one output pixel held in registers (o[c] = raw accumulator sums).
 template <int COUT, int EPI>
-__device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool valid, size_t q0, size_t p0, size_t HW) {
+__device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool valid, size_t q0, size_t p0, size_t HW,
+                                          const float* s_tw) {
     constexpr int NCH = COUT / 8;
     const float inv_c = 1.0f / COUT;
     if constexpr (EPI == EPI_FWD_PN) {
@@ -113,9 +114,18 @@ __device__ __forceinline__ void conv_tail(const ConvArgs& a, float* o, bool vali
         if (valid) {
             if (a.img_out) {
                 // fused ToImage (models.py:141-149): plain 1x1 conv to one channel + tanh on the normalised activation
+                // (weights from shared memory as four-float loads: 16 scalar __ldg per pixel cost the issue-bound
+                // epilogue more than the y store this variant saves)
                 float dot = 0.f;
+                const float4* tw4 = reinterpret_cast<const float4*>(s_tw);
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) dot = fmaf(__ldg(a.toim_w + c), o[c], dot);
+                for (int c = 0; c < COUT / 4; ++c) {
+                    const float4 w = tw4[c];
+                    dot = fmaf(w.x, o[4 * c], dot);
+                    dot = fmaf(w.y, o[4 * c + 1], dot);
+                    dot = fmaf(w.z, o[4 * c + 2], dot);
+                    dot = fmaf(w.w, o[4 * c + 3], dot);
+                }
                 const float im = tanhf(k * dot);
                 if (a.img_bf16) reinterpret_cast<__nv_bfloat16*>(a.img_out)[p0] = __float2bfloat16(im);
                 else a.img_out[p0] = im;
@@ -283,6 +293,7 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
     uint64_t* bar_acc_full = bars + 1 + 2 * kFoldMaxStages;        // [n_acc <= kFoldMaxAcc]
     uint64_t* bar_acc_empty = bar_acc_full + kFoldMaxAcc;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + kFoldMaxAcc);
+    float* s_tw = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
     // warp index through a shuffle: tells the compiler it is warp-uniform, so everything derived from it (tile
     // counters, descriptors) stays in uniform registers and the UTCHMMA / UTMALDG issue needs no per-lane loop
@@ -310,6 +321,12 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     pdl_wait();        // everything above overlapped the previous kernel's tail; its results are needed from here on
+    if constexpr (EPI == EPI_FWD_PN) {
+        if (a.img_out) {       // fused ToImage: its COUT weights, once per CTA
+            if (threadIdx.x < COUT) s_tw[threadIdx.x] = __ldg(a.toim_w + threadIdx.x);
+            __syncthreads();
+        }
+    }
 
     if (warp == 0) {
         if (lane == 0) {
@@ -459,7 +476,7 @@ __global__ void __launch_bounds__(FoldCfg<COUT, EPI>::kThreads) conv3x3_fold_ker
                 }
                 const size_t q0 = static_cast<size_t>(b) * (COUT / 8) * HW + static_cast<size_t>(oy) * a.W + ox;
                 const size_t p0 = static_cast<size_t>(b) * HW + static_cast<size_t>(oy) * a.W + ox;
-                conv_tail<COUT, EPI>(a, o, valid, q0, p0, HW);
+                conv_tail<COUT, EPI>(a, o, valid, q0, p0, HW, s_tw);
             }
             if (!released) acc_release(bar_acc_empty + buf);     // (or no M-tile of this tile fell to this group)
             if (trace) a.dbg_clock[it * 8 + 7] = clock64();

@@ -50,7 +50,8 @@ __device__ __forceinline__ void warp_store8(const float* v, float* row8, int lan
 template <int OPB>
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int n_partials,
                                                               long long n, long long ld, float scale,
-                                                              float* __restrict__ out, int accumulate) {
+                                                              float* __restrict__ out, int accumulate,
+                                                              float* __restrict__ out2, long long n_split) {
     pdl_trigger();
     pdl_wait();           // launched right behind the kernel that writes the partials
     constexpr int S = 256 / OPB;
@@ -78,23 +79,24 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 #pragma unroll
         for (int k = 0; k < S; ++k) t += red[k][o];
         t *= scale;
-        out[i] = accumulate ? out[i] + t : t;
+        float* dst = (out2 && i >= n_split) ? out2 + (i - n_split) : out + i;      // a row may feed two tensors
+        *dst = accumulate ? *dst + t : t;
     }
 }
 int reduce_partials(const float* partials, int n_partials, long long n, long long ld, float scale, float* out,
-                    int accumulate, cudaStream_t st) {
+                    int accumulate, cudaStream_t st, float* out2, long long n_split) {
     // outputs per block: wide results with few partial rows take 64 (coalesced 256-byte rows, 4 slices); many partial
     // rows are split over 16 or 32 slices so that no thread walks more than a few dozen rows
     cudaError_t e;
     if (n >= 2048 && n_partials <= 32)
         e = launch_pdl(reduce_partials_kernel<64>, dim3(static_cast<unsigned>((n + 63) / 64)), dim3(256), 0, st,
-                       partials, n_partials, n, ld, scale, out, accumulate);
+                       partials, n_partials, n, ld, scale, out, accumulate, out2, n_split);
     else if (n >= 2048)
         e = launch_pdl(reduce_partials_kernel<16>, dim3(static_cast<unsigned>((n + 15) / 16)), dim3(256), 0, st,
-                       partials, n_partials, n, ld, scale, out, accumulate);
+                       partials, n_partials, n, ld, scale, out, accumulate, out2, n_split);
     else
         e = launch_pdl(reduce_partials_kernel<8>, dim3(static_cast<unsigned>((n + 7) / 8)), dim3(256), 0, st, partials,
-                       n_partials, n, ld, scale, out, accumulate);
+                       n_partials, n, ld, scale, out, accumulate, out2, n_split);
     if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(reduce_partials)");
     return check_launch("reduce_partials");
 }
@@ -368,6 +370,9 @@ int pn_bwd_c8(const void* g, int unpool, float gscale, const float* dyn, const v
 // One thread per (pixel, 8-channel group); the NCH threads of a pixel are adjacent lanes and combine their partial
 // sums of mean_c(g*y) with xor-shuffles.  (One thread per pixel looping over the groups left the 128-channel,
 // 16x16 launches of the generator's backward with 32 CTAs of serial 256-load threads: 49 us for 1 MB.)
+// (A shared-memory-tiled variant -- the block stages the haloed high-resolution tile once instead of every pixel
+// reading its 4 x 4 window through L1/L2 -- was measured in round 2: 74.6 us against 63.6 us at 512 -> 256; the
+// windows of a warp already overlap in L1.)
 template <int NCH>
 __global__ void __launch_bounds__(128) up2_bwd_pn_bwd_kernel(const uint4* __restrict__ g_up, const uint4* __restrict__ y,
                                                              const float* __restrict__ r,
@@ -665,29 +670,43 @@ __global__ void __launch_bounds__(128) fromim_bwd_kernel(const uint4* __restrict
     }
     const size_t stride = static_cast<size_t>(gridDim.x) * PL;
     const size_t n_iter = (total + stride - 1) / stride;        // the same trip count for every thread (shuffles inside)
-    for (size_t k = 0; k < n_iter; ++k) {
-        const size_t i = k * stride + static_cast<size_t>(blockIdx.x) * PL + pl;
-        const bool ok = i < total;
-        const size_t ii = ok ? i : 0;
-        int px, py;
-        size_t b;
-        split_xyb(ii, W, H, px, py, b);
-        const size_t gq = unpool ? (b * NCH + j) * gHW + static_cast<size_t>(py >> 1) * (W >> 1) + (px >> 1)
-                                 : (b * NCH + j) * HW + static_cast<size_t>(py) * W + px;
-        float gv[8];
-        unpack8(ok ? __ldg(g + gq) : make_uint4(0, 0, 0, 0), gv);
-        const float xv = ok ? __ldg(xp + ii) : 0.f;
-        float im = 0.f;
+    constexpr int U = 4;                                        // pixels in flight per thread: all loads of a batch are
+    for (size_t k0 = 0; k0 < n_iter; k0 += U) {                 // issued before the first use (the loop ran at load latency)
+        uint4 gq4[U];
+        float xv4[U];
+        size_t ii4[U];
+        bool ok4[U];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float G = gscale * gv[e];
-            sw[e] = fmaf(G, xv, sw[e]);
-            sb[e] += G;
-            im = fmaf(wj[e], G, im);
+        for (int u = 0; u < U; ++u) {
+            const size_t i = (k0 + u) * stride + static_cast<size_t>(blockIdx.x) * PL + pl;
+            ok4[u] = (k0 + u) < n_iter && i < total;
+            ii4[u] = ok4[u] ? i : 0;
+            int px, py;
+            size_t b;
+            split_xyb(ii4[u], W, H, px, py, b);
+            const size_t gq = unpool ? (b * NCH + j) * gHW + static_cast<size_t>(py >> 1) * (W >> 1) + (px >> 1)
+                                     : (b * NCH + j) * HW + static_cast<size_t>(py) * W + px;
+            gq4[u] = ok4[u] ? __ldg(g + gq) : make_uint4(0, 0, 0, 0);
+            xv4[u] = ok4[u] ? __ldg(xp + ii4[u]) : 0.f;
         }
 #pragma unroll
-        for (int o = 1; o < NCH; o <<= 1) im += __shfl_xor_sync(0xffffffffu, im, o);
-        if (g_img && ok && j == 0) g_img[ii] = (accumulate ? g_img[ii] : 0.f) + im;
+        for (int u = 0; u < U; ++u) {
+            if ((k0 + u) >= n_iter) break;                      // uniform over the block
+            float gv[8];
+            unpack8(gq4[u], gv);
+            const float xv = xv4[u];
+            float im = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float G = gscale * gv[e];
+                sw[e] = fmaf(G, xv, sw[e]);
+                sb[e] += G;
+                im = fmaf(wj[e], G, im);
+            }
+#pragma unroll
+            for (int o = 1; o < NCH; o <<= 1) im += __shfl_xor_sync(0xffffffffu, im, o);
+            if (g_img && ok4[u] && j == 0) g_img[ii4[u]] = (accumulate ? g_img[ii4[u]] : 0.f) + im;
+        }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -706,7 +725,7 @@ __global__ void __launch_bounds__(128) fromim_bwd_kernel(const uint4* __restrict
 }
 static int pointwise_blocks(size_t total, int pixel_lanes) {
     size_t blocks = (total + static_cast<size_t>(pixel_lanes) * kPixPerThread - 1) / (static_cast<size_t>(pixel_lanes) * kPixPerThread);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > 148 * 8) blocks = 148 * 8;      // every block ends with one partial row for the ordered reduction
     if (blocks < 1) blocks = 1;
     return static_cast<int>(blocks);
 }
@@ -734,6 +753,7 @@ int fromim_bwd(const void* g, int unpool, float gscale, const float* dyn, const 
 #undef NGAN_FIB
     int rc = check_launch("fromim_bwd");
     if (rc || !partials) return rc;
+    if (gw && gb) return reduce_partials(partials, blocks, 2 * C, 2 * C, 1.f, gw, grad_accumulate, st, gb, C);
     if (gw) rc = reduce_partials(partials, blocks, C, 2 * C, 1.f, gw, grad_accumulate, st);
     if (!rc && gb) rc = reduce_partials(partials + C, blocks, C, 2 * C, 1.f, gb, grad_accumulate, st);
     return rc;
@@ -845,32 +865,49 @@ __global__ void __launch_bounds__(128) toim_bwd_kernel(const float* __restrict__
     }
     const size_t stride = static_cast<size_t>(gridDim.x) * PL;
     const size_t n_iter = (total + stride - 1) / stride;
-    for (size_t k = 0; k < n_iter; ++k) {
-        const size_t i = k * stride + static_cast<size_t>(blockIdx.x) * PL + pl;
-        const bool ok = i < total;
-        const size_t ii = ok ? i : 0;
-        size_t b, pix;
-        split_bpix(ii, HW, b, pix);
-        const size_t q = (b * NCH + j) * HW + pix;
-        const float im = __ldg(img + ii);
-        const float gpre = ok ? gscale * __ldg(g_img + ii) * (1.f - im * im) : 0.f;
-        if (gpre_out && ok && j == 0) gpre_out[ii] = gpre;
-        float yv[8], t = 0.f;
-        unpack8(__ldg(y + q), yv);
+    constexpr int U = 4;                                        // pixels in flight per thread (see fromim_bwd_kernel)
+    for (size_t k0 = 0; k0 < n_iter; k0 += U) {
+        uint4 yq4[U];
+        float im4[U], gi4[U], r4[U];
+        size_t ii4[U], q4[U];
+        bool ok4[U];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            sw[e] = fmaf(gpre, yv[e], sw[e]);
-            t = fmaf(wj[e], yv[e], t);
+        for (int u = 0; u < U; ++u) {
+            const size_t i = (k0 + u) * stride + static_cast<size_t>(blockIdx.x) * PL + pl;
+            ok4[u] = (k0 + u) < n_iter && i < total;
+            ii4[u] = ok4[u] ? i : 0;
+            size_t b, pix;
+            split_bpix(ii4[u], HW, b, pix);
+            q4[u] = (b * NCH + j) * HW + pix;
+            im4[u] = __ldg(img + ii4[u]);
+            gi4[u] = __ldg(g_img + ii4[u]);
+            yq4[u] = __ldg(y + q4[u]);
+            r4[u] = ga ? __ldg(r + ii4[u]) : 0.f;
         }
-        if (ga) {
 #pragma unroll
-            for (int o = 1; o < NCH; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            const float tp = t * gpre * (1.0f / C);
-            const float rinv = __ldg(r + ii);
-            float o8[8];
+        for (int u = 0; u < U; ++u) {
+            if ((k0 + u) >= n_iter) break;                      // uniform over the block
+            const bool ok = ok4[u];
+            const float im = im4[u];
+            const float gpre = ok ? gscale * gi4[u] * (1.f - im * im) : 0.f;
+            if (gpre_out && ok && j == 0) gpre_out[ii4[u]] = gpre;
+            float yv[8], t = 0.f;
+            unpack8(yq4[u], yv);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o8[e] = lrelu_mask(yv[e], leak) * rinv * (wj[e] * gpre - yv[e] * tp);
-            if (ok) ga[q] = pack8(o8);
+            for (int e = 0; e < 8; ++e) {
+                sw[e] = fmaf(gpre, yv[e], sw[e]);
+                t = fmaf(wj[e], yv[e], t);
+            }
+            if (ga) {
+#pragma unroll
+                for (int o = 1; o < NCH; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                const float tp = t * gpre * (1.0f / C);
+                const float rinv = r4[u];
+                float o8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o8[e] = lrelu_mask(yv[e], leak) * rinv * (wj[e] * gpre - yv[e] * tp);
+                if (ok) ga[q4[u]] = pack8(o8);
+            }
         }
     }
     if (partials) {

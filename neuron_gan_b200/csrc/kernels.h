@@ -21,7 +21,7 @@ int conv3x3_wgrad(const void* x, const void* ga, float scale, float* dw, int acc
 
 // elementwise.cu
 int reduce_partials(const float* partials, int n_partials, long long n, long long ld, float scale, float* out,
-                    int accumulate, cudaStream_t st);
+                    int accumulate, cudaStream_t st, float* out2 = nullptr, long long n_split = 0);
 int sum_slots(const float* slots, int n_slots, long long n, long long ld, float scale, float* out, cudaStream_t st);
 size_t pixel_reduction_workspace_bytes(int B, int C, int H, int W);
 int nchw_to_c8(const float* src, void* dst, int B, int C, int H, int W, cudaStream_t st);

@@ -314,7 +314,7 @@ def fromim_bwd(g, xp, w, gw, gb, gscale=1.0, unpool=False, g_img=None, accumulat
     ws = _pixel_ws(B, C, H, W, xp.device) if want else None
     _lib.call('ngan_fromim_bwd', _p(g, BF16), int(unpool), gs, dyn, _p(xp, F32), _p(w, F32), _p(gw, F32), _p(gb, F32),
               int(grad_accumulate), _p(ws, F32), _p(g_img, F32), int(accumulate), B, C, H, W, _stream(),
-              launches=1 + (gw is not None) + (gb is not None))
+              launches=1 + (1 if (gw is not None and gb is not None) else (gw is not None) + (gb is not None)))
 
 
 def fromim_dbl(ghat_xp, g, w, what, in_scale=1.0, gscale=1.0, unpool=False, want_out=True, grad_accumulate=True):
