@@ -129,7 +129,9 @@ def mark_updated(param, shadow_is_fresh=False):
 # ---------------------------------------------------------------------------------------------------------
 class _Side:
     streams = []       # torch.cuda.Stream pool, created on first use
-    n_streams = 3      # the low-resolution wgrads are latency-bound on a few dozen CTAs: several run side by side
+    n_streams = 6      # the low-resolution wgrads (kernel + dependent reduction) are latency-bound on a few dozen CTAs:
+                       # several run side by side (measured, graph replay: 16x16 phase 0.667 -> 0.625 ms from 3 to 6
+                       # streams, 64x64 2.08 -> 2.06, 512x512 unchanged)
     enabled = True
     keep = []          # tensors a pending side-stream kernel reads: kept alive until side_join()
     used = set()       # indices of pool streams with work since the last join
@@ -298,6 +300,24 @@ def g_forward(net, z, save, img_out=None):
     if bf16_out is not None:
         return ops.f32_to_bf16(img, bf16_out), ctx
     return img, ctx
+
+
+def g_ctx_slice(ctx, lo, hi):
+    """The saved generator context of samples [lo, hi) of a forward pass over a larger batch (TrainStep runs the three
+    generator passes of an iteration as ONE batch at the low resolutions and backpropagates through the last third)."""
+    def cut(v):
+        if torch.is_tensor(v) and v.dim() > 0:
+            return v[lo:hi]
+        if isinstance(v, SimpleNamespace):
+            return SimpleNamespace(**{k: cut(x) for k, x in vars(v).items()})
+        if isinstance(v, list):
+            return [cut(x) for x in v]
+        return v
+    keep = {k: v for k, v in vars(ctx).items() if k in ('net', 'toim', 'toim_new', 'alpha')}
+    out = SimpleNamespace(**{k: cut(v) for k, v in vars(ctx).items() if k not in keep})
+    for k, v in keep.items():
+        setattr(out, k, v)
+    return out
 
 
 def _g_block_bwd(rec, ga2, y_prev, r_prev, leak, sink, extra_pre=None, extra_w=None):

@@ -54,6 +54,12 @@ class TrainStep:
         self.factor_linear = True
         self.fuse_linear_adam = False
         self.materialize_linear_grad = False
+        self.merge_g_forward = None     # run the iteration's three generator passes (z1, z2 detached; z3 with saved
+                                        # activations) as ONE batch: one chain of launches instead of two (measured,
+                                        # graph replay: 16x16 0.636 -> 0.617 ms, 128x128 2.907 -> 2.869, 512x512 3.537
+                                        # -> 3.494 although the activations of 2B samples are then saved for nothing).
+                                        # None = always, except data parallel at >= 256x256, where the separate pass
+                                        # hides the critic's gradient all-reduce
         self.fork_chains = True         # run the two independent halves of the critic step on two streams
         self._chain_stream = None
         self._comm_stream = None        # data parallel: the critic's gradient all-reduce overlaps the generator forward
@@ -166,10 +172,10 @@ class TrainStep:
         """Step inputs: imgs = [x | G(z1) | G(z2)] (the critic batch [real; fake] and x_tilde are views of it),
         z12 = [z1; z2] (both detached generator passes of the critic step run as one batch)."""
         L = self.G.latent_dim
-        buf = SimpleNamespace(imgs=torch.empty((3 * B, R, R), dtype=F32, device=dev),
-                              z12=torch.empty((2 * B, L), dtype=F32, device=dev),
-                              z3=torch.empty((B, L), dtype=F32, device=dev),
-                              eps=torch.empty((B,), dtype=F32, device=dev), B=B, out=SimpleNamespace())
+        z_all = torch.empty((3 * B, L), dtype=F32, device=dev)          # [z1; z2; z3]
+        buf = SimpleNamespace(imgs=torch.empty((4 * B, R, R), dtype=F32, device=dev),   # [x | G(z1) | G(z2) | G(z3)]
+                              z_all=z_all, z12=z_all[:2 * B], z3=z_all[2 * B:],
+                              eps=torch.empty((B,), dtype=F32, device=dev), B=B, R=R, out=SimpleNamespace())
         if self.dp and self.factor_linear:
             buf.pack = self._make_pack(B, dev)
         return buf
@@ -201,7 +207,12 @@ class TrainStep:
         leaves idle."""
         G, D, B = self.G, self.D, buf.B
         flat_d, (sink_w, sink_s1, sink_s2) = self._bind(D, 3)
-        engine.g_forward(G, buf.z12, save=False, img_out=buf.imgs[B:])
+        if self._merged(buf):
+            _, gctx = engine.g_forward(G, buf.z_all, save=True, img_out=buf.imgs[B:])
+            buf.out.fake, buf.out.gctx = buf.imgs[3 * B:], engine.g_ctx_slice(gctx, 2 * B, 3 * B)
+            del gctx
+        else:
+            engine.g_forward(G, buf.z12, save=False, img_out=buf.imgs[B:3 * B])
         main = torch.cuda.current_stream()
         fork = self.fork_chains
         if fork:
@@ -210,7 +221,7 @@ class TrainStep:
             engine.prepare_weights(D)
             self._chain_stream.wait_stream(main)
         with torch.cuda.stream(self._chain_stream if fork else main):
-            x_hat = ops.interp_images(buf.imgs[:B], buf.imgs[2 * B:], buf.eps)
+            x_hat = ops.interp_images(buf.imgs[:B], buf.imgs[2 * B:3 * B], buf.eps)
             buf.out.pen, _, _ = engine.d_grad_penalty(D, x_hat, self.lam, (sink_s1, sink_s2))
             del x_hat
         scores, ctx = engine.d_forward(D, buf.imgs[:2 * B], save=True)
@@ -227,7 +238,15 @@ class TrainStep:
     def _seg_g1(self, buf):
         """The generator's forward pass of the generator step (train.py:376).  It depends on neither the critic's
         gradients nor its update, so with data parallelism it runs while the critic's gradients are all-reduced."""
-        buf.out.fake, buf.out.gctx = engine.g_forward(self.G, buf.z3, save=True)
+        if not self._merged(buf):
+            buf.out.fake, buf.out.gctx = engine.g_forward(self.G, buf.z3, save=True)
+
+    def _merged(self, buf):
+        if self.n_critic != 1:
+            return False
+        if self.merge_g_forward is None:
+            return buf.R <= 128 or not self.dp
+        return bool(self.merge_g_forward)
 
     def _seg_g(self, buf, adam_d=True):
         self._seg_g1(buf)
@@ -351,6 +370,7 @@ class TrainStep:
         # serves every epoch of a fade-in; only whether a fade is in progress changes the kernel sequence
         return (B, R, self.G.alpha_value() < 1, self.D.alpha_value() < 1, self.G.N_layers, self.D.N_layers, self.dp,
                 self.lam, self.drift, self.factor_linear, self.fuse_linear_adam, self.materialize_linear_grad,
+                self.merge_g_forward,
                 tuple(id(p) for p in self.G.active_parameters()), tuple(id(p) for p in self.D.active_parameters()))
 
     def _capture(self, key, B, R, dev):
@@ -377,6 +397,8 @@ class TrainStep:
         # calls into one graph was measured: same iteration time at 2 GPUs, and the process then hung in
         # destroy_process_group -- not worth it.)
         parts = [self._seg_d, self._seg_g1, self._seg_g2, self._seg_end]
+        if self._merged(buf):
+            parts.pop(1)                # the generator's forward pass already ran with the critic step's
         if self.dp or self.segment_graphs:
             ent.graphs, ent.flats = capture(parts)
         else:
@@ -439,16 +461,18 @@ class TrainStep:
                 self._comm_stream.wait_stream(cur)
                 with torch.cuda.stream(self._comm_stream):
                     self._allreduce(ent.flats[0])
-            ent.graphs[1].replay()
+            rest = ent.graphs[1:]
+            if len(rest) == 3:
+                rest.pop(0).replay()    # the generator's forward pass, beside the all-reduce
             if self.dp:
                 cur.wait_stream(self._comm_stream)
             if ev:
                 ev[1].record()
-            ent.graphs[2].replay()
+            rest[0].replay()
             self._exchange_g(ent.buf)
             if ev:
                 ev[2].record()
-            ent.graphs[3].replay()
+            rest[1].replay()
             if ev:
                 ev[3].record()
         self._last_key = key

@@ -55,12 +55,14 @@ def noop(name, ret=None):
 
 
 base = measure('baseline')
+measure('three generator passes as one batch', merge_g_forward=True)
+measure('generator passes separate', merge_g_forward=False)
 measure('four graphs (segment_graphs)', segment_graphs=True)
 for ns in (2, 4, 6):
     def setn(n=ns):
         engine._Side.n_streams = n; engine._Side.streams = []
     def unsetn():
-        engine._Side.n_streams = 3; engine._Side.streams = []
+        engine._Side.n_streams = 6; engine._Side.streams = []
     measure(f'{ns} wgrad side streams', setn, unsetn)
 measure('factored linear grad + plain Adam', factor_linear=True)
 measure('factored linear grad fused into Adam', factor_linear=True, fuse_linear_adam=True)
