@@ -1,5 +1,5 @@
 """The JSON line bench.py prints is a contract with the driver.  Checked here on CPU: the committed line of the last
-B200 run (profiles/r01_bench_512_b16.json) and a live `--impl reference` line."""
+B200 run (profiles/r02_bench_512_b16.json) and a live `--impl reference` line."""
 import json
 import os
 import subprocess
@@ -15,7 +15,7 @@ def _last_json_line(text):
 
 
 def test_recorded_b200_line_has_every_contract_key():
-    line = _last_json_line(open(os.path.join(ROOT, 'profiles', 'r01_bench_512_b16.json')).read())
+    line = _last_json_line(open(os.path.join(ROOT, 'profiles', 'r02_bench_512_b16.json')).read())
     assert BASE_KEYS | {'gpu_launches', 'clocks', 'roofline'} <= set(line)
     baseline = json.load(open(os.path.join(ROOT, 'BASELINE.json')))
     assert line['unit'] == 'images/s' and line['higher_is_better'] is True and line['scaling'] == 'weak'
@@ -31,6 +31,14 @@ def test_recorded_b200_line_has_every_contract_key():
     roof = line['roofline']
     assert {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'} <= set(roof)
     assert roof['bound'] in ('hbm', 'tensor') and abs(roof['frac'] - roof['achieved'] / roof['peak']) < 1e-3
+    # the headline roofline figure is the STEP-level one: algorithmic bytes of an iteration / measured time / peak
+    assert roof['scope'] == 'step'
+    assert abs(roof['achieved'] - roof['algorithmic_bytes_per_step'] / (line['ms_per_step'] * 1e-3) / 1e9) < 1.0
+    for fam in ('family', 'wgrad_family'):
+        assert 0 < roof[fam]['frac'] < 1.2 and roof[fam]['launches_per_step'] > 0
+    assert roof['best_launch']['frac'] >= roof['family']['frac']
+    assert line['rounds']['n'] >= 3 and len(line['rounds']['ms_per_step']) == line['rounds']['n']
+    assert line['gpu_eager_baseline']['value'] > 0 and line['gpu_eager_baseline']['kind'] == 'reference'
     clocks = line['clocks']
     assert {'sm_mhz', 'sm_max_mhz', 'reasons'} <= set(clocks)
     assert not {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'} & set(clocks['reasons'])
