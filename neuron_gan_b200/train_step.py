@@ -58,8 +58,9 @@ class TrainStep:
                                         # activations) as ONE batch: one chain of launches instead of two (measured,
                                         # graph replay: 16x16 0.636 -> 0.617 ms, 128x128 2.907 -> 2.869, 512x512 3.537
                                         # -> 3.494 although the activations of 2B samples are then saved for nothing).
-                                        # None = always, except data parallel at >= 256x256, where the separate pass
-                                        # hides the critic's gradient all-reduce
+                                        # None = always.  (With data parallelism a separate third pass could hide the
+                                        # critic's 2 MB gradient all-reduce, but measured at 2 GPUs the merged pass wins:
+                                        # set False to get the overlapped arrangement.)
         self.fork_chains = True         # run the two independent halves of the critic step on two streams
         self._chain_stream = None
         self._comm_stream = None        # data parallel: the critic's gradient all-reduce overlaps the generator forward
@@ -244,9 +245,7 @@ class TrainStep:
     def _merged(self, buf):
         if self.n_critic != 1:
             return False
-        if self.merge_g_forward is None:
-            return buf.R <= 128 or not self.dp
-        return bool(self.merge_g_forward)
+        return True if self.merge_g_forward is None else bool(self.merge_g_forward)
 
     def _seg_g(self, buf, adam_d=True):
         self._seg_g1(buf)
