@@ -203,8 +203,8 @@ class TrainStep:
     def _seg_d(self, buf):
         """critic step up to complete gradients (train.py:356-365).  After the shared generator pass the
         Wasserstein part ([real; fake] forward + backward) and the gradient-penalty part (x_hat forward,
-        first-order backward, double backward) are independent chains that only meet in the gradient buffer
-        (atomics): they run on two streams, so the narrow low-resolution kernels of one fill the SMs the other
+        first-order backward, double backward) are independent chains that write separate gradient slots (summed in
+        order afterwards): they run on two streams, so the narrow low-resolution kernels of one fill the SMs the other
         leaves idle."""
         G, D, B = self.G, self.D, buf.B
         flat_d, (sink_w, sink_s1, sink_s2) = self._bind(D, 3)
