@@ -2,7 +2,9 @@
 
 Run in the build container only (needs /root/reference):
 
-    PYTHONDONTWRITEBYTECODE=1 python tests/golden/gen_golden.py
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/gen_golden.py [--add]
+
+(--add keeps the cases already in the fixture byte for byte and only generates the missing ones.)
 
 For every (resolution, alpha, batch) case it builds the reference Generator_PG / Discriminator_PG
 after torch.manual_seed(1) (order G, D: train.py:114, 172, 184), calls set_resolution, and runs the
@@ -37,6 +39,11 @@ CASES = [  # (res, alpha, batch)
     (512, 0.5, 1),
     (512, 1.0, 2),     # BASELINE config 3 shape (reduced batch)
     (512, 1.0, 16),    # BASELINE config 3 at its per-GPU batch (16 images per GPU)
+    # ragged batches: what the reference's DataLoader delivers as the last batch of an epoch (drop_last=False)
+    (16, 1.0, 1),
+    (64, 1.0, 3),
+    (128, 0.25, 5),
+    (256, 0.5, 3),
 ]
 
 
@@ -96,7 +103,10 @@ def run_case(res, alpha, batch):
 
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    path = os.path.join(HERE, 'pggan_step_golden.pt')
     golden = {'torch': torch.__version__, 'cases': {}}
+    if '--add' in sys.argv and os.path.exists(path):
+        golden['cases'] = torch.load(path, weights_only=False)['cases']
     # initial parameters (seed 1) are pinned by checksum so that the GPU box can rebuild them
     gp, dp = O.build_params(O.Arch(), seed=1)
     G, D = rh.build_nets(16, 1.0)
@@ -109,9 +119,10 @@ def main():
                       'd': {k: summarize(v) for k, v in dp.items()}}
     for res, alpha, batch in CASES:
         key = f'r{res}_a{alpha}_b{batch}'
+        if key in golden['cases']:
+            continue
         golden['cases'][key] = run_case(res, alpha, batch)
         print(key, golden['cases'][key]['stats'])
-    path = os.path.join(HERE, 'pggan_step_golden.pt')
     torch.save(golden, path)
     print('wrote', path, os.path.getsize(path), 'bytes')
 

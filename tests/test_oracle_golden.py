@@ -7,7 +7,8 @@ from oracle import pggan_oracle as O
 
 ARCH = O.Arch()
 CASES = ['r16_a1.0_b16', 'r32_a0.5_b4', 'r32_a1.0_b4', 'r64_a0.5_b64', 'r64_a1.0_b4',
-         'r128_a0.25_b2', 'r128_a1.0_b2', 'r256_a1.0_b1', 'r512_a0.5_b1', 'r512_a1.0_b2']
+         'r128_a0.25_b2', 'r128_a1.0_b2', 'r256_a1.0_b1', 'r512_a0.5_b1', 'r512_a1.0_b2',
+         'r16_a1.0_b1', 'r64_a1.0_b3', 'r128_a0.25_b5', 'r256_a0.5_b3']        # ragged last batches
 
 
 def close(a, b, rel=2e-5, abs_=1e-7):

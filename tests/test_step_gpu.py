@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 ARCH = O.Arch()
 DEV = 'cuda'
 
-SMALL = ['r16_a1.0_b16', 'r32_a0.5_b4', 'r32_a1.0_b4', 'r64_a0.5_b64', 'r64_a1.0_b4', 'r128_a0.25_b2', 'r128_a1.0_b2']
+SMALL = ['r16_a1.0_b16', 'r32_a0.5_b4', 'r32_a1.0_b4', 'r64_a0.5_b64', 'r64_a1.0_b4', 'r128_a0.25_b2', 'r128_a1.0_b2',
+         'r16_a1.0_b1', 'r64_a1.0_b3', 'r128_a0.25_b5', 'r256_a0.5_b3']      # ragged last batches (drop_last=False)
 LARGE = ['r256_a1.0_b1', 'r512_a0.5_b1', 'r512_a1.0_b2', 'r512_a1.0_b16']    # the last: BASELINE config 3 per GPU
 
 
@@ -57,7 +58,17 @@ def test_forward_and_first_order_gradient_match_reference(golden, key):
     # Element-wise the input gradient of a 12-layer bf16 critic differs from the fp32 reference through
     # LeakyReLU-mask flips; its per-sample norm -- what the penalty uses -- must agree.  The
     # element-wise check is done against the bf16-emulating oracle in test_gradients_match_bf16_emulating_oracle.
-    assert torch.allclose(g.norm(2, dim=(1, 2, 3)).cpu(), ref['gp_grad_norms'], rtol=3e-2)
+    norms = g.norm(2, dim=(1, 2, 3)).cpu()
+    dev = (norms / ref['gp_grad_norms'] - 1).abs().max().item()
+    if dev > 3e-2:
+        # a sample whose norm bf16 storage itself moves by more than 3 % (r128_a0.25_b5, sample 4: +4.7 %): the oracle
+        # with bf16-rounded weights and feature maps must then show the same norm
+        assert dev < 8e-2, (norms, ref['gp_grad_norms'])
+        gp_, dp_ = O.build_params(ARCH, seed=1)
+        n = O.n_layers_for(res, ARCH)
+        with O.emulate_bf16():
+            _, g_emu = O.grad_penalty(gp_, dp_, x, z2, eps, n, alpha, ARCH, return_grad=True)
+        assert torch.allclose(norms, g_emu.detach().norm(2, dim=(1, 2, 3)), rtol=1.5e-2), (norms, ref['gp_grad_norms'])
     assert rel(g[:2, 0, :8, :8].cpu(), ref['gp_grad_patch']) < 0.6
 
 
@@ -101,7 +112,7 @@ def test_train_step_losses_match_reference(golden, key):
             assert torch.allclose(sd[key_].flatten()[:8].cpu(), refp[name]['head'], rtol=0, atol=2.1e-4), name
 
 
-@pytest.mark.parametrize('res,alpha,batch', [(16, 1.0, 4), (32, 0.5, 4), (64, 1.0, 2)])
+@pytest.mark.parametrize('res,alpha,batch', [(16, 1.0, 4), (32, 0.5, 4), (64, 1.0, 2), (64, 0.5, 3)])
 def test_autograd_api_equals_train_step(res, alpha, batch):
     """loss modules + .backward() + FusedAdam (the reference's train.py call pattern) == TrainStep."""
     from neuron_gan_b200.loss_functions import D_W_loss, D_grad_pen_loss, G_W_loss
@@ -309,7 +320,7 @@ def _restore(nets_, opts, snap):
                 o.state[p]['exp_avg_sq'].copy_(v)
 
 
-@pytest.mark.parametrize('res,alpha,batch', [(16, 1.0, 8), (64, 0.5, 4), (128, 1.0, 2)])
+@pytest.mark.parametrize('res,alpha,batch', [(16, 1.0, 8), (64, 0.5, 4), (128, 1.0, 2), (32, 0.5, 5), (256, 1.0, 3)])
 def test_graph_replay_equals_eager(res, alpha, batch):
     """One iteration replayed from the captured CUDA graph (critic step forked over two streams, wgrad kernels on a
     third, Adam scalars read from device memory) against the same iteration launched kernel by kernel from the
