@@ -178,58 +178,82 @@ __device__ __forceinline__ void split_bpix(size_t i, size_t HW, size_t& b, size_
 }
 
 // ------------------------------------------------------------------------------- resampling (forward)
-// One thread per INPUT granule (y, x): its 2x2 output quad needs the clamped 3x3 neighbourhood (align_corners =
-// False, scale 2: out[2i] = .25 x[i-1] + .75 x[i], out[2i+1] = .75 x[i] + .25 x[i+1], separable; the fixed tap
-// pattern of models.py:78-89).  9 loads (neighbours are L1 hits) and 4 stores per thread; a warp writes two
-// contiguous 1 KB row segments.
+// One thread per INPUT column granule x over a strip of RP input rows (align_corners = False, scale 2:
+// out[2i] = .25 x[i-1] + .75 x[i], out[2i+1] = .75 x[i] + .25 x[i+1], indices clamped, separable; the fixed tap
+// pattern of models.py:78-89).  The horizontally interpolated (left, right) output columns of three consecutive input
+// rows roll through registers, so a strip costs 3 (RP + 2) loads (the x -/+ 1 neighbours are L1 hits) instead of 9 RP,
+// and each thread writes its two adjacent output granules as ONE 32-byte store (whole sectors per instruction).
+// Measured: the row reuse is what pays (96 -> 76 us at 256 -> 512, B = 48; 6.6 TB/s), the wide store alone does not.
+__device__ __forceinline__ void st_global_256(uint4* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
+                 "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+__device__ __forceinline__ void up2_hrow(const uint4* __restrict__ row, int xm, int ix, int xp, float* hl, float* hr) {
+    float a[8], b[8], c[8];
+    unpack8(__ldg(row + xm), a);
+    unpack8(__ldg(row + ix), b);
+    unpack8(__ldg(row + xp), c);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        hl[e] = __fmaf_rn(0.75f, b[e], 0.25f * a[e]);
+        hr[e] = __fmaf_rn(0.75f, b[e], 0.25f * c[e]);
+    }
+}
+template <int RP>
 __global__ void __launch_bounds__(128) upsample2x_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int H,
                                                             int W) {
     pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     const int ix = blockIdx.x * blockDim.x + threadIdx.x;
     if (ix >= W) return;
-    const int iy = blockIdx.y;
+    const int y0 = blockIdx.y * RP;
     const size_t plane = blockIdx.z;
     const uint4* p = x + plane * H * W;
     const int xm = max(ix - 1, 0), xp = min(ix + 1, W - 1);
-    const int ys[3] = {max(iy - 1, 0), iy, min(iy + 1, H - 1)};
-    float hl[3][8], hr[3][8];     // horizontally interpolated left / right output columns of the three rows
+    float hl[3][8], hr[3][8];     // rows y-1, y, y+1 of the current input row, rolling (index = row mod 3)
+    up2_hrow(p + static_cast<size_t>(max(y0 - 1, 0)) * W, xm, ix, xp, hl[0], hr[0]);
+    up2_hrow(p + static_cast<size_t>(y0) * W, xm, ix, xp, hl[1], hr[1]);
+    uint4* q = out + plane * 4 * H * W + static_cast<size_t>(2 * y0) * (2 * W) + 2 * ix;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const uint4* row = p + static_cast<size_t>(ys[r]) * W;
-        float a[8], b[8], c[8];
-        unpack8(__ldg(row + xm), a);
-        unpack8(__ldg(row + ix), b);
-        unpack8(__ldg(row + xp), c);
+    for (int r = 0; r < RP; ++r) {
+        up2_hrow(p + static_cast<size_t>(min(y0 + r + 1, H - 1)) * W, xm, ix, xp, hl[(r + 2) % 3], hr[(r + 2) % 3]);
+        const float *l0 = hl[r % 3], *l1 = hl[(r + 1) % 3], *l2 = hl[(r + 2) % 3];
+        const float *r0 = hr[r % 3], *r1 = hr[(r + 1) % 3], *r2 = hr[(r + 2) % 3];
+        float ol[8], orr[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            hl[r][e] = 0.25f * a[e] + 0.75f * b[e];
-            hr[r][e] = 0.75f * b[e] + 0.25f * c[e];
+            ol[e] = __fmaf_rn(0.75f, l1[e], 0.25f * l0[e]);
+            orr[e] = __fmaf_rn(0.75f, r1[e], 0.25f * r0[e]);
         }
+        st_global_256(q, pack8(ol), pack8(orr));
+        q += 2 * W;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            ol[e] = __fmaf_rn(0.75f, l1[e], 0.25f * l2[e]);
+            orr[e] = __fmaf_rn(0.75f, r1[e], 0.25f * r2[e]);
+        }
+        st_global_256(q, pack8(ol), pack8(orr));
+        q += 2 * W;
     }
-    float o[8];
-    uint4* q = out + plane * 4 * H * W + static_cast<size_t>(2 * iy) * (2 * W) + 2 * ix;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = 0.25f * hl[0][e] + 0.75f * hl[1][e];
-    q[0] = pack8(o);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = 0.25f * hr[0][e] + 0.75f * hr[1][e];
-    q[1] = pack8(o);
-    q += 2 * W;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = 0.75f * hl[1][e] + 0.25f * hl[2][e];
-    q[0] = pack8(o);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = 0.75f * hr[1][e] + 0.25f * hr[2][e];
-    q[1] = pack8(o);
 }
 int upsample2x_c8(const void* x, void* out, int B, int C, int H, int W, cudaStream_t st) {
     const int threads = W < 128 ? ((W + 31) / 32 * 32) : 128;
-    const dim3 grid((W + threads - 1) / threads, H, B * (C / 8));
+    // rows per thread, measured on B200 at the generator's shapes (scripts/bench_upsample.py, B = 48): 2 rows 75.7 /
+    // 39.3 / 9.9 us at 512 / 256 / 128 outputs (4 rows 79.2 / 40.7 / 10.3), 4 rows 5.8 / 5.1 us at 64 / 32 (2 rows
+    // 7.3 / 7.2); one row per thread (the round-1 arrangement) 96 / 49 / 14 / 13.6 / 13.5 us
+    static const int rp_env = getenv("NGAN_UP2_ROWS") ? atoi(getenv("NGAN_UP2_ROWS")) : 0;
+    const int want = rp_env > 0 ? rp_env : (H <= 32 ? 4 : 2);
+    const int rp = (want >= 4 && H % 4 == 0) ? 4 : (want >= 2 && H % 2 == 0) ? 2 : 1;
+    const dim3 grid((W + threads - 1) / threads, H / rp, B * (C / 8));
     if (grid.z > 65535) {
         set_error("upsample2x: too many planes (%u)", grid.z);
         return NGAN_ERR_UNSUPPORTED;
     }
-    upsample2x_c8_kernel<<<grid, threads, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), H, W);
+    const uint4* xi = static_cast<const uint4*>(x);
+    uint4* o = static_cast<uint4*>(out);
+    if (rp == 4) upsample2x_c8_kernel<4><<<grid, threads, 0, st>>>(xi, o, H, W);
+    else if (rp == 2) upsample2x_c8_kernel<2><<<grid, threads, 0, st>>>(xi, o, H, W);
+    else upsample2x_c8_kernel<1><<<grid, threads, 0, st>>>(xi, o, H, W);
     return check_launch("upsample2x_c8");
 }
 
