@@ -665,80 +665,124 @@ int d_fade_fwd(const void* y_end, const float* xp, const float* w_old, const flo
 
 // Backward of FromImage: with G = gscale * g[(y,x) or (y/2,x/2)]:
 //   gw[c] += sum G_c * xp,  gb[c] += sum G_c,  g_img[b,p] (+)= sum_c w_c * G_c
-// Thread layout of the two 1x1-conv backward kernels below: a block of 128 threads = (128 / NCH) pixel lanes x NCH
-// channel groups, the NCH threads of a pixel being adjacent lanes.  Each thread walks many pixels (grid-stride) and
-// keeps the per-channel sums of its group (weight / bias gradient) in registers; per pixel, sums over all channels
-// go through xor-shuffles over the NCH lanes; the per-channel sums meet once per block in shared memory (summed in
-// lane order) and leave as one row [gw | gb] of the partials workspace, which reduce_partials adds in block order
-// (no atomics: bit-reproducible gradients).  (Warp-reducing 8 values per group per pixel, as before, made these
-// kernels shuffle-bound at 512x512 and left the 128-channel 16x16 launches at 36-49 us for 1 MB.)
-constexpr int kPixPerThread = 8;
+// Thread layout of the 1x1-conv backward kernels below: a block of 128 threads = (128 / NCH) pixel lanes x NCH
+// channel groups, the NCH threads of a pixel being adjacent lanes.  The work is cut into chunks of consecutive pixels
+// of ONE image (pixel_chunks: a block takes chunk blockIdx.x, blockIdx.x + gridDim.x, ...), so all addressing
+// inside the loop is "base + pixel" in 32 bits -- ncu (round 2) showed these kernels issue-bound, not HBM-bound:
+// fromim_bwd spent 125 warp-instructions per (16 pixels x 16 channels), most of them 64-bit index arithmetic and
+// the two integer divisions that turned a flat index back into (image, row, column) for every pixel.
+// Each thread keeps the per-channel sums of its group (weight / bias gradient) in registers; per pixel, sums over
+// all channels go through xor-shuffles over the NCH lanes; the per-channel sums meet once per block in shared
+// memory (summed in lane order) and leave as one row of the partials workspace, which reduce_partials adds in
+// block order (no atomics: bit-reproducible gradients).
+struct PixelChunks {
+    unsigned chunk, per_img, n;
+    int blocks;
+};
+static PixelChunks pixel_chunks(int B, size_t HW, int pixel_lanes, int resident_per_sm) {
+    // One resident wave.  If the work fits it as one chunk per block (16, 8 or 4 pixels per thread -- the smaller
+    // ones only to get at least two blocks per SM on the small maps), that is the grid.  Otherwise chunks of 8
+    // pixels per thread and as many blocks as are resident at once, each walking several chunks: the load is then
+    // balanced to ~10 %.  (Measured, toim_bwd at 512x512: 1024 one-chunk blocks at 6 resident per SM = 1.15 waves,
+    // 82 us; 888 blocks over 4096 chunks 64 us.  fromim_bwd at 256x256: 1024 one-chunk blocks in one wave 14.3 us;
+    // 888 blocks over 1024 chunks 18.1 us.)
+    const unsigned cap = 148u * static_cast<unsigned>(resident_per_sm);
+    PixelChunks c;
+    for (int iters = 16;; iters /= 2) {
+        c.chunk = static_cast<unsigned>(pixel_lanes * iters);
+        c.per_img = static_cast<unsigned>((HW + c.chunk - 1) / c.chunk);
+        c.n = static_cast<unsigned>(B) * c.per_img;
+        if (c.n >= 2 * 148u || iters == 4) break;
+    }
+    if (c.n > cap) {
+        c.chunk = static_cast<unsigned>(pixel_lanes * 8);
+        c.per_img = static_cast<unsigned>((HW + c.chunk - 1) / c.chunk);
+        c.n = static_cast<unsigned>(B) * c.per_img;
+    }
+    c.blocks = static_cast<int>(c.n < cap ? c.n : cap);       // every block ends with one partial row
+    return c;
+}
+static int log2_exact(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return (1 << l) == v ? l : -1;
+}
+// index of pixel p of an H x W map in the half-resolution map (the adjoint of AvgPool2d(2) reads its cotangent there)
+__device__ __forceinline__ unsigned unpool_index(unsigned p, int W, int wshift) {
+    unsigned py, px;
+    if (wshift >= 0) {
+        py = p >> wshift;
+        px = p & static_cast<unsigned>(W - 1);
+    } else {
+        py = p / static_cast<unsigned>(W);
+        px = p - py * W;
+    }
+    return (py >> 1) * static_cast<unsigned>(W >> 1) + (px >> 1);
+}
 template <int NCH>
 __global__ void __launch_bounds__(128) fromim_bwd_kernel(const uint4* __restrict__ g, int unpool, float gscale_h,
                                                          const float* __restrict__ dyn,
                                                          const float* __restrict__ xp, const float* __restrict__ w,
                                                          float* __restrict__ partials,
                                                          float* __restrict__ g_img, int accumulate, int H, int W,
-                                                         size_t total) {
+                                                         int wshift, unsigned chunk, unsigned per_img,
+                                                         unsigned n_chunks) {
     constexpr int PL = 128 / NCH, C = NCH * 8;
+    constexpr int U = 4;              // pixels in flight per thread: all loads of a batch are issued before the first use
     const float gscale = dyn ? gscale_h * __ldg(dyn) : gscale_h;
     __shared__ float red[2][PL][C];
     const int pl = threadIdx.x / NCH, j = threadIdx.x % NCH;
-    const size_t HW = static_cast<size_t>(H) * W;
-    const size_t gHW = unpool ? HW / 4 : HW;
-    float wj[8], sw[8], sb[8];
+    const unsigned HW = static_cast<unsigned>(H) * W;
+    const unsigned gHW = unpool ? HW / 4 : HW;
+    float wj[8], sw[8], sb[8];        // sums of the raw cotangent; gscale is applied once at the end
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         wj[e] = __ldg(w + j * 8 + e);
         sw[e] = sb[e] = 0.f;
     }
-    const size_t stride = static_cast<size_t>(gridDim.x) * PL;
-    const size_t n_iter = (total + stride - 1) / stride;        // the same trip count for every thread (shuffles inside)
-    constexpr int U = 4;                                        // pixels in flight per thread: all loads of a batch are
-    for (size_t k0 = 0; k0 < n_iter; k0 += U) {                 // issued before the first use (the loop ran at load latency)
-        uint4 gq4[U];
-        float xv4[U];
-        size_t ii4[U];
-        bool ok4[U];
+    for (unsigned cid = blockIdx.x; cid < n_chunks; cid += gridDim.x) {
+        const unsigned b = cid / per_img;
+        const unsigned p0 = (cid - b * per_img) * chunk;
+        const unsigned p_end = min(HW, p0 + chunk);
+        const uint4* gp = g + static_cast<size_t>(b * NCH + j) * gHW;
+        const float* xb = xp + static_cast<size_t>(b) * HW;
+        float* gi = g_img ? g_img + static_cast<size_t>(b) * HW : nullptr;
+        for (unsigned q = p0; q < p_end; q += U * PL) {        // the same trip count for every thread (shuffles inside)
+            uint4 gq4[U];
+            float xv4[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const size_t i = (k0 + u) * stride + static_cast<size_t>(blockIdx.x) * PL + pl;
-            ok4[u] = (k0 + u) < n_iter && i < total;
-            ii4[u] = ok4[u] ? i : 0;
-            int px, py;
-            size_t b;
-            split_xyb(ii4[u], W, H, px, py, b);
-            const size_t gq = unpool ? (b * NCH + j) * gHW + static_cast<size_t>(py >> 1) * (W >> 1) + (px >> 1)
-                                     : (b * NCH + j) * HW + static_cast<size_t>(py) * W + px;
-            gq4[u] = ok4[u] ? __ldg(g + gq) : make_uint4(0, 0, 0, 0);
-            xv4[u] = ok4[u] ? __ldg(xp + ii4[u]) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if ((k0 + u) >= n_iter) break;                      // uniform over the block
-            float gv[8];
-            unpack8(gq4[u], gv);
-            const float xv = xv4[u];
-            float im = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float G = gscale * gv[e];
-                sw[e] = fmaf(G, xv, sw[e]);
-                sb[e] += G;
-                im = fmaf(wj[e], G, im);
+            for (int u = 0; u < U; ++u) {
+                const unsigned p = q + u * PL + pl;
+                const bool ok = p < p_end;
+                gq4[u] = ok ? __ldg(gp + (unpool ? unpool_index(p, W, wshift) : p)) : make_uint4(0, 0, 0, 0);
+                xv4[u] = ok ? __ldg(xb + p) : 0.f;
             }
 #pragma unroll
-            for (int o = 1; o < NCH; o <<= 1) im += __shfl_xor_sync(0xffffffffu, im, o);
-            if (g_img && ok4[u] && j == 0) g_img[ii4[u]] = (accumulate ? g_img[ii4[u]] : 0.f) + im;
+            for (int u = 0; u < U; ++u) {
+                const unsigned p = q + u * PL + pl;
+                float gv[8];
+                unpack8(gq4[u], gv);
+                const float xv = xv4[u];
+                float im = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    sw[e] = fmaf(gv[e], xv, sw[e]);
+                    sb[e] += gv[e];
+                    im = fmaf(wj[e], gv[e], im);
+                }
+#pragma unroll
+                for (int o = 1; o < NCH; o <<= 1) im += __shfl_xor_sync(0xffffffffu, im, o);
+                if (gi && j == 0 && p < p_end) gi[p] = accumulate ? fmaf(gscale, im, gi[p]) : gscale * im;
+            }
         }
     }
+    if (!partials) return;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        red[0][pl][j * 8 + e] = sw[e];
-        red[1][pl][j * 8 + e] = sb[e];
+        red[0][pl][j * 8 + e] = gscale * sw[e];
+        red[1][pl][j * 8 + e] = gscale * sb[e];
     }
     __syncthreads();
-    if (!partials) return;
     for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
         const int which = c / C, cc = c - which * C;
         float v = 0.f;
@@ -747,23 +791,17 @@ __global__ void __launch_bounds__(128) fromim_bwd_kernel(const uint4* __restrict
         partials[static_cast<size_t>(blockIdx.x) * 2 * C + c] = v;
     }
 }
-static int pointwise_blocks(size_t total, int pixel_lanes) {
-    size_t blocks = (total + static_cast<size_t>(pixel_lanes) * kPixPerThread - 1) / (static_cast<size_t>(pixel_lanes) * kPixPerThread);
-    if (blocks > 148 * 8) blocks = 148 * 8;      // every block ends with one partial row for the ordered reduction
-    if (blocks < 1) blocks = 1;
-    return static_cast<int>(blocks);
-}
 int fromim_bwd(const void* g, int unpool, float gscale, const float* dyn, const float* xp, const float* w, float* gw, float* gb,
                int grad_accumulate, float* workspace, float* g_img, int g_img_accumulate, int B, int C, int H, int W,
                cudaStream_t st) {
-    const size_t total = static_cast<size_t>(B) * H * W;
     float* partials = (gw || gb) ? workspace : nullptr;
-    const int blocks = pointwise_blocks(total, 128 / (C / 8));
+    const PixelChunks pc = pixel_chunks(B, static_cast<size_t>(H) * W, 128 / (C / 8), 7);
+    const int blocks = pc.blocks;
 #define NGAN_FIB(N)                                                                                                  \
     case N:                                                                                                          \
         fromim_bwd_kernel<N><<<blocks, 128, 0, st>>>(                                                                \
             static_cast<const uint4*>(g), unpool, gscale, dyn, xp, w, partials, g_img, g_img_accumulate, H, W,       \
-            total);                                                                                                  \
+            log2_exact(W), pc.chunk, pc.per_img, pc.n);                                                              \
         break;
     switch (C / 8) {
         NGAN_FIB(2)
@@ -784,52 +822,93 @@ int fromim_bwd(const void* g, int unpool, float gscale, const float* dyn, const 
 }
 // Double backward of FromImage's input-gradient: first order was g_xp = sum_c w_c * G_c.  With cotangent
 // X = in_scale * ghat_xp on g_xp:  ghat_out[c] = w_c * X (cotangent on G_c),  what[c] += sum X * G_c.
-__global__ void fromim_dbl_kernel(const float* __restrict__ ghat_xp, float in_scale, const uint4* __restrict__ g,
-                                  int unpool, float gscale_h, const float* __restrict__ dyn,
-                                  const float* __restrict__ w, uint4* __restrict__ ghat_out,
-                                  float* __restrict__ partials, int C, int H, int W, size_t total) {
+// (thread layout and chunking: see fromim_bwd_kernel)
+template <int NCH>
+__global__ void __launch_bounds__(128) fromim_dbl_kernel(const float* __restrict__ ghat_xp, float in_scale,
+                                                         const uint4* __restrict__ g, int unpool, float gscale_h,
+                                                         const float* __restrict__ dyn, const float* __restrict__ w,
+                                                         uint4* __restrict__ ghat_out, float* __restrict__ partials,
+                                                         int H, int W, int wshift, unsigned chunk, unsigned per_img,
+                                                         unsigned n_chunks) {
     pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
+    constexpr int PL = 128 / NCH, C = NCH * 8;
+    constexpr int U = 4;
     const float gscale = dyn ? gscale_h * __ldg(dyn) : gscale_h;
-    extern __shared__ float sacc[];  // [4 warps][C]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t HW = static_cast<size_t>(H) * W;
-    const size_t gHW = unpool ? HW / 4 : HW;
-    const int nch = C / 8;
-    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const bool ok = i < total;
-    const size_t ii = ok ? i : 0;
-    int px, py;
-    size_t b;
-    split_xyb(ii, W, H, px, py, b);
-    const size_t q0 = b * nch * HW + static_cast<size_t>(py) * W + px;
-    const size_t g0 = unpool ? b * nch * gHW + static_cast<size_t>(py >> 1) * (W >> 1) + (px >> 1) : q0;
-    const float X = ok ? in_scale * ghat_xp[ii] : 0.f;
-    for (int j = 0; j < nch; ++j) {
-        float gv[8], o[8], sw[8];
-        unpack8(ok ? __ldg(g + g0 + j * gHW) : make_uint4(0, 0, 0, 0), gv);
+    __shared__ float red[PL][C];
+    const int pl = threadIdx.x / NCH, j = threadIdx.x % NCH;
+    const unsigned HW = static_cast<unsigned>(H) * W;
+    const unsigned gHW = unpool ? HW / 4 : HW;
+    float wj[8], sw[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            o[e] = __ldg(w + j * 8 + e) * X;
-            sw[e] = X * gscale * gv[e];
+    for (int e = 0; e < 8; ++e) {
+        wj[e] = __ldg(w + j * 8 + e);
+        sw[e] = 0.f;
+    }
+    for (unsigned cid = blockIdx.x; cid < n_chunks; cid += gridDim.x) {
+        const unsigned b = cid / per_img;
+        const unsigned p0 = (cid - b * per_img) * chunk;
+        const unsigned p_end = min(HW, p0 + chunk);
+        const uint4* gp = g + static_cast<size_t>(b * NCH + j) * gHW;
+        const float* xb = ghat_xp + static_cast<size_t>(b) * HW;
+        uint4* ob = ghat_out ? ghat_out + static_cast<size_t>(b * NCH + j) * HW : nullptr;
+        for (unsigned q = p0; q < p_end; q += U * PL) {
+            uint4 gq4[U];
+            float X4[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned p = q + u * PL + pl;
+                const bool ok = p < p_end;
+                gq4[u] = (ok && partials) ? __ldg(gp + (unpool ? unpool_index(p, W, wshift) : p)) : make_uint4(0, 0, 0, 0);
+                X4[u] = ok ? in_scale * __ldg(xb + p) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned p = q + u * PL + pl;
+                float gv[8], o[8];
+                unpack8(gq4[u], gv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    o[e] = wj[e] * X4[u];
+                    sw[e] = fmaf(X4[u], gv[e], sw[e]);
+                }
+                if (ob && p < p_end) ob[p] = pack8(o);
+            }
         }
-        if (ok && ghat_out) ghat_out[q0 + j * HW] = pack8(o);
-        if (partials) warp_store8(sw, sacc + warp * C + j * 8, lane);
     }
     if (!partials) return;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[pl][j * 8 + e] = gscale * sw[e];
     __syncthreads();
-    for (int k = threadIdx.x; k < C; k += blockDim.x)
-        partials[static_cast<size_t>(blockIdx.x) * C + k] = (sacc[k] + sacc[C + k]) + (sacc[2 * C + k] + sacc[3 * C + k]);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float v = 0.f;
+#pragma unroll 4
+        for (int q = 0; q < PL; ++q) v += red[q][c];
+        partials[static_cast<size_t>(blockIdx.x) * C + c] = v;
+    }
 }
 int fromim_dbl(const float* ghat_xp, float in_scale, const void* g, int unpool, float gscale, const float* dyn,
                const float* w,
                void* ghat_out, float* what, int grad_accumulate, float* workspace, int B, int C, int H, int W,
                cudaStream_t st) {
-    const size_t total = static_cast<size_t>(B) * H * W;
-    const int blocks = nblocks(total, 128);
     float* partials = what ? workspace : nullptr;
-    fromim_dbl_kernel<<<blocks, 128, 4 * C * sizeof(float), st>>>(
-        ghat_xp, in_scale, static_cast<const uint4*>(g), unpool, gscale, dyn, w, static_cast<uint4*>(ghat_out),
-        partials, C, H, W, total);
+    const PixelChunks pc = pixel_chunks(B, static_cast<size_t>(H) * W, 128 / (C / 8), 8);
+    const int blocks = pc.blocks;
+#define NGAN_FID(N)                                                                                                  \
+    case N:                                                                                                          \
+        fromim_dbl_kernel<N><<<blocks, 128, 0, st>>>(ghat_xp, in_scale, static_cast<const uint4*>(g), unpool, gscale, \
+                                                     dyn, w, static_cast<uint4*>(ghat_out), partials, H, W,          \
+                                                     log2_exact(W), pc.chunk, pc.per_img, pc.n);                     \
+        break;
+    switch (C / 8) {
+        NGAN_FID(2)
+        NGAN_FID(4)
+        NGAN_FID(8)
+        NGAN_FID(16)
+        default:
+            set_error("fromim_dbl: unsupported channel count %d (16, 32, 64, 128 are built)", C);
+            return NGAN_ERR_UNSUPPORTED;
+    }
+#undef NGAN_FID
     int rc = check_launch("fromim_dbl");
     if (rc || !partials) return rc;
     return reduce_partials(partials, blocks, C, C, 1.f, what, grad_accumulate, st);
@@ -874,10 +953,11 @@ __global__ void __launch_bounds__(128) toim_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ img, const uint4* __restrict__ y,
                                                        const float* __restrict__ r, const float* __restrict__ w,
                                                        uint4* __restrict__ ga, float* __restrict__ gpre_out,
-                                                       float* __restrict__ partials, float leak, size_t HW,
-                                                       size_t total) {
+                                                       float* __restrict__ partials, float leak, unsigned HW,
+                                                       unsigned chunk, unsigned per_img, unsigned n_chunks) {
     pdl_trigger();   // the next kernel (a PDL-launched conv) may start its prologue now
     constexpr int PL = 128 / NCH, C = NCH * 8;
+    constexpr int U = 4;                                        // pixels in flight per thread (see fromim_bwd_kernel)
     const float gscale = dyn ? gscale_h * __ldg(dyn) : gscale_h;
     __shared__ float red[PL][C];
     const int pl = threadIdx.x / NCH, j = threadIdx.x % NCH;
@@ -887,50 +967,53 @@ __global__ void __launch_bounds__(128) toim_bwd_kernel(const float* __restrict__
         wj[e] = __ldg(w + j * 8 + e);
         sw[e] = 0.f;
     }
-    const size_t stride = static_cast<size_t>(gridDim.x) * PL;
-    const size_t n_iter = (total + stride - 1) / stride;
-    constexpr int U = 4;                                        // pixels in flight per thread (see fromim_bwd_kernel)
-    for (size_t k0 = 0; k0 < n_iter; k0 += U) {
-        uint4 yq4[U];
-        float im4[U], gi4[U], r4[U];
-        size_t ii4[U], q4[U];
-        bool ok4[U];
+    for (unsigned cid = blockIdx.x; cid < n_chunks; cid += gridDim.x) {
+        const unsigned b = cid / per_img;
+        const unsigned p0 = (cid - b * per_img) * chunk;
+        const unsigned p_end = min(HW, p0 + chunk);
+        const size_t img_off = static_cast<size_t>(b) * HW, feat_off = static_cast<size_t>(b * NCH + j) * HW;
+        const float* imb = img + img_off;
+        const float* gib = g_img + img_off;
+        const float* rb = r ? r + img_off : nullptr;
+        const uint4* yb = y + feat_off;
+        uint4* gab = ga ? ga + feat_off : nullptr;
+        float* gpo = gpre_out ? gpre_out + img_off : nullptr;
+        for (unsigned q = p0; q < p_end; q += U * PL) {        // the same trip count for every thread (shuffles inside)
+            uint4 yq4[U];
+            float im4[U], gi4[U], r4[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const size_t i = (k0 + u) * stride + static_cast<size_t>(blockIdx.x) * PL + pl;
-            ok4[u] = (k0 + u) < n_iter && i < total;
-            ii4[u] = ok4[u] ? i : 0;
-            size_t b, pix;
-            split_bpix(ii4[u], HW, b, pix);
-            q4[u] = (b * NCH + j) * HW + pix;
-            im4[u] = __ldg(img + ii4[u]);
-            gi4[u] = __ldg(g_img + ii4[u]);
-            yq4[u] = __ldg(y + q4[u]);
-            r4[u] = ga ? __ldg(r + ii4[u]) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if ((k0 + u) >= n_iter) break;                      // uniform over the block
-            const bool ok = ok4[u];
-            const float im = im4[u];
-            const float gpre = ok ? gscale * gi4[u] * (1.f - im * im) : 0.f;
-            if (gpre_out && ok && j == 0) gpre_out[ii4[u]] = gpre;
-            float yv[8], t = 0.f;
-            unpack8(yq4[u], yv);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                sw[e] = fmaf(gpre, yv[e], sw[e]);
-                t = fmaf(wj[e], yv[e], t);
+            for (int u = 0; u < U; ++u) {
+                const unsigned p = q + u * PL + pl;
+                const bool ok = p < p_end;
+                im4[u] = ok ? __ldg(imb + p) : 0.f;
+                gi4[u] = ok ? __ldg(gib + p) : 0.f;
+                yq4[u] = ok ? __ldg(yb + p) : make_uint4(0, 0, 0, 0);
+                r4[u] = (ok && gab) ? __ldg(rb + p) : 0.f;
             }
-            if (ga) {
 #pragma unroll
-                for (int o = 1; o < NCH; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-                const float tp = t * gpre * (1.0f / C);
-                const float rinv = r4[u];
-                float o8[8];
+            for (int u = 0; u < U; ++u) {
+                const unsigned p = q + u * PL + pl;
+                const bool ok = p < p_end;
+                const float im = im4[u];
+                const float gpre = gscale * gi4[u] * (1.f - im * im);      // 0 for an out-of-range lane (gi = 0)
+                if (gpo && ok && j == 0) gpo[p] = gpre;
+                float yv[8], t = 0.f;
+                unpack8(yq4[u], yv);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o8[e] = lrelu_mask(yv[e], leak) * rinv * (wj[e] * gpre - yv[e] * tp);
-                if (ok) ga[q4[u]] = pack8(o8);
+                for (int e = 0; e < 8; ++e) {
+                    sw[e] = fmaf(gpre, yv[e], sw[e]);
+                    t = fmaf(wj[e], yv[e], t);
+                }
+                if (gab) {
+#pragma unroll
+                    for (int o = 1; o < NCH; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    const float tp = t * gpre * (1.0f / C);
+                    const float rinv = r4[u];
+                    float o8[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o8[e] = lrelu_mask(yv[e], leak) * rinv * (wj[e] * gpre - yv[e] * tp);
+                    if (ok) gab[p] = pack8(o8);
+                }
             }
         }
     }
@@ -949,14 +1032,15 @@ __global__ void __launch_bounds__(128) toim_bwd_kernel(const float* __restrict__
 int toim_bwd(const float* g_img, float gscale, const float* dyn, const float* img, const void* y, const float* r, const float* w,
              void* ga, float* gpre, float* gw, int grad_accumulate, float* workspace, float leak, int B, int C, int H,
              int W, cudaStream_t st) {
-    const size_t HW = static_cast<size_t>(H) * W, total = B * HW;
+    const size_t HW = static_cast<size_t>(H) * W;
     float* partials = gw ? workspace : nullptr;
-    const int blocks = pointwise_blocks(total, 128 / (C / 8));
+    const PixelChunks pc = pixel_chunks(B, HW, 128 / (C / 8), 6);
+    const int blocks = pc.blocks;
 #define NGAN_TIB(N)                                                                                                 \
     case N:                                                                                                         \
         toim_bwd_kernel<N><<<blocks, 128, 0, st>>>(                                                                 \
             g_img, gscale, dyn, img, static_cast<const uint4*>(y), r, w, static_cast<uint4*>(ga), gpre, partials,   \
-            leak, HW, total);                                                                                       \
+            leak, static_cast<unsigned>(HW), pc.chunk, pc.per_img, pc.n);                                           \
         break;
     switch (C / 8) {
         NGAN_TIB(2)
