@@ -488,6 +488,7 @@ int up2_bwd_pn_bwd_c8(const void* g_up, const void* y, const float* r, const flo
     const int nch = C / 8;
     const int lanes = W * nch;
     const int threads = lanes < 128 ? (lanes + 31) / 32 * 32 : 128;
+    // rows per thread, measured (512 -> 256, B = 16): 1 row 61.8 us, 2 rows 50.2 us, 4 rows 50.6 us (spills)
     const int rp = H % 2 == 0 ? 2 : 1;
     const dim3 grid((lanes + threads - 1) / threads, H / rp, B);
     if (B > 65535) {
