@@ -191,6 +191,39 @@ def test_image_ops():
     assert torch.allclose(o.scale_rows(x, eps, 2.0), 2 * eps.view(3, 1, 1) * x, atol=1e-6)
 
 
+@pytest.mark.parametrize('misalign', [False, True])
+def test_image_ops_vector_path(misalign):
+    """The four-floats-per-thread variants (rows >= 128 floats, 16-byte aligned) against torch, and the same shapes
+    through the scalar kernels when the base pointer is only 4-byte aligned."""
+    o = ops()
+
+    def mk(*shape):
+        n = 1
+        for d in shape:
+            n *= d
+        flat = torch.randn(n + 1, device='cuda')
+        return flat[1:].view(*shape) if misalign else flat[:n].view(*shape)
+
+    x, y = mk(3, 64, 256), mk(3, 64, 256)
+    assert (x.data_ptr() % 16 != 0) == misalign
+    assert torch.allclose(o.pool_image(x), F.avg_pool2d(x.unsqueeze(1), 2)[:, 0], atol=1e-6)
+    assert torch.equal(o.unpool_image(x, 0.25), 0.25 * F.interpolate(x.unsqueeze(1), scale_factor=2)[:, 0])
+    eps = torch.rand(3, device='cuda')
+    e = eps.view(3, 1, 1)
+    assert torch.allclose(o.interp_images(x, y, eps), e * x + (1 - e) * y, atol=1e-6)
+    assert torch.allclose(o.scale_rows(x, eps, 2.0), 2 * e * x, atol=1e-6)
+    assert torch.allclose(o.lerp(x, y, 0.3), x + 0.3 * (y - x), atol=1e-6)
+    assert torch.allclose(o.up2_image(x), F.interpolate(x.unsqueeze(1), scale_factor=2, mode='bilinear')[:, 0], atol=2e-6)
+    g = mk(3, 128, 512)
+    xr = x.clone().requires_grad_()
+    ref, = torch.autograd.grad(F.interpolate(xr.unsqueeze(1), scale_factor=2, mode='bilinear'), xr, g.unsqueeze(1))
+    assert torch.allclose(o.up2_image_bwd(g, 0.5), 0.5 * ref, atol=1e-5)
+    # whatever the alignment, the same values (vector against scalar kernels)
+    xa = x.clone()
+    assert torch.allclose(o.pool_image(xa), o.pool_image(x), rtol=0, atol=1e-7)
+    assert torch.allclose(o.interp_images(xa, y.clone(), eps), o.interp_images(x, y, eps), rtol=0, atol=1e-6)
+
+
 @pytest.mark.parametrize('C', [16, 128])
 def test_fromim_toim(C):
     o = ops()
