@@ -522,3 +522,96 @@ def test_fused_toimage_is_refused_for_wide_layers():
     w_fwd, _ = o.prep_conv_weight(w)
     with pytest.raises(NganError):
         o.conv3x3_fwd_toim(o.nchw_to_c8(x), w_fwd, None, 1.0, LEAK, 128, torch.zeros(128, device='cuda'))
+
+
+class _GuardedAlloc:
+    """Stand-in for torch.empty / torch.empty_like while an op runs: every buffer the wrapper allocates (outputs AND
+    scratch workspaces) sits between two 256-byte guard zones filled with a sentinel; `check()` asserts that no kernel
+    wrote into them.  (compute-sanitizer is not available on the GPU pool; this is the out-of-bounds-write check for
+    the kernels whose indexing was rewritten in round 2.)"""
+    GUARD_BYTES = 256
+
+    def __init__(self):
+        self._empty, self._empty_like = torch.empty, torch.empty_like
+        self.bufs = []
+
+    def empty(self, *size, dtype=None, device=None, **kw):
+        shape = tuple(size[0]) if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)) else tuple(size)
+        dtype = dtype or torch.float32
+        n = 1
+        for d in shape:
+            n *= int(d)
+        g = self.GUARD_BYTES // self._empty((), dtype=dtype).element_size()
+        buf = self._empty(n + 2 * g, dtype=dtype, device=device)
+        buf.fill_(1232.0)
+        self.bufs.append((buf, g, n))
+        return buf[g:g + n].view(shape)
+
+    def empty_like(self, t, **kw):
+        return self.empty(tuple(t.shape), dtype=kw.get('dtype', t.dtype), device=kw.get('device', t.device))
+
+    def __enter__(self):
+        torch.empty, torch.empty_like = self.empty, self.empty_like
+        return self
+
+    def __exit__(self, *exc):
+        torch.empty, torch.empty_like = self._empty, self._empty_like
+
+    def check(self, what):
+        torch.cuda.synchronize()
+        assert self.bufs, what
+        for buf, g, n in self.bufs:
+            lo, hi = buf[:g].float(), buf[g + n:].float()
+            assert bool((lo == 1232.0).all()) and bool((hi == 1232.0).all()), f'{what}: write outside a {n}-element buffer'
+        self.bufs = []
+
+
+@pytest.mark.parametrize('B,C,R', [(2, 16, 128), (3, 32, 64), (2, 128, 16), (1, 16, 256)])
+def test_no_out_of_bounds_writes(B, C, R):
+    """Row-blocked resampling kernels, chunked 1x1-conv backward kernels and the float4 image kernels at shapes that
+    take their vector / multi-row / multi-chunk paths: nothing is written outside the output and workspace buffers."""
+    o = ops()
+    torch.manual_seed(0)
+    lo = o.nchw_to_c8(torch.randn(B, C, R // 2, R // 2, device='cuda'))
+    hi = o.nchw_to_c8(torch.randn(B, C, R, R, device='cuda'))
+    r_lo = torch.rand(B, R // 2, R // 2, device='cuda') + 0.5
+    r_hi = torch.rand(B, R, R, device='cuda') + 0.5
+    img = torch.rand(B, R, R, device='cuda')
+    img_lo = torch.rand(B, R // 2, R // 2, device='cuda')
+    w = torch.randn(C, device='cuda')
+    eps = torch.rand(B, device='cuda')
+    gw, gb = torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda')
+    with _GuardedAlloc() as ga:
+        o.upsample2x(lo)
+        ga.check('upsample2x')
+        o.avgpool2(hi)
+        ga.check('avgpool2')
+        o.up2_bwd_pn_bwd(hi, lo, r_lo)
+        ga.check('up2_bwd_pn_bwd')
+        o.up2_bwd_pn_bwd(hi, lo, r_lo, extra_pre=img_lo, extra_w=w)
+        ga.check('up2_bwd_pn_bwd + extra')
+        gi = torch.empty(B, R, R, device='cuda')
+        o.fromim_bwd(hi, img, w, gw, gb, g_img=gi, accumulate=False)
+        ga.check('fromim_bwd')
+        o.fromim_bwd(lo, img, w, gw, gb, gscale=0.25, unpool=True, g_img=gi, accumulate=True)
+        ga.check('fromim_bwd unpool')
+        o.fromim_dbl(img, hi, w, gw)
+        ga.check('fromim_dbl')
+        o.toim_bwd(img, img, hi, r_hi, w, gw, want_ga=True, want_gpre=True)
+        ga.check('toim_bwd')
+        o.pool_image(img)
+        ga.check('pool_image')
+        o.unpool_image(img_lo, 0.25)
+        ga.check('unpool_image')
+        o.up2_image(img_lo)
+        ga.check('up2_image')
+        o.up2_image_bwd(img, 0.5)
+        ga.check('up2_image_bwd')
+        o.interp_images(img, img.flip(0).contiguous(), eps)
+        ga.check('interp_images')
+        o.scale_rows(img, eps, 2.0)
+        ga.check('scale_rows')
+        o.lerp(img, img.flip(0).contiguous(), 0.3)
+        ga.check('lerp')
+        o.axpby(img, 0.5, img, 0.25)
+        ga.check('axpby')
