@@ -139,8 +139,9 @@ class _Side:
 
 
 def _on_side(fn, *tensors):
-    """Run fn() -- a parameter-gradient kernel that only accumulates (atomics) into a gradient tensor -- on a side
-    stream, after everything already queued on the current stream; `tensors` are its inputs (kept alive)."""
+    """Run fn() -- a parameter-gradient kernel whose only output is its own slice of a gradient buffer, which nothing
+    reads before side_join() -- on a side stream, after everything already queued on the current stream; `tensors`
+    are its inputs (kept alive)."""
     if not _Side.enabled:
         fn()
         return
