@@ -314,7 +314,8 @@ class TrainStep:
     def _run_multi_critic(self, images, draws, dev):
         """n_critic > 1 (train.py:356-366): every critic step takes the same images and fresh draws (z, z, eps);
         the statistics are those of the last critic step, as in the reference.  draws: None, or a list of n_critic
-        (z1, z2, eps) tuples followed by one z3."""
+        (z1, z2, eps) tuples followed by one z3 (n_critic = 0: [z3], or [(z1, z2, eps), z3] for the monitoring-only
+        evaluation of the critic losses)."""
         B, R = images.shape[0], images.shape[-1]
         buf = self._buffers(B, R, dev)
         self._bind(self.D, 3)
@@ -332,12 +333,19 @@ class TrainStep:
             self.opt_d.launch()
             self._last_critic_out = (buf.out.out3, buf.out.pen)
         if self.n_critic == 0:
-            # adapt_critic can ask for no critic step (train.py:336-340 with N_min = 0): the reference then reports
-            # the critic statistics of the last iteration that had one (its Python variables are simply not updated)
-            if getattr(self, '_last_critic_out', None) is None:
-                raise RuntimeError('n_critic = 0 before any critic step has run: no critic statistics to report')
-            buf.out.out3, buf.out.pen = (t.clone() for t in self._last_critic_out)
-        z3 = sample_latent_vec((B, self.G.latent_dim)) if draws is None else draws[self.n_critic]
+            # adapt_critic can ask for no critic step (train.py:336-340 with N_min = 0).  The reference then still
+            # EVALUATES the critic losses for its statistics (train.py:369-374) -- consuming the draws z, z, eps --
+            # without backward or optimiser step.  Here the critic segment runs as usual (its gradients stay in the
+            # critic's buffers and are never applied: no all-reduce, no Adam launch, no step-count advance).
+            if draws is None or len(draws) < 2:
+                z1 = sample_latent_vec((B, self.G.latent_dim))
+                z2 = sample_latent_vec((B, self.G.latent_dim))
+                eps = torch.rand((B, 1, 1, 1))
+            else:
+                z1, z2, eps = draws[0]            # optional: [(z1, z2, eps), z3]
+            self._load(buf, images, z1, z2, eps, z1)
+            self._seg_d(buf)
+        z3 = sample_latent_vec((B, self.G.latent_dim)) if draws is None else draws[-1]
         buf.z3.copy_(z3.to(dev) if not z3.is_cuda else z3)
         self.opt_g.advance()
         self._seg_g(buf, adam_d=False)
