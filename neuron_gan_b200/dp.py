@@ -40,12 +40,17 @@ def shard_rows(t, rank=None, world=None):
     return t[rank * per:(rank + 1) * per]
 
 
-def global_draws(sample_latent_vec, global_batch, latent_dim, rank=None, world=None):
+def global_draws(sample_latent_vec, global_batch, latent_dim, rank=None, world=None, penalty=True):
     """Draw (z, z, eps, z) for the GLOBAL batch on the CPU generator in the reference's order
-    (loss_functions.py:25, 166, 170, 63) and return this rank's rows."""
+    (loss_functions.py:25, 166, 170, 63) and return this rank's rows.  penalty=False (grad_pen_lambda == 0): the
+    reference's D_grad_pen_loss then draws nothing (loss_functions.py:159), so neither does this -- its z and eps
+    come back as zeros."""
     z1 = sample_latent_vec((global_batch, latent_dim))
-    z2 = sample_latent_vec((global_batch, latent_dim))
-    eps = torch.rand((global_batch, 1, 1, 1))
+    if penalty:
+        z2 = sample_latent_vec((global_batch, latent_dim))
+        eps = torch.rand((global_batch, 1, 1, 1))
+    else:
+        z2, eps = torch.zeros((global_batch, latent_dim)), torch.zeros((global_batch, 1, 1, 1))
     z3 = sample_latent_vec((global_batch, latent_dim))
     return tuple(shard_rows(t, rank, world).contiguous() for t in (z1, z2, eps, z3))
 

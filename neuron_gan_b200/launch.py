@@ -98,10 +98,10 @@ def _global_draws(step, global_batch, rank, world):
     from .utils import sample_latent_vec
     L = step.G.latent_dim
     if step.n_critic == 1:
-        return dp.global_draws(sample_latent_vec, global_batch, L, rank, world)
+        return dp.global_draws(sample_latent_vec, global_batch, L, rank, world, penalty=step.lam > 0)
     rows = lambda t: dp.shard_rows(t, rank, world).contiguous()
-    out = [(rows(sample_latent_vec((global_batch, L))), rows(sample_latent_vec((global_batch, L))),
-            rows(torch.rand((global_batch, 1, 1, 1)))) for _ in range(step.n_critic)]
+    # n_critic = 0 (adapt_critic): one monitoring-only evaluation of the critic losses, with its draws (train.py:369-374)
+    out = [tuple(rows(t) for t in step.draw_critic_host(global_batch)) for _ in range(max(step.n_critic, 1))]
     return out + [rows(sample_latent_vec((global_batch, L)))]
 
 

@@ -157,12 +157,26 @@ class TrainStep:
         count consumes the single-process random stream bit-exactly (dp.global_draws)."""
         if self.dp and dist.is_initialized() and self.global_draws:
             from .dp import global_draws
-            return global_draws(sample_latent_vec, batch * dist.get_world_size(), self.G.latent_dim)
+            return global_draws(sample_latent_vec, batch * dist.get_world_size(), self.G.latent_dim,
+                                penalty=self.lam > 0)
         z1 = sample_latent_vec((batch, self.G.latent_dim))
-        z2 = sample_latent_vec((batch, self.G.latent_dim))
-        eps = torch.rand((batch, 1, 1, 1))          # CPU generator (SURVEY.md section 8d) for reproducibility
+        if self.lam > 0:
+            z2 = sample_latent_vec((batch, self.G.latent_dim))
+            eps = torch.rand((batch, 1, 1, 1))      # CPU generator (SURVEY.md section 8d) for reproducibility
+        else:
+            # grad_pen_lambda == 0: the reference's D_grad_pen_loss returns 0 WITHOUT drawing (loss_functions.py:159);
+            # the penalty chain still runs here with coefficient 0 (zero loss, zero gradients) on placeholder inputs
+            z2, eps = torch.zeros((batch, self.G.latent_dim)), torch.zeros((batch, 1, 1, 1))
         z3 = sample_latent_vec((batch, self.G.latent_dim))
         return z1, z2, eps, z3
+
+    def draw_critic_host(self, batch):
+        """(z, z, eps) of one critic round (loss_functions.py:25, 166, 170) for `batch` rows; no penalty draws when
+        grad_pen_lambda == 0 (loss_functions.py:159)."""
+        z1 = sample_latent_vec((batch, self.G.latent_dim))
+        if self.lam > 0:
+            return z1, sample_latent_vec((batch, self.G.latent_dim)), torch.rand((batch, 1, 1, 1))
+        return z1, torch.zeros((batch, self.G.latent_dim)), torch.zeros((batch, 1, 1, 1))
 
     def draw(self, batch, device):
         """The four draws of one iteration as device tensors (for callers that keep draws resident)."""
@@ -321,12 +335,7 @@ class TrainStep:
         self._bind(self.D, 3)
         self._bind(self.G)
         for j in range(self.n_critic):
-            if draws is None:
-                z1 = sample_latent_vec((B, self.G.latent_dim))
-                z2 = sample_latent_vec((B, self.G.latent_dim))
-                eps = torch.rand((B, 1, 1, 1))
-            else:
-                z1, z2, eps = draws[j]
+            z1, z2, eps = self.draw_critic_host(B) if draws is None else draws[j]
             self._load(buf, images, z1, z2, eps, z1)          # (z3 slot: overwritten below)
             self.opt_d.advance()
             self._allreduce(self._seg_d(buf))
@@ -337,12 +346,7 @@ class TrainStep:
             # EVALUATES the critic losses for its statistics (train.py:369-374) -- consuming the draws z, z, eps --
             # without backward or optimiser step.  Here the critic segment runs as usual (its gradients stay in the
             # critic's buffers and are never applied: no all-reduce, no Adam launch, no step-count advance).
-            if draws is None or len(draws) < 2:
-                z1 = sample_latent_vec((B, self.G.latent_dim))
-                z2 = sample_latent_vec((B, self.G.latent_dim))
-                eps = torch.rand((B, 1, 1, 1))
-            else:
-                z1, z2, eps = draws[0]            # optional: [(z1, z2, eps), z3]
+            z1, z2, eps = self.draw_critic_host(B) if draws is None or len(draws) < 2 else draws[0]
             self._load(buf, images, z1, z2, eps, z1)
             self._seg_d(buf)
         z3 = sample_latent_vec((B, self.G.latent_dim)) if draws is None else draws[-1]

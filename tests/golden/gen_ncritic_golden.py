@@ -19,7 +19,8 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import ref_harness as rh                      # noqa: E402
 from oracle import pggan_oracle as O          # noqa: E402
 
-CASES = [(32, 0.5, 4, 2), (32, 0.5, 4, 0), (64, 1.0, 3, 3)]     # (res, alpha, batch, N_D_steps)
+CASES = [(32, 0.5, 4, 2, 10), (32, 0.5, 4, 0, 10), (64, 1.0, 3, 3, 10),     # (res, alpha, batch, N_D_steps, Lambda)
+         (32, 0.5, 4, 1, 0)]       # grad_pen_lambda = 0: D_grad_pen_loss returns 0 without drawing (loss_functions.py:159)
 
 
 def summarize(t):
@@ -28,7 +29,7 @@ def summarize(t):
             'head': t.detach().flatten()[:8].clone()}
 
 
-def run_case(res, alpha, batch, n_d):
+def run_case(res, alpha, batch, n_d, lam):
     _, ref_losses, _ = rh.load()
     arch = O.Arch()
     n = O.n_layers_for(res, arch)
@@ -38,7 +39,7 @@ def run_case(res, alpha, batch, n_d):
     opt_d = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.5, 0.999))
     opt_g = torch.optim.Adam(G.parameters(), lr=1e-4, betas=(0.5, 0.999))
     d_loss_f = ref_losses.D_W_loss(G, D, drift_epsilon=1e-3)
-    gp_f = ref_losses.D_grad_pen_loss(G, D, Lambda=10)
+    gp_f = ref_losses.D_grad_pen_loss(G, D, Lambda=lam)
     g_loss_f = ref_losses.G_W_loss(G, D)
     torch.manual_seed(123)                      # the draws of the iteration (the test re-seeds the same way)
     for _ in range(n_d):                        # train.py:356-366
@@ -57,9 +58,11 @@ def run_case(res, alpha, batch, n_d):
     g_loss.backward()
     opt_g.step()
     gs, ds = G.state_dict(), D.state_dict()
-    return {'res': res, 'alpha': alpha, 'batch': batch, 'n_critic': n_d, 'draw_seed': 123, 'image_seed': 61,
+    next_draw = torch.rand(1).item()            # where the CPU stream stands after the iteration
+    return {'res': res, 'alpha': alpha, 'batch': batch, 'n_critic': n_d, 'lam': lam, 'draw_seed': 123, 'image_seed': 61,
+            'next_draw': next_draw,
             'stats': {'score_real': sr.item(), 'score_fake': sf.item(), 'D_loss': d_loss.item(),
-                      'G_loss': g_loss.item(), 'D_grad_pen': pen.item()},
+                      'G_loss': g_loss.item(), 'D_grad_pen': float(pen)},
             'g_after': {k: summarize(gs[v]) for k, v in gkm.items()},
             'd_after': {k: summarize(ds[v]) for k, v in dkm.items()}}
 
@@ -67,9 +70,9 @@ def run_case(res, alpha, batch, n_d):
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     out = {'torch': torch.__version__, 'cases': {}}
-    for res, alpha, batch, n_d in CASES:
-        key = f'r{res}_a{alpha}_b{batch}_n{n_d}'
-        out['cases'][key] = run_case(res, alpha, batch, n_d)
+    for res, alpha, batch, n_d, lam in CASES:
+        key = f'r{res}_a{alpha}_b{batch}_n{n_d}' + ('' if lam == 10 else f'_lam{lam}')
+        out['cases'][key] = run_case(res, alpha, batch, n_d, lam)
         print(key, out['cases'][key]['stats'])
     path = os.path.join(HERE, 'ncritic_golden.pt')
     torch.save(out, path)

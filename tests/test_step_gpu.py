@@ -537,31 +537,28 @@ def test_captured_graph_follows_alpha():
     assert (s_stale[tight] - s_replay[tight]).abs().max().item() > 1e-3, (s_stale, s_replay)
 
 
-@pytest.mark.parametrize('key', ['r32_a0.5_b4_n2', 'r32_a0.5_b4_n0', 'r64_a1.0_b3_n3'])
+@pytest.mark.parametrize('key', ['r32_a0.5_b4_n2', 'r32_a0.5_b4_n0', 'r64_a1.0_b3_n3', 'r32_a0.5_b4_n1_lam0'])
 def test_critic_loop_variants_match_reference(key):
-    """N_D_steps = 2 / 3 (train.py:356-366) and N_D_steps = 0 (adapt_critic, train.py:336-340: the critic losses are
-    then only EVALUATED for the statistics, train.py:369-374, consuming their draws) against the unmodified reference
-    run on CPU from the same seeds (tests/golden/gen_ncritic_golden.py): statistics of the last critic round, and
-    every parameter after the iteration within (number of Adam steps) x 2 lr of the reference's."""
+    """N_D_steps = 2 / 3 (train.py:356-366), N_D_steps = 0 (adapt_critic, train.py:336-340: the critic losses are then
+    only EVALUATED for the statistics, train.py:369-374, consuming their draws) and grad_pen_lambda = 0 (the penalty
+    module returns 0 without drawing, loss_functions.py:159) against the unmodified reference run on CPU from the same
+    seeds (tests/golden/gen_ncritic_golden.py): statistics of the last critic round, the position of the CPU random
+    stream after the iteration, and every parameter within (number of Adam steps) x 2 lr of the reference's."""
     import os
     from neuron_gan_b200.train_step import TrainStep
     ref = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'ncritic_golden.pt'), weights_only=False)['cases'][key]
-    res, alpha, batch, n_d = ref['res'], ref['alpha'], ref['batch'], ref['n_critic']
+    res, alpha, batch, n_d, lam = ref['res'], ref['alpha'], ref['batch'], ref['n_critic'], ref['lam']
     G, D = nets(res, alpha)
     d_init = {k: v.clone() for k, v in D.state_dict().items()}
-    step = TrainStep(G, D, n_critic=n_d)
+    step = TrainStep(G, D, grad_pen_lambda=lam, n_critic=n_d)
     x = O.synthetic_images(batch, res, seed=ref['image_seed']).to(DEV)
     torch.manual_seed(ref['draw_seed'])
     stats = TrainStep.stats_dict(step(x).cpu())
+    assert torch.rand(1).item() == ref['next_draw']       # the iteration consumed exactly the reference's draws
     for k, v in ref['stats'].items():
         assert abs(stats[k] - v) <= 1e-2 * max(1.0, abs(v)), (k, stats[k], v)
-    # the iteration consumed exactly the reference's draws: the next number of the CPU stream is the same
-    nxt = torch.rand(1).item()
-    torch.manual_seed(ref['draw_seed'])
-    for _ in range(max(n_d, 1)):
-        O.sample_latent((batch, 512)), O.sample_latent((batch, 512)), torch.rand((batch, 1, 1, 1))
-    O.sample_latent((batch, 512))
-    assert nxt == torch.rand(1).item()
+    if lam == 0:
+        assert stats['D_grad_pen'] == 0.0
     n = O.n_layers_for(res, ARCH)
     for net, km, refp, steps in ((G, O.g_key_map(n, alpha < 1, ARCH), ref['g_after'], 1),
                                  (D, O.d_key_map(n, alpha < 1, ARCH), ref['d_after'], n_d)):
