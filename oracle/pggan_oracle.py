@@ -487,19 +487,44 @@ class Trainer:
         gs = torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)
         return dict(zip(names, gs))
 
-    def iteration(self, x, draws=None):
-        """Returns dict(score_real, score_fake, D_loss, G_loss, D_grad_pen) as Python floats."""
+    def draw_critic(self, batch, generator=None):
+        """(z, z, eps) of one critic round; with lam == 0 D_grad_pen_loss draws nothing (loss_functions.py:159)."""
+        z1 = sample_latent((batch, self.arch.latent_dim), generator)
+        if self.lam > 0:
+            return z1, sample_latent((batch, self.arch.latent_dim), generator), torch.rand((batch, 1, 1, 1), generator=generator)
+        return z1, None, None
+
+    def iteration(self, x, draws=None, n_critic=1):
+        """Returns dict(score_real, score_fake, D_loss, G_loss, D_grad_pen) as Python floats.
+        n_critic = k > 1: k critic rounds on the same images with fresh draws, statistics of the last round
+        (train.py:356-366); n_critic = 0: the critic losses are evaluated once for the statistics, no update
+        (train.py:369-374).  `draws` = (z1, z2, eps, z3) is only accepted for the plain n_critic = 1 iteration."""
         dt = next(iter(self.gp.values())).dtype
         x = x.to(dt)
-        z1, z2, eps, z3 = [t.to(dt) for t in (draws or self.draw(x.shape[0]))]
-        d_total, sr, sf, pen = self.d_losses(x, z1, z2, eps)
-        names = active_d_names(self.n_layers, self.alpha, self.arch)
-        self.last_d_grads = self._grads(d_total, self.dp, names)
-        self.opt_d.step(self.last_d_grads)                                   # train.py:365-366
+        a = (self.n_layers, self.alpha, self.arch)
+        z3 = None
+        for j in range(max(n_critic, 1)):
+            if draws is not None:
+                assert n_critic == 1
+                z1, z2, eps, z3 = [t.to(dt) for t in draws]
+            else:
+                z1, z2, eps = [t if t is None else t.to(dt) for t in self.draw_critic(x.shape[0])]
+            d_total, sr, sf = d_w_loss(self.gp, self.dp, x, z1, *a, drift=self.drift)
+            if self.lam > 0:
+                pen = grad_penalty(self.gp, self.dp, x, z2, eps, *a, lam=self.lam)
+                d_total = d_total + pen
+            else:
+                pen = torch.zeros(())                                            # loss_functions.py:177-178
+            if n_critic > 0:
+                names = active_d_names(self.n_layers, self.alpha, self.arch)
+                self.last_d_grads = self._grads(d_total, self.dp, names)
+                self.opt_d.step(self.last_d_grads)                               # train.py:365-366
+        if z3 is None:
+            z3 = sample_latent((x.shape[0], self.arch.latent_dim)).to(dt)
         g_loss = g_w_loss(self.gp, self.dp, z3, self.n_layers, self.alpha, self.arch)
         names = active_g_names(self.n_layers, self.alpha, self.arch)
         self.last_g_grads = self._grads(g_loss, self.gp, names)
-        self.opt_g.step(self.last_g_grads)                                   # train.py:384-385
+        self.opt_g.step(self.last_g_grads)                                       # train.py:384-385
         return {'score_real': sr.item(), 'score_fake': sf.item(), 'D_loss': d_total.item(),
                 'G_loss': g_loss.item(), 'D_grad_pen': pen.item()}
 

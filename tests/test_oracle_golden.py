@@ -129,3 +129,23 @@ def test_adam_matches_torch_optim():
         adam.step(grads)
     for p, k in zip(theirs, mine):
         assert torch.allclose(p.data, mine[k], rtol=1e-6, atol=1e-7), k
+
+
+@pytest.mark.parametrize('key', ['r32_a0.5_b4_n2', 'r32_a0.5_b4_n0', 'r64_a1.0_b3_n3', 'r32_a0.5_b4_n1_lam0'])
+def test_critic_loop_variants(key):
+    """The oracle's n_critic = 2 / 3 / 0 and grad_pen_lambda = 0 iterations against the unmodified reference
+    (tests/golden/gen_ncritic_golden.py): statistics, stream position, parameters after the iteration."""
+    import os
+    ref = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'ncritic_golden.pt'), weights_only=False)['cases'][key]
+    tr = O.Trainer(ARCH, seed=1, res=ref['res'], alpha=ref['alpha'], lam=ref['lam'])
+    x = O.synthetic_images(ref['batch'], ref['res'], seed=ref['image_seed'])
+    torch.manual_seed(ref['draw_seed'])
+    stats = tr.iteration(x, n_critic=ref['n_critic'])
+    assert torch.rand(1).item() == ref['next_draw']
+    for k, v in ref['stats'].items():
+        assert close(stats[k], v, 2e-5, 2e-7), (k, stats[k], v)
+    for params, refp in ((tr.gp, ref['g_after']), (tr.dp, ref['d_after'])):
+        for k, s in refp.items():
+            p = params[k].detach()
+            assert abs(p.double().sum().item() - s['sum']) <= 2.5e-4 * max(1, ref['n_critic']) * max(1, p.numel() ** 0.5), k
+            assert torch.allclose(p.flatten()[:8], s['head'], rtol=0, atol=2.1e-4 * max(1, ref['n_critic'])), k
