@@ -71,3 +71,24 @@ def test_shard_rows_rejects_ragged_batches():
     with pytest.raises(ValueError):
         dp.shard_rows(t, 0, 2)
     assert torch.equal(dp.shard_rows(torch.arange(8).reshape(4, 2), 1, 2), torch.tensor([[4, 5], [6, 7]]))
+
+
+@pytest.mark.parametrize('penalty', [True, False])
+def test_global_draws_follow_the_reference_stream(penalty):
+    """dp.global_draws consumes the CPU stream exactly as one process running the reference does: z, (z, eps), z --
+    the middle pair only when the gradient penalty is on (loss_functions.py:159) -- and hands each rank its rows."""
+    torch.manual_seed(5)
+    shards = [dp.global_draws(sample_latent_vec, 8, 512, rank=0, world=2, penalty=penalty)]
+    nxt = torch.rand(1).item()
+    torch.manual_seed(5)
+    shards.append(dp.global_draws(sample_latent_vec, 8, 512, rank=1, world=2, penalty=penalty))
+    torch.manual_seed(5)
+    z1 = sample_latent_vec((8, 512))
+    if penalty:
+        z2, eps = sample_latent_vec((8, 512)), torch.rand((8, 1, 1, 1))
+    else:
+        z2, eps = torch.zeros(8, 512), torch.zeros(8, 1, 1, 1)
+    z3 = sample_latent_vec((8, 512))
+    assert torch.rand(1).item() == nxt
+    for i, full in enumerate((z1, z2, eps, z3)):
+        assert torch.equal(torch.cat([shards[0][i], shards[1][i]]), full)
