@@ -113,6 +113,20 @@ def _sum_over_ranks(values):
     return values
 
 
+def restored_series(checkpoint, epoch_init, names):
+    """Per-epoch statistics so far: empty for a fresh run; after a resume the four series the reference's checkpoint
+    holds (train.py:277-280: Score_real_series = checkpoint.Loss_real ...), so that adapt_critic (train.py:336-338)
+    sees the epochs before the restart.  (The reference's arrays are pre-allocated to N_epochs, which makes its
+    `len(Score_real_series) > 100` test vacuous; only completed epochs count here.)"""
+    series = {k: [] for k in names}
+    if checkpoint is not None and epoch_init > 1:
+        done = epoch_init - 1
+        for key, attr in (('score_real', 'Loss_real'), ('score_fake', 'Loss_fake'), ('G_loss', 'Loss_G'),
+                          ('D_loss', 'Loss_D')):
+            series[key] = [float(v) for v in getattr(checkpoint, attr)[:done]]
+    return series
+
+
 def pggan_train(cfg: TrainConfig, images: NeuronImages, Generator_net, Discriminator_net, checkpoint=None,
                 samples_dir=None, rank=0, world=1, log=print, epoch_init=1):
     """Runs epochs [epoch_init, N_epochs] (or N_epochs_session of them).  Returns the per-epoch statistics."""
@@ -131,7 +145,7 @@ def pggan_train(cfg: TrainConfig, images: NeuronImages, Generator_net, Discrimin
     schedule.apply(step.opt_d, epoch_init - 1)
     schedule.apply(step.opt_g, epoch_init - 1)
     names = ('D_loss', 'score_real', 'score_fake', 'G_loss', 'D_grad_pen')
-    series = {k: [] for k in names}
+    series = restored_series(checkpoint, epoch_init, names)
     history = []
     start = time.time()
     sim_lambda = cfg.sim_loss_lambda                                                                # train.py:300

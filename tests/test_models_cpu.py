@@ -178,6 +178,13 @@ def test_launcher_resume_restores_the_last_training_state(tmp_path):
         sa, sb = a.state_dict(), b.state_dict()
         assert list(sa.keys()) == list(sb.keys())
         assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    # the epoch loop continues the statistic series of the checkpoint (adapt_critic looks at the epochs so far)
+    from neuron_gan_b200.launch import restored_series
+    names = ('D_loss', 'score_real', 'score_fake', 'G_loss', 'D_grad_pen')
+    series = restored_series(ckpt2, first2, names)
+    assert series['score_real'] == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0] and len(series['score_fake']) == 6
+    assert series['D_grad_pen'] == [] and restored_series(None, 1, names) == {k: [] for k in names}
+    assert restored_series(ckpt2, 1, names) == {k: [] for k in names}
     _, first3 = open_checkpoint(cfg, *fresh(3), str(tmp_path), resume=False, device=torch.device('cpu'))
     assert first3 == 1
     assert open_checkpoint(cfg, G, D, None, True, torch.device('cpu')) == (None, 1)
